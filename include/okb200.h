@@ -1,0 +1,207 @@
+/*
+ * okb200.h — C ABI of libokb200.so, the B200-native (sm_100a) replacement for the
+ * knowledge-graph-embedding hot path of luigiba/OpenKEonSpark.
+ *
+ * Two layers are exported.
+ *
+ *  (1) Reference-compatible layer: the same symbols, argument order, widths (INT = int64,
+ *      REAL = float) and process-global state as the reference's release/Base.so, so the
+ *      reference's own ctypes binding (/root/reference/Config.py:30-51) can load this library
+ *      instead of Base.so.  Pointers are HOST buffers; each call runs the CUDA kernels on the
+ *      current device and copies the result back.
+ *
+ *  (2) Native layer (okb_*): an explicit context instead of globals, DEVICE pointers and a
+ *      cudaStream_t (passed as void*), int status codes (0 = ok; okb_last_error() explains).
+ *      It also carries what the reference delegates to TensorFlow: the model's train step
+ *      (loss_def + optimizer) and scoring (predict_def).
+ *
+ * No torch / C++ types cross this boundary.  The library never falls back to the CPU for the
+ * hot path: without a CUDA device every compute entry point returns OKB_ERR_CUDA.
+ */
+#ifndef OKB200_H
+#define OKB200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int64_t INT;
+typedef float REAL;
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Reference-compatible layer (process-global default context)
+ * ---------------------------------------------------------------------------------------- */
+void setInPath(char *path);                 /* base/Setting.h:12-19 */
+void setOutPath(char *path);                /* base/Setting.h:21-28 */
+void setWorkThreads(INT threads);           /* base/Setting.h:36-39 */
+INT getWorkThreads(void);                   /* base/Setting.h:41-44 */
+void setBern(INT con);                      /* base/Setting.h:110-113 */
+INT getEntityTotal(void);                   /* base/Setting.h:63-66 */
+INT getRelationTotal(void);                 /* base/Setting.h:68-71 */
+INT getTripleTotal(void);                   /* base/Setting.h:73-76 */
+INT getTrainTotal(void);                    /* base/Setting.h:78-81  (deduplicated) */
+INT getTrainTotal_(void);                   /* base/Setting.h:84-87  (file rows) */
+INT getBatchTotal(void);                    /* base/Setting.h:90-93 */
+INT getTestTotal(void);                     /* base/Setting.h:95-98 */
+INT getValidTotal(void);                    /* base/Setting.h:100-103 */
+void randReset(void);                       /* base/Random.h:8-13   (seeds from libc rand()) */
+void importTrainFiles(void);                /* base/Reader.h:26-179 */
+void importTestFiles(void);                 /* base/Reader.h:185-292 */
+void importTypeFiles(void);                 /* base/Reader.h:301-365 */
+void importOntologyFiles(void);             /* base/Reader.h:375-449 */
+/* base/Base.cpp:149-172.  batch_h/t/r: INT[batchSize*(1+negRate+negRelRate)], plane-major. */
+void sampling(INT *batch_h, INT *batch_t, INT *batch_r, REAL *batch_y, INT batchSize, INT negRate,
+              INT negRelRate);
+void getHeadBatch(INT index, INT *ph, INT *pt, INT *pr);   /* base/Test.h:10-17 */
+void getTailBatch(INT index, INT *ph, INT *pt, INT *pr);   /* base/Test.h:19-26 */
+/* base/Test.h:30-136 / 140-249.  con = REAL[entityTotal] scores.  Returns INT[8]; unlike the
+ * reference (which leaks a new INT[8] per call) the buffer is owned by the library and reused. */
+INT *testHead(INT index, REAL *con);
+INT *testTail(INT index, REAL *con);
+void getNegTest(void);                      /* base/Test.h:257-264 */
+void getNegValid(void);                     /* base/Test.h:267-274 */
+void getTestBatch(INT *ph, INT *pt, INT *pr, INT *nh, INT *nt, INT *nr);    /* base/Test.h:276-287 */
+void getValidBatch(INT *ph, INT *pt, INT *pr, INT *nh, INT *nt, INT *nr);   /* base/Test.h:289-300 */
+void getBestThreshold(REAL *relThresh, REAL *score_pos, REAL *score_neg);   /* base/Test.h:303-341 */
+void test_triple_classification(REAL *relThresh, REAL *score_pos, REAL *score_neg,
+                                REAL *acc_addr);                            /* base/Test.h:345-387 */
+INT get_n_interval(INT r, REAL *score_pos, REAL *score_neg);                /* base/Test.h:390-407 */
+INT *get_TPFP(INT r, REAL *score_pos, REAL *score_neg, REAL *score_pos_test,
+              REAL *score_neg_test);                                        /* base/Test.h:410-444 */
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Native layer
+ * ---------------------------------------------------------------------------------------- */
+typedef struct okb_ctx okb_ctx;
+
+enum { OKB_OK = 0, OKB_ERR_ARG = 1, OKB_ERR_IO = 2, OKB_ERR_CUDA = 3, OKB_ERR_STATE = 4 };
+enum { OKB_TRANSE = 0, OKB_TRANSH = 1, OKB_TRANSR = 2, OKB_TRANSD = 3 };
+enum { OKB_SGD = 0, OKB_ADAM = 1 };
+
+int okb_version(void);
+okb_ctx *okb_default_ctx(void);                    /* the context behind layer (1) */
+int okb_create(okb_ctx **out);
+int okb_destroy(okb_ctx *c);
+const char *okb_last_error(okb_ctx *c);
+int okb_set_device(okb_ctx *c, int device);       /* cudaSetDevice for this thread; one process per GPU */
+
+/* ---- dataset: replaces Setting.h / Reader.h.  Host-side parse + index build (C++), then the
+ *      index is uploaded once and stays resident in HBM as int32 SoA. */
+int okb_set_in_path(okb_ctx *c, const char *path);
+int okb_set_bern(okb_ctx *c, INT flag);
+int okb_set_work_threads(okb_ctx *c, INT w);
+int okb_import_train_files(okb_ctx *c);
+int okb_import_test_files(okb_ctx *c);
+int okb_import_type_files(okb_ctx *c);
+int okb_import_ontology_files(okb_ctx *c);
+/* Same as the file importers but from host arrays (rows in file order; columns h, t, r).
+ * Used for large synthetic graphs where writing and re-parsing text is pointless. */
+int okb_import_train_arrays(okb_ctx *c, INT n_ent, INT n_rel, const INT *h, const INT *t, const INT *r,
+                            INT n, INT new_batch_total);
+int okb_import_test_arrays(okb_ctx *c, const INT *th, const INT *tt, const INT *tr, INT n_test,
+                           const INT *vh, const INT *vt, const INT *vr, INT n_valid);
+/* what: 0 entities, 1 relations, 2 train rows (file), 3 train dedup, 4 test, 5 valid, 6 all triples,
+ *       7 new-batch total */
+INT okb_total(okb_ctx *c, int what);
+
+/* ---- RNG streams (Random.h).  okb_rand_reset draws the seeds from libc rand() like the
+ *      reference; okb_set_streams / okb_get_streams inject / read the W 64-bit LCG states. */
+int okb_rand_reset(okb_ctx *c);
+int okb_set_streams(okb_ctx *c, const uint64_t *state, INT w);
+int okb_get_streams(okb_ctx *c, uint64_t *state_out, INT w);
+
+/* ---- sampler (Base.cpp:74-172, Corrupt.h:7-101) on the GPU.
+ * Fills the context's device-resident batch (int32, plane-major) for `steps` consecutive
+ * sampling() calls in ONE launch (LCG jump-ahead makes every slot independent) and advances
+ * the stream states exactly as `steps` reference calls would.
+ * stream_lo/stream_hi: only slots owned by streams [stream_lo, stream_hi) are produced
+ * (data-parallel ranks); pass 0, W for all. */
+int okb_sample(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, INT stream_lo,
+               INT stream_hi, void *cuda_stream);
+/* Device pointers to step `step` of the last okb_sample: int32[batch_size*(1+neg_ent+neg_rel)]. */
+int okb_batch_ptrs(okb_ctx *c, INT step, const int32_t **h, const int32_t **t, const int32_t **r);
+/* Copy step `step` to host in the reference's types (int64 ids, float labels +1/-1). */
+int okb_batch_to_host(okb_ctx *c, INT step, INT *h, INT *t, INT *r, REAL *y, void *cuda_stream);
+/* Replace the device batch of step 0 with caller-provided host ids (Config.train_step path). */
+int okb_batch_from_host(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, const INT *h, const INT *t,
+                        const INT *r, void *cuda_stream);
+
+/* ---- model parameters: device pointers owned by the caller (row-major fp32). */
+typedef struct {
+    int32_t model;        /* OKB_TRANSE .. OKB_TRANSD */
+    int32_t ent_dim;      /* De (hidden_size / ent_size) */
+    int32_t rel_dim;      /* Dr (== De except TransR) */
+    int32_t optimizer;    /* OKB_SGD / OKB_ADAM */
+    float *ent;           /* ent_embeddings  [E, De] */
+    float *rel;           /* rel_embeddings  [R, Dr] */
+    float *ent_aux;       /* TransD ent_transfer [E, De]; else NULL */
+    float *rel_aux;       /* TransH normal_vectors [R, D]; TransD rel_transfer [R, D];
+                             TransR transfer_matrix [R, De*Dr]; TransE NULL */
+    /* Adam slots, same shapes as the four tables above (NULL for SGD) */
+    float *m_ent, *v_ent, *m_rel, *v_rel, *m_ent_aux, *v_ent_aux, *m_rel_aux, *v_rel_aux;
+} okb_model;
+
+typedef struct {
+    float margin;         /* Config.margin */
+    float lr;             /* SGD: alpha.  Adam: lr_t = alpha*sqrt(1-b2^t)/(1-b1^t), computed by the host */
+    float beta1, beta2, eps;
+} okb_hyper;
+
+/* ---- train step = TransX.loss_def + optimizer.minimize (TransE.py:26-51 ...,
+ *      distribute_training.py:94-101) on step `step` of the sampled batch.
+ * Phases (all asynchronous on cuda_stream):
+ *   okb_plan   : gradient-row keys of the batch + stable radix sort (integer work only)
+ *   okb_grad   : fused gather / project / normalise / L1 / hinge / backward for positives
+ *                [b_lo, b_hi); writes one gradient row per distinct (positive-group, role)
+ *                into grad_ent / grad_rel and per-positive loss terms into loss_terms
+ *   okb_update : segmented sum of gradient rows in sorted (deterministic) order fused with the
+ *                SGD or TF1-Adam update
+ * okb_train_step runs the three phases on context-owned buffers and writes the mean loss to
+ * loss_out (device float).  The phases are public so that data-parallel ranks can all-gather
+ * grad_ent / grad_rel / loss_terms between okb_grad and okb_update. */
+int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT batch_size, INT neg_ent, INT neg_rel,
+                   INT *ent_rows, INT *ent_cols, INT *rel_rows, INT *rel_cols);
+int okb_plan(okb_ctx *c, INT step, void *cuda_stream);
+int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi,
+             float *grad_ent, float *grad_rel, float *loss_terms, void *cuda_stream);
+int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *grad_ent,
+               const float *grad_rel, const float *loss_terms, float *loss_out, void *cuda_stream);
+int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, float *loss_out,
+                   void *cuda_stream);
+
+/* ---- scoring = TransX.predict_def (TransE.py:53-58 ...).  h,t,r: device int64[n]; out: device
+ *      float[n] (TransE: mean over d; others: sum).  Canonical evaluation order, see DESIGN.md. */
+int okb_predict(okb_ctx *c, const okb_model *m, const int64_t *h, const int64_t *t, const int64_t *r, INT n,
+                float *out, void *cuda_stream);
+
+/* ---- link prediction = getHead/TailBatch + predict + testHead/testTail for test triples
+ *      [q_lo, q_hi) of the (r,h,t)-sorted test list, both sides if heads != 0, against candidate
+ *      entities [cand_lo, cand_hi).  counts: device int64[(q_hi-q_lo)*2*4] better-than counts
+ *      (raw, filter, raw_constrain, filter_constrain; side 0 = head, 1 = tail) ADDED to the
+ *      buffer; best: device uint64[(q_hi-q_lo)*2*4] packed (score_bits<<32 | id) minima, combined
+ *      with atomicMin.  Candidate-sharded ranks all-reduce counts (sum) and best (min). */
+int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT cand_lo, INT cand_hi,
+             int64_t *counts, uint64_t *best, void *cuda_stream);
+/* counts/best -> the reference's 8-int records (Test.h:99-134): out device int64[(q_hi-q_lo)*2*8] */
+int okb_rank_finalize(okb_ctx *c, INT q_lo, INT q_hi, const int64_t *counts, const uint64_t *best,
+                      int64_t *out, void *cuda_stream);
+/* Reference-shaped single query with caller-provided scores (device float[E]); out device int64[8]. */
+int okb_rank_scores(okb_ctx *c, INT index, int side, const float *scores, int64_t *out, void *cuda_stream);
+
+/* ---- triple classification (Test.h:253-387): host-side, tiny. */
+int okb_tc_batch(okb_ctx *c, int which /*0 test, 1 valid*/, INT *ph, INT *pt, INT *pr, INT *nh, INT *nt, INT *nr);
+int okb_best_threshold(okb_ctx *c, REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg);
+int okb_tc_eval(okb_ctx *c, const REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg,
+                INT *tp_tn_fp_fn, REAL *acc);
+int okb_test_list(okb_ctx *c, int which, INT *h, INT *t, INT *r);
+INT okb_n_interval(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg);            /* Test.h:390-407 */
+INT *okb_tpfp(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg, const REAL *score_pos_test,
+              const REAL *score_neg_test);                                                        /* Test.h:410-444 */
+
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+INT okb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

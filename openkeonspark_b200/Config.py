@@ -1,0 +1,581 @@
+"""Config — the user API of the reference (/root/reference/Config.py), re-backed by libokb200.so.
+
+Same class name, same setter names and positional arguments, same public attributes; the
+TensorFlow session and the ctypes calls into release/Base.so are replaced by PyTorch-owned device
+memory and the hand-written sm_100a kernels behind include/okb200.h.  What the reference only
+implements inside distribute_training.py is provided here as methods:
+
+    run() / train()            the train loop of distribute_training.py:267-283
+    test()                     triple classification (Config.py:491-516) AND, when
+                               set_test_link_prediction(True), the link-prediction evaluation of
+                               distribute_training.py:464-607 + the tables of main_spark.py:447-469
+
+There is no CPU fallback: a missing library or GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import time
+
+import numpy as np
+import torch
+
+from . import _native, metrics
+from ._native import MODEL_ID, OkbError, okb_hyper, okb_model
+
+_vp = ctypes.c_void_p
+_AUX_ENT = {"TransD": "ent_transfer"}
+_AUX_REL = {"TransH": "normal_vectors", "TransR": "transfer_matrix", "TransD": "rel_transfer"}
+
+
+def _addr(a):
+    return _vp(a.__array_interface__["data"][0])
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+class Config(object):
+    """Set the essential parameters, load the data, train and evaluate (reference Config.py:12)."""
+
+    def __init__(self, cpp_lib_path=None, init_new_entities=False, private_context=False):
+        self.init_new_entities = init_new_entities
+        # `lib` is the raw C library like the reference's (Config.py:30); its Base.so-compatible
+        # symbols act on the same process-global context this Config uses.
+        self.lib = _native.load(cpp_lib_path)
+        self.ctx = _native.Ctx(self.lib, default=not private_context)
+        self.in_path = None
+        self.out_path = None
+        self.bern = 0
+        self.hidden_size = 64
+        self.ent_size = self.hidden_size
+        self.rel_size = self.hidden_size
+        self.train_times = 0
+        self.margin = 1.0
+        self.nbatches = 0
+        self.negative_ent = 1
+        self.negative_rel = 0
+        self.workThreads = 8
+        self.alpha = 0.001
+        self.exportName = None
+        self.importName = None
+        self.opt_method = "SGD"
+        self.test_link_prediction = False
+        self.test_triple_classification = False
+        self.valid_triple_classification = False
+        # additions (not in the reference)
+        self.test_head = 0            # main_spark.py --test_head
+        self.log_every = 0            # read the loss back every n steps in run(); 0 = once per epoch
+        self.seed = 0
+        self.trainModel = None
+        self.model = None
+        self._step = 0
+        self._adam = None
+        self._world = None            # parallel.DataParallel when running under torch.distributed
+
+    # ------------------------------------------------------------------ init (Config.py:74-186)
+    def init_link_prediction(self):
+        self.ctx.call("okb_import_test_files")
+        self.ctx.call("okb_import_type_files")
+        self.ctx.call("okb_import_ontology_files")
+        self.testTotal = self.ctx.total(4)
+        self.validTotal = self.ctx.total(5)
+
+    def _alloc_tc(self, with_test):
+        n_t, n_v = self.ctx.total(4), self.ctx.total(5)
+        self.testTotal, self.validTotal = n_t, n_v
+        if with_test:
+            for nm in ("test_pos_h", "test_pos_t", "test_pos_r", "test_neg_h", "test_neg_t", "test_neg_r"):
+                setattr(self, nm, np.zeros(n_t, dtype=np.int64))
+                setattr(self, nm + "_addr", getattr(self, nm).__array_interface__["data"][0])
+        for nm in ("valid_pos_h", "valid_pos_t", "valid_pos_r", "valid_neg_h", "valid_neg_t", "valid_neg_r"):
+            setattr(self, nm, np.zeros(n_v, dtype=np.int64))
+            setattr(self, nm + "_addr", getattr(self, nm).__array_interface__["data"][0])
+        self.relThresh = np.zeros(self.ctx.total(1), dtype=np.float32)
+        self.relThresh_addr = self.relThresh.__array_interface__["data"][0]
+        self.acc = np.zeros(1, dtype=np.float32)
+        self.acc_addr = self.acc.__array_interface__["data"][0]
+
+    def init_triple_classification(self):
+        self.ctx.call("okb_import_test_files")
+        self.ctx.call("okb_import_type_files")
+        self._alloc_tc(True)
+
+    def init_valid_triple_classification(self):
+        self.ctx.call("okb_import_test_files")
+        self.ctx.call("okb_import_type_files")
+        self._alloc_tc(False)
+
+    def init(self):
+        """prepare for train and test (Config.py:153-186)"""
+        if self.init_new_entities:
+            return
+        if not torch.cuda.is_available():
+            raise OkbError("no CUDA device: openkeonspark_b200 has no CPU path")
+        self.trainModel = None
+        if self.in_path is not None:
+            self.ctx.call("okb_set_device", torch.cuda.current_device())
+            self.ctx.call("okb_set_in_path", self.in_path.encode())
+            self.ctx.call("okb_set_bern", self.bern)
+            self.ctx.call("okb_set_work_threads", self.workThreads)
+            self.ctx.call("okb_rand_reset")
+            self.ctx.call("okb_import_train_files")
+            self._after_train_import()
+        if self.test_link_prediction:
+            self.init_link_prediction()
+        if self.test_triple_classification:
+            self.init_triple_classification()
+        if self.valid_triple_classification:
+            self.init_valid_triple_classification()
+
+    def init_from_arrays(self, n_ent, n_rel, train, valid=None, test=None, new_batch=0):
+        """Same as init() but from [n,3] int64 arrays with columns h, t, r (large synthetic graphs)."""
+        if not torch.cuda.is_available():
+            raise OkbError("no CUDA device: openkeonspark_b200 has no CPU path")
+        cols = lambda a: [np.ascontiguousarray(a[:, k], dtype=np.int64) for k in range(3)]
+        h, t, r = cols(train)
+        self.ctx.call("okb_set_device", torch.cuda.current_device())
+        self.ctx.call("okb_set_bern", self.bern)
+        self.ctx.call("okb_set_work_threads", self.workThreads)
+        self.ctx.call("okb_rand_reset")
+        self.ctx.call("okb_import_train_arrays", n_ent, n_rel, _addr(h), _addr(t), _addr(r), h.size, new_batch)
+        self._after_train_import()
+        if test is not None:
+            a, b = cols(test), cols(valid)
+            self.ctx.call("okb_import_test_arrays", _addr(a[0]), _addr(a[1]), _addr(a[2]), a[0].size,
+                          _addr(b[0]), _addr(b[1]), _addr(b[2]), b[0].size)
+            self.testTotal, self.validTotal = self.ctx.total(4), self.ctx.total(5)
+
+    def _after_train_import(self):
+        self.relTotal = self.ctx.total(1)
+        self.entTotal = self.ctx.total(0)
+        self.trainTotal = self.ctx.total(2)
+        self.testTotal = self.ctx.total(4)
+        self.validTotal = self.ctx.total(5)
+        self.bt = self.ctx.total(7)
+        self.set_mini_batch()
+        self.batch_seq_size = self.batch_size * (1 + self.negative_ent + self.negative_rel)
+        self.batch_h = np.zeros(self.batch_seq_size, dtype=np.int64)
+        self.batch_t = np.zeros(self.batch_seq_size, dtype=np.int64)
+        self.batch_r = np.zeros(self.batch_seq_size, dtype=np.int64)
+        self.batch_y = np.zeros(self.batch_seq_size, dtype=np.float32)
+        self.batch_h_addr = self.batch_h.__array_interface__["data"][0]
+        self.batch_t_addr = self.batch_t.__array_interface__["data"][0]
+        self.batch_r_addr = self.batch_r.__array_interface__["data"][0]
+        self.batch_y_addr = self.batch_y.__array_interface__["data"][0]
+
+    def set_mini_batch(self):
+        """Config.py:189-210 (note the truncating division: tot % nbatches samples are dropped)."""
+        tot = self.bt if self.bt > 0 else self.trainTotal
+        if self.nbatches > 0:
+            self.batch_size = int(tot / self.nbatches)
+        else:
+            self.batch_size = tot
+            while self.batch_size > 9999:
+                self.batch_size = int(self.batch_size / 10)
+            self.nbatches = int(tot / self.batch_size)
+        print("Batch size is {}".format(self.batch_size))
+        print("Number of batches: {}".format(self.nbatches))
+
+    # ------------------------------------------------------------------ setters (Config.py:213-340)
+    def get_ent_total(self):
+        return self.entTotal
+
+    def get_rel_total(self):
+        return self.relTotal
+
+    def set_opt_method(self, method):
+        self.opt_method = method
+
+    def set_test_link_prediction(self, flag):
+        self.test_link_prediction = flag
+
+    def set_test_triple_classification(self, flag):
+        self.test_triple_classification = flag
+
+    def set_valid_triple_classification(self, flag):
+        self.valid_triple_classification = flag
+
+    def set_alpha(self, alpha):
+        self.alpha = alpha
+
+    def set_in_path(self, path):
+        self.in_path = path
+
+    def set_out_files(self, path):
+        self.out_path = path
+
+    def set_bern(self, bern):
+        self.bern = bern
+
+    def set_dimension(self, dim):
+        self.hidden_size = dim
+        self.ent_size = dim
+        self.rel_size = dim
+
+    def set_ent_dimension(self, dim):
+        self.ent_size = dim
+
+    def set_rel_dimension(self, dim):
+        self.rel_size = dim
+
+    def set_train_times(self, times):
+        self.train_times = times
+
+    def set_nbatches(self, nbatches):
+        self.nbatches = nbatches
+
+    def set_margin(self, margin):
+        self.margin = margin
+
+    def set_ent_neg_rate(self, rate):
+        self.negative_ent = rate
+
+    def set_rel_neg_rate(self, rate):
+        self.negative_rel = rate
+
+    def set_import_files(self, path):
+        self.importName = path
+
+    def set_export_files(self, path):
+        self.exportName = path
+
+    def set_test_head(self, flag):
+        self.test_head = int(flag)
+
+    # ------------------------------------------------------------------ sampling (Config.py:343-347)
+    def sampling(self):
+        """One reference sampling() call on the GPU; results land in batch_h/t/r/y like the reference's."""
+        self.sampling_device()
+        self.ctx.call("okb_batch_to_host", 0, _vp(self.batch_h_addr), _vp(self.batch_t_addr), _vp(self.batch_r_addr),
+                      _vp(self.batch_y_addr), _stream())
+
+    def sampling_device(self, steps=1):
+        """Sample `steps` consecutive batches, leaving them resident in HBM (no host copy)."""
+        self.ctx.call("okb_sample", self.batch_size, self.negative_ent, self.negative_rel, steps, 0, self.workThreads, _stream())
+
+    # ------------------------------------------------------------------ parameters (Config.py:379-422)
+    def get_parameter_lists(self):
+        return self.trainModel.parameter_lists
+
+    def get_parameters_by_name(self, var_name):
+        if var_name in self.trainModel.parameter_lists:
+            return self.trainModel.parameter_lists[var_name].detach().cpu().numpy()
+        return None
+
+    def get_parameters(self, mode="numpy"):
+        res = {}
+        for var_name in self.get_parameter_lists():
+            v = self.get_parameters_by_name(var_name)
+            res[var_name] = v if mode == "numpy" else v.tolist()
+        return res
+
+    def save_parameters(self, path=None):
+        if path is None:
+            path = self.out_path
+        with open(path, "w") as f:
+            f.write(json.dumps(self.get_parameters("list")))
+
+    def set_parameters_by_name(self, var_name, tensor):
+        if var_name in self.trainModel.parameter_lists:
+            dst = self.trainModel.parameter_lists[var_name]
+            src = torch.as_tensor(np.asarray(tensor, dtype=np.float32)).reshape(dst.shape)
+            dst.copy_(src)
+
+    def set_parameters(self, lists):
+        for i in lists:
+            self.set_parameters_by_name(i, lists[i])
+
+    def save_tensorflow(self):
+        """Reference: Saver.save (Config.py:350-356).  Here: a torch checkpoint of tables + optimizer state."""
+        state = {"params": {k: v.cpu() for k, v in self.trainModel.parameter_lists.items()}, "step": self._step,
+                 "adam": None if self._adam is None else {k: v.cpu() if torch.is_tensor(v) else v for k, v in self._adam.items()}}
+        torch.save(state, self.exportName)
+
+    def restore_tensorflow(self):
+        state = torch.load(self.importName, map_location="cpu")
+        self.set_parameters({k: v.numpy() for k, v in state["params"].items()})
+        self._step = state.get("step", 0)
+        if state.get("adam") is not None and self._adam is not None:
+            for k, v in state["adam"].items():
+                if torch.is_tensor(v):
+                    self._adam[k].copy_(v)
+                else:
+                    self._adam[k] = v
+
+    # ------------------------------------------------------------------ model (Config.py:425-461)
+    def set_model(self, model):
+        self.model = model
+
+    def set_model_and_session(self, model):
+        """Allocate the model's tables in HBM (the reference builds a TF graph + session here)."""
+        self.model = model
+        self.trainModel = self.model(config=self, define=True, seed=self.seed)
+        self._step = 0
+        self._adam = None
+        if self.opt_method.lower() == "adam":
+            self._adam = {"b1p": np.float32(1.0), "b2p": np.float32(1.0)}
+            for k, v in self.trainModel.parameter_lists.items():
+                self._adam["m_" + k] = torch.zeros_like(v)
+                self._adam["v_" + k] = torch.zeros_like(v)
+        self._loss_dev = torch.zeros(1, dtype=torch.float32, device=self.trainModel.device)
+        self._model_struct = None
+
+    def _ensure_model(self):
+        if self.trainModel is None:
+            if self.model is None:
+                raise OkbError("call set_model / set_model_and_session first")
+            self.set_model_and_session(self.model)
+
+    def _cmodel(self):
+        """okb_model for the current tables (device pointers stay valid: tables are updated in place)."""
+        if self._model_struct is not None:
+            return self._model_struct
+        P = self.trainModel.parameter_lists
+        name = self.trainModel.name
+        m = okb_model()
+        m.model = MODEL_ID[name]
+        m.ent_dim = P["ent_embeddings"].shape[1]
+        m.rel_dim = P["rel_embeddings"].shape[1]
+        m.optimizer = 1 if self._adam is not None else 0
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        m.ent, m.rel = ptr(P["ent_embeddings"]), ptr(P["rel_embeddings"])
+        ae, ar = _AUX_ENT.get(name), _AUX_REL.get(name)
+        m.ent_aux = ptr(P[ae]) if ae else None
+        m.rel_aux = ptr(P[ar]) if ar else None
+        if self._adam is not None:
+            A = self._adam
+            m.m_ent, m.v_ent = ptr(A["m_ent_embeddings"]), ptr(A["v_ent_embeddings"])
+            m.m_rel, m.v_rel = ptr(A["m_rel_embeddings"]), ptr(A["v_rel_embeddings"])
+            if ae:
+                m.m_ent_aux, m.v_ent_aux = ptr(A["m_" + ae]), ptr(A["v_" + ae])
+            if ar:
+                m.m_rel_aux, m.v_rel_aux = ptr(A["m_" + ar]), ptr(A["v_" + ar])
+        self._model_struct = m
+        return m
+
+    def _hyper(self, advance=True):
+        hp = okb_hyper()
+        hp.margin = float(self.margin)
+        hp.beta1, hp.beta2, hp.eps = 0.9, 0.999, 1e-8
+        if self._adam is not None:
+            # tf.train.AdamOptimizer: beta powers are fp32 variables multiplied once per step;
+            # lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), all in fp32.
+            b1p, b2p = self._adam["b1p"], self._adam["b2p"]
+            if advance:
+                b1p = np.float32(b1p * np.float32(0.9))
+                b2p = np.float32(b2p * np.float32(0.999))
+                self._adam["b1p"], self._adam["b2p"] = b1p, b2p
+            one = np.float32(1.0)
+            hp.lr = float(np.float32(self.alpha) * np.sqrt(one - b2p, dtype=np.float32) / (one - b1p))
+        else:
+            hp.lr = float(self.alpha)
+        return hp
+
+    # ------------------------------------------------------------------ training
+    def train_step_device(self, step=0):
+        """loss_def + optimizer on batch `step` of the last sampling_device(); loss stays on the GPU."""
+        self._ensure_model()
+        m, hp = self._cmodel(), self._hyper()
+        if self._world is not None:
+            self._world.train_step(self, m, hp, step)
+        else:
+            self.ctx.call("okb_train_step", ctypes.byref(m), ctypes.byref(hp), step, _vp(self._loss_dev.data_ptr()), _stream())
+        self._step += 1
+        return self._loss_dev
+
+    def train_step(self, batch_h, batch_t, batch_r, batch_y):
+        """Perform a single training step on a caller-provided batch (Config.py:464-475)."""
+        self._ensure_model()
+        h = np.ascontiguousarray(batch_h, dtype=np.int64)
+        t = np.ascontiguousarray(batch_t, dtype=np.int64)
+        r = np.ascontiguousarray(batch_r, dtype=np.int64)
+        if h.size != self.batch_seq_size:
+            raise OkbError("batch has %d rows, expected batch_seq_size=%d" % (h.size, self.batch_seq_size))
+        self.ctx.call("okb_batch_from_host", self.batch_size, self.negative_ent, self.negative_rel, _addr(h), _addr(t), _addr(r), _stream())
+        return float(self.train_step_device(0).item())
+
+    def run(self):
+        """The train loop of distribute_training.py:267-283: train_times x nbatches x [sampling, step]."""
+        self._ensure_model()
+        losses = []
+        for epoch in range(self.train_times):
+            t0 = time.time()
+            acc = torch.zeros(1, dtype=torch.float32, device=self._loss_dev.device)
+            for batch in range(self.nbatches):
+                self.sampling_device()
+                loss = self.train_step_device(0)
+                acc += loss
+                if self.log_every and (self._step % self.log_every == 0):
+                    print("Global step: {} Epoch: {} Batch: {} loss: {}".format(self._step, epoch, batch, float(loss.item())))
+            res = float(acc.item())
+            losses.append(res)
+            print("Epoch: {} loss: {} ({:.3f} s)".format(epoch, res, time.time() - t0))
+        if self.exportName is not None:
+            self.save_tensorflow()
+        if self.out_path is not None:
+            self.save_parameters(self.out_path)
+        return losses
+
+    train = run
+
+    # ------------------------------------------------------------------ scoring (Config.py:478-488)
+    def test_step(self, test_h, test_t, test_r):
+        """predict for arbitrary triples: float32 [n] (TransE) or [n,1] (TransH/R/D)."""
+        self._ensure_model()
+        dev = self.trainModel.device
+        h = torch.as_tensor(np.ascontiguousarray(test_h, dtype=np.int64)).to(dev)
+        t = torch.as_tensor(np.ascontiguousarray(test_t, dtype=np.int64)).to(dev)
+        r = torch.as_tensor(np.ascontiguousarray(test_r, dtype=np.int64)).to(dev)
+        out = torch.empty(h.numel(), dtype=torch.float32, device=dev)
+        m = self._cmodel()
+        self.ctx.call("okb_predict", ctypes.byref(m), _vp(h.data_ptr()), _vp(t.data_ptr()), _vp(r.data_ptr()), h.numel(),
+                      _vp(out.data_ptr()), _stream())
+        res = out.cpu().numpy()
+        return res.reshape(-1, 1) if self.trainModel.predict_keepdims else res
+
+    # ------------------------------------------------------------------ evaluation
+    def link_prediction_records(self, q_lo=0, q_hi=None, cand_lo=0, cand_hi=None, reduce_fn=None):
+        """8-int records of testHead/testTail for test triples [q_lo,q_hi): int64 [n, 2, 8] on the GPU."""
+        self._ensure_model()
+        dev = self.trainModel.device
+        q_hi = self.testTotal if q_hi is None else q_hi
+        cand_hi = self.entTotal if cand_hi is None else cand_hi
+        n = q_hi - q_lo
+        counts = torch.zeros(n * 8, dtype=torch.int64, device=dev)
+        best = torch.full((n * 8,), -1, dtype=torch.int64, device=dev)       # all ones = "no candidate"
+        m = self._cmodel()
+        self.ctx.call("okb_rank", ctypes.byref(m), q_lo, q_hi, int(bool(self.test_head)), cand_lo, cand_hi,
+                      _vp(counts.data_ptr()), _vp(best.data_ptr()), _stream())
+        if reduce_fn is not None:
+            counts, best = reduce_fn(counts, best)
+        out = torch.empty(n * 16, dtype=torch.int64, device=dev)
+        self.ctx.call("okb_rank_finalize", q_lo, q_hi, _vp(counts.data_ptr()), _vp(best.data_ptr()), _vp(out.data_ptr()), _stream())
+        return out.view(n, 2, 8)
+
+    def test(self):
+        """Triple classification (Config.py:491-516) and/or link prediction (distribute_training.py:464-607)."""
+        self._ensure_model()
+        if self.importName is not None:
+            self.restore_tensorflow()
+        t0 = time.time()
+        if self.test_triple_classification:
+            self.ctx.call("okb_tc_batch", 1, *[_vp(getattr(self, "valid_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")])
+            res_pos = self.test_step(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
+            res_neg = self.test_step(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
+            self.ctx.call("okb_best_threshold", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg))
+            self.ctx.call("okb_tc_batch", 0, *[_vp(getattr(self, "test_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")])
+            res_pos = self.test_step(self.test_pos_h, self.test_pos_t, self.test_pos_r)
+            res_neg = self.test_step(self.test_neg_h, self.test_neg_t, self.test_neg_r)
+            cnt = np.zeros(4, np.int64)
+            self.ctx.call("okb_tc_eval", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg), _addr(cnt), _vp(self.acc_addr))
+            TP, TN, FP, FN = [float(x) for x in cnt]
+            prec, rec = TP / max(TP + FP, 1.0), TP / max(TP + FN, 1.0)
+            self.tc_counts = cnt
+            print("triple classification accuracy is %f" % self.acc[0])          # Test.h:381-384
+            print("triple classification precision is %f" % prec)
+            print("triple classification recall is %f" % rec)
+            print("triple classification f-measure is %f" % ((2 * prec * rec) / max(prec + rec, 1e-30)))
+        if self.test_link_prediction:
+            if self._world is not None:
+                rec = self._world.link_prediction(self)
+            else:
+                rec = self.link_prediction_records()
+            rec = rec.cpu().numpy()
+            self.lp_records = rec
+            d = metrics.accumulate(rec, bool(self.test_head))
+            self.lp_results = metrics.finalize(d, self.testTotal)
+            print(metrics.format_table(self.lp_results, bool(self.test_head)))
+        print("\nElapsed test time (seconds): {}".format(time.time() - t0))
+        return getattr(self, "lp_results", None)
+
+    def plot_roc(self, rel_index, fig_name=None):
+        """ROC of one relation (Config.py:519-571).  matplotlib is optional: returns (FPR, TPR, auc)."""
+        self._ensure_model()
+        if self.importName is not None:
+            self.restore_tensorflow()
+        self.init_triple_classification()
+        a = lambda pre: [_vp(getattr(self, pre + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")]
+        self.ctx.call("okb_tc_batch", 1, *a("valid_"))
+        pv = self.test_step(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
+        nv = self.test_step(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
+        self.ctx.call("okb_tc_batch", 0, *a("test_"))
+        pt = self.test_step(self.test_pos_h, self.test_pos_t, self.test_pos_r)
+        nt = self.test_step(self.test_neg_h, self.test_neg_t, self.test_neg_r)
+        n_int = int(self.lib.okb_n_interval(self.ctx.h, rel_index, _addr(pv), _addr(nv)))
+        self.lib.okb_tpfp.restype = ctypes.POINTER(ctypes.c_int64 * ((n_int + 1) * 2))
+        res = [j for j in self.lib.okb_tpfp(self.ctx.h, rel_index, _addr(pv), _addr(nv), _addr(pt), _addr(nt)).contents]
+        TPR, FPR = [], []
+        if res[0] != 0 or res[0 + n_int + 1] != 0:
+            TPR.append(0)
+            FPR.append(0)
+        for i in range(0, n_int + 1):
+            TPR.append(res[i])
+            FPR.append(res[i + n_int + 1])
+        if TPR[-1] != len(pt.flatten()) or FPR[-1] != len(nt.flatten()):
+            TPR.append(len(pt.flatten()))
+            FPR.append(len(nt.flatten()))
+        TPR = [x / TPR[-1] for x in TPR]
+        FPR = [x / FPR[-1] for x in FPR]
+        auc = float(np.trapz(TPR, FPR)) if hasattr(np, "trapz") else float(np.trapezoid(TPR, FPR))
+        try:
+            import matplotlib.pyplot as plt
+            plt.figure()
+            plt.plot(FPR, TPR, color="darkorange", lw=2, label="ROC curve (area = %0.3f)" % auc)
+            plt.plot([0, 1], [0, 1], color="navy", lw=2, linestyle="--")
+            plt.xlabel("False Positive Rate (FPR)")
+            plt.ylabel("True Positive Rate (TPR)")
+            plt.legend(loc="lower right")
+            plt.savefig(fig_name) if fig_name else plt.show()
+        except ImportError:
+            pass
+        return FPR, TPR, auc
+
+    # ------------------------------------------------------------------ predict_* (Config.py:574-663)
+    def predict_head_entity(self, t, r, k):
+        if self.importName is not None:
+            self.restore_tensorflow()
+        test_h = np.array(range(self.entTotal))
+        test_r = np.array([r] * self.entTotal)
+        test_t = np.array([t] * self.entTotal)
+        res = self.test_step(test_h, test_t, test_r).reshape(-1).argsort()[:k]
+        print(res)
+        return res
+
+    def predict_tail_entity(self, h, r, k):
+        if self.importName is not None:
+            self.restore_tensorflow()
+        test_h = np.array([h] * self.entTotal)
+        test_r = np.array([r] * self.entTotal)
+        test_t = np.array(range(self.entTotal))
+        res = self.test_step(test_h, test_t, test_r).reshape(-1).argsort()[:k]
+        print(res)
+        return res
+
+    def predict_relation(self, h, t, k):
+        if self.importName is not None:
+            self.restore_tensorflow()
+        test_h = np.array([h] * self.relTotal)
+        test_r = np.array(range(self.relTotal))
+        test_t = np.array([t] * self.relTotal)
+        res = self.test_step(test_h, test_t, test_r).reshape(-1).argsort()[:k]
+        print(res)
+        return res
+
+    def predict_triple(self, h, t, r, thresh=None):
+        self.init_triple_classification()
+        if self.importName is not None:
+            self.restore_tensorflow()
+        res = self.test_step(np.array([h]), np.array([t]), np.array([r]))
+        if thresh is None:
+            a = [_vp(getattr(self, "valid_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")]
+            self.ctx.call("okb_tc_batch", 1, *a)
+            res_pos = self.test_step(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
+            res_neg = self.test_step(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
+            self.ctx.call("okb_best_threshold", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg))
+            thresh = self.relThresh[r]
+        ok = bool(res.reshape(-1)[0] < thresh)
+        print("triple (%d,%d,%d) is %s" % (h, t, r, "correct" if ok else "wrong"))
+        return ok

@@ -1,0 +1,90 @@
+// Internal declarations shared by the translation units of libokb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/okb200.h"
+
+typedef int32_t i32;
+typedef int64_t i64;
+typedef uint64_t u64;
+
+struct DevBuf {                       // grow-only device allocation
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <class T> T *as() const { return (T *)p; }
+};
+
+// Sorted id lists keyed by relation or entity (type constraints, ontology): CSR, int32.
+struct Lists {
+    std::vector<i32> lef, rig, ids;   // ids[lef[k]..rig[k]) sorted
+    i32 *d_lef = nullptr, *d_rig = nullptr, *d_ids = nullptr;
+};
+
+struct okb_ctx {
+    std::string in_path = "../data/FB15K/", out_path = "../data/FB15K/", err;
+    i64 W = 1, bern = 0;
+    // ---------------- totals
+    i64 E = 0, R = 0, n_raw = 0, n = 0, new_batch = 0, n_test = 0, n_valid = 0, n_all = 0;
+    // ---------------- host index (kept for the tiny host-side paths: TC negatives, thresholds)
+    std::vector<i32> raw_h, raw_t, raw_r;              // train2id.txt order
+    std::vector<i32> byh_r, byh_t, byt_r, byt_h, byht_t, byht_r;   // secondary key / value of the 3 sorted copies
+    std::vector<i32> lef_h, rig_h, lef_t, rig_t, lef_ht, rig_ht;
+    std::vector<float> tph, hpt;                       // left_mean / right_mean
+    std::vector<i32> test_h, test_t, test_r, valid_h, valid_t, valid_r;   // sorted (r,h,t)
+    std::vector<i32> test_lef, test_rig, valid_lef, valid_rig;
+    std::vector<u64> all_hrt;                          // packed keys of train+valid+test sorted (h,r,t), dups kept
+    std::vector<i32> neg_test_t, neg_valid_t;
+    Lists head_type, tail_type, sup, sub;
+    bool have_types = false, have_onto = false;
+    // ---------------- device index
+    int4 *d_raw = nullptr;            // {h, t, r, 0}
+    int4 *d_run = nullptr;            // {llH, rrH, llT, rrT}: runs of (h,r) in by-head order and (t,r) in by-tail order
+    int2 *d_run_ht = nullptr;         // {ll, rr}: run of (h,t) in by-(h,t) order
+    i32 *d_byh_t = nullptr, *d_byt_h = nullptr, *d_byht_r = nullptr;
+    float *d_prob = nullptr;          // per relation 1000*hpt/(hpt+tph) (bern) — Base.cpp:116-117
+    // test side
+    i32 *d_test_h = nullptr, *d_test_t = nullptr, *d_test_r = nullptr;
+    i32 *d_known_t = nullptr, *d_known_h = nullptr;    // unique known tails per (h,r) run / heads per (t,r) run
+    int4 *d_test_run = nullptr;       // {tail-list lo, hi, head-list lo, hi} into d_known_t / d_known_h
+    std::vector<i32> grp_rel, grp_lo, grp_hi;          // relation groups of the test list
+    // ---------------- sampler state
+    std::vector<u64> state;           // host mirror (valid when !state_dirty)
+    u64 *d_state = nullptr;
+    bool state_dirty = false;         // device copy is newer than host mirror
+    // ---------------- sampled batches
+    i64 B = 0, K = 0, KR = 0, steps = 0;
+    DevBuf batch;                     // int32 [steps][3][S]
+    // ---------------- plan / workspace
+    DevBuf keys_ent, keys_rel, perm_ent, perm_rel, sort_tmp, hist, gent, grel, flags, lossterms, rowseg_e, rowseg_r;
+    DevBuf rank_ws, host_io;
+    i64 plan_ne = 0, plan_nr = 0;
+    int ent_bits = 0, rel_bits = 0;
+    // legacy result buffers
+    i64 res8[8];
+    std::vector<i64> tpfp;
+};
+
+#define OKB_FAIL(c, code, msg) do { (c)->err = (msg); return (code); } while (0)
+#define OKB_CUDA(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
+    (c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return OKB_ERR_CUDA; } } while (0)
+
+extern i64 g_launches;                // kernels launched by this library
+#define OKB_LAUNCHED(n) (g_launches += (n))
+
+// loader.cpp
+int okb_upload_train(okb_ctx *c);
+int okb_upload_test(okb_ctx *c);
+int okb_upload_lists(okb_ctx *c);
+bool okb_host_find(const okb_ctx *c, i64 h, i64 t, i64 r);
+i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(0, h, r) on stream 0
+
+// radix.cu
+int okb_sort_pairs(okb_ctx *c, const i32 *keys, i32 *keys_out, i32 *perm_out, i64 n, int bits, cudaStream_t s);
+
+static inline int bits_for(i64 n) { int b = 1; while ((1ll << b) < n) b++; return b; }

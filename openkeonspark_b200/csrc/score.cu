@@ -1,0 +1,660 @@
+// Scoring and link-prediction ranking.
+//
+//   okb_predict        TransX.predict_def on arbitrary (h,t,r) lists (Config.test_step)
+//   okb_rank           getHeadBatch/getTailBatch + predict + testHead/testTail (Test.h:11-249,
+//                      distribute_training.py:465-590) for a range of test triples: every candidate
+//                      entity is scored against every query and the raw / filtered /
+//                      type-constrained better-than counts and argmins are accumulated on the GPU
+//   okb_rank_finalize  counts + argmins -> the reference's 8-int records (incl. ontology classes)
+//   okb_rank_scores    the reference-shaped call: one query, caller-provided scores[E]
+//
+// Canonical fp32 order (shared with oracle/kge_oracle.c so scores, hence ranks, are bit-identical):
+// reductions over the embedding dimension run sequentially d = 0..D-1, every multiply and add is
+// individually rounded (__fmul_rn/__fadd_rn: never contracted to FMA), 1/sqrt = IEEE sqrt + divide.
+//
+// Ranking layout: the test list is sorted by relation (Reader.h:260), so queries are processed in
+// relation groups.  Per group the (projected, normalised) candidate table is materialised once,
+// TRANSPOSED ([D][E_pad]: thread j reads column j, coalesced), tiles of 128 candidates x D are
+// staged into shared memory with bulk-async (TMA) copies, and each thread keeps QB query
+// accumulators per side in registers: 2 FADD per (query, candidate, dim) — FP32-ALU bound; L1
+// distance has no tensor-core form.
+#include <algorithm>
+
+#include "okb_internal.h"
+
+#define FULL 0xffffffffu
+#define EPS_NORM 1e-12f
+#define CT 128                 // candidates per tile (= threads per CTA)
+#define QB 8                   // queries per register block
+
+// ------------------------------------------------------------------------------------------ canonical helpers
+__device__ __forceinline__ float c_inv_norm(float ss) { return __fdiv_rn(1.0f, __fsqrt_rn(ss > EPS_NORM ? ss : EPS_NORM)); }
+
+// sequential dot over a strided vector pair
+__device__ __forceinline__ float c_dot(const float *a, int sa, const float *b, int sb, int D) {
+    float s = 0.f;
+    for (int d = 0; d < D; d++) s = __fadd_rn(s, __fmul_rn(a[d * sa], b[d * sb]));
+    return s;
+}
+__device__ __forceinline__ float c_finish(int model, float s, int D) { return model == OKB_TRANSE ? __fdiv_rn(s, (float)D) : s; }
+
+// ------------------------------------------------------------------------------------------ predict (any triples)
+// One thread per triple; rows are re-read from global/L2 in several sequential passes instead of
+// being held in local arrays.  Not a hot path (triple classification, predict_*).
+struct PredArgs {
+    okb_model m;
+    const i64 *h, *t, *r;
+    float *out;
+    i64 n;
+    i32 E, R;
+};
+
+__device__ float pred_one(const okb_model &m, i64 h, i64 t, i64 r) {
+    const int D = m.ent_dim;
+    const float *eh = m.ent + h * D, *et = m.ent + t * D, *er = m.rel + r * D;
+    const float inv_r = c_inv_norm(c_dot(er, 1, er, 1, D));
+    float s = 0.f;
+    if (m.model == OKB_TRANSE) {
+        const float ih = c_inv_norm(c_dot(eh, 1, eh, 1, D)), it = c_inv_norm(c_dot(et, 1, et, 1, D));
+        for (int d = 0; d < D; d++) {
+            const float a = __fadd_rn(__fmul_rn(eh[d], ih), __fmul_rn(er[d], inv_r));
+            s = __fadd_rn(s, fabsf(__fsub_rn(a, __fmul_rn(et[d], it))));
+        }
+    } else if (m.model == OKB_TRANSH) {
+        const float *n = m.rel_aux + r * D;
+        const float in = c_inv_norm(c_dot(n, 1, n, 1, D));
+        float dh = 0.f, dt = 0.f;
+        for (int d = 0; d < D; d++) {
+            const float nh = __fmul_rn(n[d], in);
+            dh = __fadd_rn(dh, __fmul_rn(eh[d], nh));
+            dt = __fadd_rn(dt, __fmul_rn(et[d], nh));
+        }
+        float sh = 0.f, st = 0.f;
+        for (int d = 0; d < D; d++) {
+            const float nh = __fmul_rn(n[d], in);
+            const float ph = __fsub_rn(eh[d], __fmul_rn(dh, nh)), pt = __fsub_rn(et[d], __fmul_rn(dt, nh));
+            sh = __fadd_rn(sh, __fmul_rn(ph, ph));
+            st = __fadd_rn(st, __fmul_rn(pt, pt));
+        }
+        const float ih = c_inv_norm(sh), it = c_inv_norm(st);
+        for (int d = 0; d < D; d++) {
+            const float nh = __fmul_rn(n[d], in);
+            const float ph = __fsub_rn(eh[d], __fmul_rn(dh, nh)), pt = __fsub_rn(et[d], __fmul_rn(dt, nh));
+            const float a = __fadd_rn(__fmul_rn(ph, ih), __fmul_rn(er[d], inv_r));
+            s = __fadd_rn(s, fabsf(__fsub_rn(a, __fmul_rn(pt, it))));
+        }
+    } else {  // TransD
+        const float *rt = m.rel_aux + r * D;
+        const float ch = c_dot(eh, 1, m.ent_aux + h * D, 1, D), ct = c_dot(et, 1, m.ent_aux + t * D, 1, D);
+        float sh = 0.f, st = 0.f;
+        for (int d = 0; d < D; d++) {
+            const float ph = __fadd_rn(eh[d], __fmul_rn(ch, rt[d])), pt = __fadd_rn(et[d], __fmul_rn(ct, rt[d]));
+            sh = __fadd_rn(sh, __fmul_rn(ph, ph));
+            st = __fadd_rn(st, __fmul_rn(pt, pt));
+        }
+        const float ih = c_inv_norm(sh), it = c_inv_norm(st);
+        for (int d = 0; d < D; d++) {
+            const float ph = __fadd_rn(eh[d], __fmul_rn(ch, rt[d])), pt = __fadd_rn(et[d], __fmul_rn(ct, rt[d]));
+            const float a = __fadd_rn(__fmul_rn(ph, ih), __fmul_rn(er[d], inv_r));
+            s = __fadd_rn(s, fabsf(__fsub_rn(a, __fmul_rn(pt, it))));
+        }
+    }
+    return c_finish(m.model, s, D);
+}
+
+__global__ void __launch_bounds__(128) predict_kernel(PredArgs a) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const i64 h = a.h[i], t = a.t[i], r = a.r[i];
+    if (h < 0 || h >= a.E || t < 0 || t >= a.E || r < 0 || r >= a.R) { a.out[i] = __int_as_float(0x7fc00000); return; }
+    a.out[i] = pred_one(a.m, h, t, r);
+}
+
+// ------------------------------------------------------------------------------------------ rank: preparation
+// relation vectors of a group: rv[g][0][D] = unit(rel[r]); rv[g][1][D] = unit(normal[r]) (TransH) or rel_transfer[r] (TransD)
+__global__ void relvec_kernel(okb_model m, const i32 *__restrict__ grp_rel, float *__restrict__ rv, i32 G) {
+    const i32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const int D = m.ent_dim;
+    const i64 r = grp_rel[g];
+    const float *er = m.rel + r * D;
+    float *o = rv + (i64)g * 2 * D;
+    const float inv = c_inv_norm(c_dot(er, 1, er, 1, D));
+    for (int d = 0; d < D; d++) o[d] = __fmul_rn(er[d], inv);
+    if (m.model == OKB_TRANSH) {
+        const float *n = m.rel_aux + r * D;
+        const float in = c_inv_norm(c_dot(n, 1, n, 1, D));
+        for (int d = 0; d < D; d++) o[D + d] = __fmul_rn(n[d], in);
+    } else if (m.model == OKB_TRANSD) {
+        const float *rt = m.rel_aux + r * D;
+        for (int d = 0; d < D; d++) o[D + d] = rt[d];
+    }
+}
+
+// In-place canonical transfer + l2-normalise of one entity row held in shared memory (lane-private,
+// unit stride), given the group's auxiliary vector `aux` and (TransD) the entity's transfer row.
+__device__ __forceinline__ void canon_row(int model, float *row, const float *aux, const float *et_row, int D) {
+    if (model == OKB_TRANSH) {
+        const float dh = c_dot(row, 1, aux, 1, D);
+        for (int d = 0; d < D; d++) row[d] = __fsub_rn(row[d], __fmul_rn(dh, aux[d]));
+    } else if (model == OKB_TRANSD) {
+        const float ch = c_dot(row, 1, et_row, 1, D);
+        for (int d = 0; d < D; d++) row[d] = __fadd_rn(row[d], __fmul_rn(ch, aux[d]));
+    }
+    const float inv = c_inv_norm(c_dot(row, 1, row, 1, D));
+    for (int d = 0; d < D; d++) row[d] = __fmul_rn(row[d], inv);
+}
+
+// Candidate tables: out[tab][d][j - j0] for entities j in [j0, j0 + ncol) (ncol multiple of CT, zero padded).
+// A warp stages 32 entity rows in shared memory (coalesced), each lane canonicalises its row,
+// and the result is written transposed (coalesced over j for every d).
+struct CandArgs {
+    okb_model m;
+    const float *rv;           // [G][2][D]
+    float *out;                // [ntab][D][ncol]
+    i32 j0, ncol, E, ntab;
+};
+__global__ void __launch_bounds__(128) cand_kernel(CandArgs a) {
+    const int wpb = blockDim.x >> 5;
+    extern __shared__ float sm[];
+    const int D = a.m.ent_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int stride = D + 1;
+    const bool need_et = a.m.model == OKB_TRANSD;
+    float *rows = sm + (size_t)w * 32 * stride * (need_et ? 2 : 1);
+    float *ets = rows + 32 * stride;
+    float *aux = sm + (size_t)wpb * 32 * stride * (need_et ? 2 : 1);   // [D] per block
+    const i32 tab = blockIdx.y;
+    const i32 jbase = a.j0 + (blockIdx.x * wpb + w) * 32;
+    if (a.m.model != OKB_TRANSE) {
+        for (int d = threadIdx.x; d < D; d += blockDim.x) aux[d] = a.rv[((i64)tab * 2 + 1) * D + d];
+    }
+    for (int idx = lane; idx < 32 * D; idx += 32) {
+        const int rr = idx / D, d = idx - rr * D;
+        const i32 j = jbase + rr;
+        rows[rr * stride + d] = j < a.E ? a.m.ent[(i64)j * D + d] : 0.f;
+        if (need_et) ets[rr * stride + d] = j < a.E ? a.m.ent_aux[(i64)j * D + d] : 0.f;
+    }
+    __syncthreads();
+    const i32 j = jbase + lane;
+    if (j < a.E) canon_row(a.m.model, rows + lane * stride, aux, ets + lane * stride, D);
+    __syncwarp();
+    const i32 col = jbase - a.j0 + lane;
+    if (col < a.ncol)
+        for (int d = 0; d < D; d++) a.out[((i64)tab * D + d) * a.ncol + col] = j < a.E ? rows[lane * stride + d] : 0.f;
+}
+
+// Query vectors for test triples [q_lo, q_hi): qa[q][d] = fl(h_hat[d] + r_hat[d]) (tail side),
+// qt[q][d] = t_hat[d] (head side), ref[q] = score of the true triple (shared by both sides).
+struct QArgs {
+    okb_model m;
+    const i32 *th, *tt, *tr;
+    const i32 *q_group;        // group index of each query (relative to chunk)
+    const float *rv;
+    float *qa, *qt, *ref;
+    i32 q_lo, nq;
+};
+__global__ void __launch_bounds__(128) qvec_kernel(QArgs a) {
+    extern __shared__ float sm[];
+    const int D = a.m.ent_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int stride = D + 1;
+    const bool need_et = a.m.model == OKB_TRANSD;
+    const int wpb = blockDim.x >> 5;
+    float *H = sm + (size_t)w * 32 * stride * (need_et ? 4 : 2), *T = H + 32 * stride, *EH = T + 32 * stride, *ET = EH + 32 * stride;
+    const i32 qbase = (blockIdx.x * wpb + w) * 32;
+    for (int rr = 0; rr < 32; rr++) {
+        const i32 q = qbase + rr;
+        if (q >= a.nq) break;
+        const i64 h = a.th[a.q_lo + q], t = a.tt[a.q_lo + q];
+        for (int d = lane; d < D; d += 32) {
+            H[rr * stride + d] = a.m.ent[h * D + d];
+            T[rr * stride + d] = a.m.ent[t * D + d];
+            if (need_et) { EH[rr * stride + d] = a.m.ent_aux[h * D + d]; ET[rr * stride + d] = a.m.ent_aux[t * D + d]; }
+        }
+    }
+    __syncwarp();
+    const i32 q = qbase + lane;
+    if (q >= a.nq) return;
+    const float *rv = a.rv + (i64)a.q_group[q] * 2 * D;
+    float *h = H + lane * stride, *t = T + lane * stride;
+    canon_row(a.m.model, h, rv + D, EH + lane * stride, D);
+    canon_row(a.m.model, t, rv + D, ET + lane * stride, D);
+    float s = 0.f;
+    for (int d = 0; d < D; d++) {
+        const float x = __fadd_rn(h[d], rv[d]);
+        a.qa[(i64)q * D + d] = x;
+        a.qt[(i64)q * D + d] = t[d];
+        s = __fadd_rn(s, fabsf(__fsub_rn(x, t[d])));
+    }
+    a.ref[q] = c_finish(a.m.model, s, D);
+}
+
+// type flags per (group, candidate): bit 0 = in head_type[r], bit 1 = in tail_type[r]
+__global__ void typeflag_kernel(const i32 *__restrict__ grp_rel, const i32 *__restrict__ hl, const i32 *__restrict__ hr,
+                                const i32 *__restrict__ hid, const i32 *__restrict__ tl, const i32 *__restrict__ tr_,
+                                const i32 *__restrict__ tid, unsigned char *__restrict__ flags, i32 j0, i32 ncol) {
+    const i32 g = blockIdx.y, r = grp_rel[g];
+    unsigned char *f = flags + (i64)g * ncol;
+    for (i32 i = hl[r] + blockIdx.x * blockDim.x + threadIdx.x; i < hr[r]; i += gridDim.x * blockDim.x) {
+        const i32 c = hid[i] - j0;
+        if (c >= 0 && c < ncol) atomicOr((unsigned int *)(f + (c & ~3)), 1u << (8 * (c & 3)));
+    }
+    for (i32 i = tl[r] + blockIdx.x * blockDim.x + threadIdx.x; i < tr_[r]; i += gridDim.x * blockDim.x) {
+        const i32 c = tid[i] - j0;
+        if (c >= 0 && c < ncol) atomicOr((unsigned int *)(f + (c & ~3)), 2u << (8 * (c & 3)));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ rank: main kernel
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned phase) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    }
+}
+// 1-D bulk async copy global -> shared (TMA engine; SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct RankArgs {
+    const float *cand;         // [ntab][D][ncol]
+    const float *rv;           // [G][2][D]
+    const float *qa, *qt, *ref;   // per query of the chunk
+    const unsigned char *tflag;   // [G][ncol]
+    const i32 *th, *tt;        // test heads / tails (global test index)
+    const int4 *trun;          // known-list runs per test triple
+    const i32 *known_t, *known_h;
+    const i32 *g_qlo, *g_qhi;  // query range of each group, relative to the chunk
+    unsigned long long *counts, *best;   // [(nq)*2*4], chunk-relative
+    i32 D, ncol, j0, cand_lo, cand_hi, q_lo, model, tab_per_group;
+};
+
+template <bool HEADS>
+__global__ void __launch_bounds__(CT) rank_kernel(RankArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int D = a.D, tid = threadIdx.x;
+    float *tile = (float *)smraw;                          // [D][CT]
+    float *rhat = tile + (size_t)D * CT;                   // [D]
+    float *qa = rhat + ((D + 3) & ~3);                     // [D][QB]
+    float *qt = qa + (size_t)D * QB;                       // [D][QB]
+    float *refs = qt + (size_t)D * QB;                     // [QB]
+    i32 *tgt = (i32 *)(refs + QB);                         // [QB][2]
+    int4 *runs = (int4 *)(tgt + 2 * QB);                   // [QB]
+    unsigned *cnt = (unsigned *)(runs + QB);               // [QB][2][4]
+    unsigned long long *bst = (unsigned long long *)(cnt + QB * 8);   // [QB][2][4]
+    unsigned long long *bar = bst + QB * 8;
+
+    const i32 g = blockIdx.y;
+    const i32 col0 = blockIdx.x * CT;
+    const i32 tab = a.tab_per_group ? g : 0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_expect_tx(bar, (unsigned)(D * CT * sizeof(float)));
+        const float *src = a.cand + (i64)tab * D * a.ncol + col0;
+        for (int d = 0; d < D; d++) tma_load_1d(tile + (size_t)d * CT, src + (i64)d * a.ncol, CT * sizeof(float), bar);
+    }
+    for (int d = tid; d < D; d += CT) rhat[d] = a.rv[(i64)g * 2 * D + d];
+    const i32 j = a.j0 + col0 + tid;
+    const bool valid = j >= a.cand_lo && j < a.cand_hi;
+    const unsigned tf = valid ? a.tflag[(i64)g * a.ncol + col0 + tid] : 0u;
+    __syncthreads();                                       // barrier init visible to all waiters
+    mbar_wait(bar, 0);
+
+    const i32 qlo = a.g_qlo[g], qhi = a.g_qhi[g];
+    for (i32 qb = qlo; qb < qhi; qb += QB) {
+        __syncthreads();
+        for (int idx = tid; idx < D * QB; idx += CT) {
+            const int q = idx / D, d = idx - q * D;
+            const bool ok = qb + q < qhi;
+            qa[d * QB + q] = ok ? a.qa[(i64)(qb + q) * D + d] : 0.f;
+            if (HEADS) qt[d * QB + q] = ok ? a.qt[(i64)(qb + q) * D + d] : 0.f;
+        }
+        if (tid < QB) {
+            const bool ok = qb + tid < qhi;
+            const i32 ti = a.q_lo + qb + tid;
+            refs[tid] = ok ? a.ref[qb + tid] : 0.f;
+            tgt[2 * tid] = ok ? a.th[ti] : -1;
+            tgt[2 * tid + 1] = ok ? a.tt[ti] : -1;
+            runs[tid] = ok ? a.trun[ti] : make_int4(0, 0, 0, 0);
+        }
+        if (tid < QB * 8) { cnt[tid] = 0u; bst[tid] = ~0ull; }
+        __syncthreads();
+
+        float accT[QB], accH[QB];
+#pragma unroll
+        for (int q = 0; q < QB; q++) { accT[q] = 0.f; accH[q] = 0.f; }
+        for (int d = 0; d < D; d++) {
+            const float c = tile[d * CT + tid];
+            const float cr = __fadd_rn(c, rhat[d]);
+            const float4 *pa = (const float4 *)(qa + d * QB), *pt = (const float4 *)(qt + d * QB);
+#pragma unroll
+            for (int v = 0; v < QB / 4; v++) {
+                const float4 x = pa[v];
+                accT[4 * v + 0] = __fadd_rn(accT[4 * v + 0], fabsf(__fsub_rn(x.x, c)));
+                accT[4 * v + 1] = __fadd_rn(accT[4 * v + 1], fabsf(__fsub_rn(x.y, c)));
+                accT[4 * v + 2] = __fadd_rn(accT[4 * v + 2], fabsf(__fsub_rn(x.z, c)));
+                accT[4 * v + 3] = __fadd_rn(accT[4 * v + 3], fabsf(__fsub_rn(x.w, c)));
+                if (HEADS) {
+                    const float4 y = pt[v];
+                    accH[4 * v + 0] = __fadd_rn(accH[4 * v + 0], fabsf(__fsub_rn(cr, y.x)));
+                    accH[4 * v + 1] = __fadd_rn(accH[4 * v + 1], fabsf(__fsub_rn(cr, y.y)));
+                    accH[4 * v + 2] = __fadd_rn(accH[4 * v + 2], fabsf(__fsub_rn(cr, y.z)));
+                    accH[4 * v + 3] = __fadd_rn(accH[4 * v + 3], fabsf(__fsub_rn(cr, y.w)));
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < QB; q++) {
+            const bool qok = valid && qb + q < qhi;
+            const float ref = refs[q];
+#pragma unroll
+            for (int side = HEADS ? 0 : 1; side < 2; side++) {
+                const float s = c_finish(a.model, side ? accT[q] : accH[q], D);
+                if (qok && j != tgt[2 * q + side] && s < ref) {              // Test.h:59,62 / 168,171
+                    // known-true filter: is (j, t, r) / (h, j, r) in train+valid+test?  (Corrupt.h:104-115)
+                    const int4 rn = runs[q];
+                    const i32 *lst = side ? a.known_t : a.known_h;
+                    const i32 end = side ? rn.y : rn.w;
+                    i32 lo = side ? rn.x : rn.z, hi = end;
+                    while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (__ldg(lst + mid) < j) lo = mid + 1; else hi = mid; }
+                    const bool known = lo < end && __ldg(lst + lo) == j;
+                    const bool typed = (tf >> side) & 1u;
+                    const unsigned long long pk = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned)j;
+                    unsigned *cq = cnt + (q * 2 + side) * 4;
+                    unsigned long long *bq = bst + (q * 2 + side) * 4;
+                    atomicAdd(cq + 0, 1u); atomicMin(bq + 0, pk);
+                    if (!known) { atomicAdd(cq + 1, 1u); atomicMin(bq + 1, pk); }
+                    if (typed) {
+                        atomicAdd(cq + 2, 1u); atomicMin(bq + 2, pk);
+                        if (!known) { atomicAdd(cq + 3, 1u); atomicMin(bq + 3, pk); }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < QB * 8) {
+            const int q = tid >> 3;
+            if (qb + q < qhi) {
+                const i64 o = (i64)(qb + q) * 8 + (tid & 7);
+                if (cnt[tid]) atomicAdd(a.counts + o, (unsigned long long)cnt[tid]);
+                if (bst[tid] != ~0ull) atomicMin(a.best + o, bst[tid]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ finalize
+struct FinArgs {
+    const unsigned long long *counts, *best;
+    const i32 *th, *tt;
+    const i32 *sup_l, *sup_r, *sup_id, *sub_l, *sub_r, *sub_id;
+    i64 *out;
+    i32 q_lo, nq, has_onto;
+};
+__device__ __forceinline__ void onto_classes(const FinArgs &a, i32 target, const i64 *arg, i64 *out4) {
+    // Test.h:109-132: the two cursors are shared by the four lookups and never rewound
+    i32 p = a.has_onto ? a.sup_l[target] : 0, pe = a.has_onto ? a.sup_r[target] : 0;
+    i32 s = a.has_onto ? a.sub_l[target] : 0, se = a.has_onto ? a.sub_r[target] : 0;
+    for (int k = 0; k < 4; k++) {
+        const i64 id = arg[k];
+        if (id == target) { out4[k] = 0; continue; }
+        while (p < pe && a.sup_id[p] < id) p++;
+        if (p < pe && a.sup_id[p] == id) { out4[k] = 1; continue; }
+        while (s < se && a.sub_id[s] < id) s++;
+        if (s < se && a.sub_id[s] == id) { out4[k] = 2; continue; }
+        out4[k] = 3;
+    }
+}
+__global__ void finalize_kernel(FinArgs a) {
+    const i32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nq * 2) return;
+    const i32 q = i >> 1, side = i & 1;
+    const i32 target = side ? a.tt[a.q_lo + q] : a.th[a.q_lo + q];
+    i64 arg[4];
+    i64 *o = a.out + (i64)i * 8;
+    for (int k = 0; k < 4; k++) {
+        o[k] = (i64)a.counts[(i64)i * 4 + k];
+        const unsigned long long b = a.best[(i64)i * 4 + k];
+        arg[k] = b == ~0ull ? target : (i64)(b & 0xffffffffull);
+    }
+    if (side == 0) arg[1] = arg[0];     // Test.h:69-74: head-side filter argmin is not guarded by the filter
+    onto_classes(a, target, arg, o + 4);
+}
+
+// ------------------------------------------------------------------------------------------ one query, given scores
+struct RankScoresArgs {
+    const float *scores;
+    const i32 *known, *types;
+    i32 E, target, klo, khi, tlo, thi;
+    unsigned long long *counts, *best;   // [4] each, pre-initialised
+};
+__global__ void __launch_bounds__(256) rank_scores_kernel(RankScoresArgs a) {
+    __shared__ unsigned cnt[4];
+    __shared__ unsigned long long bst[4];
+    if (threadIdx.x < 4) { cnt[threadIdx.x] = 0; bst[threadIdx.x] = ~0ull; }
+    __syncthreads();
+    const float ref = a.scores[a.target];
+    for (i32 j = blockIdx.x * blockDim.x + threadIdx.x; j < a.E; j += gridDim.x * blockDim.x) {
+        const float s = a.scores[j];
+        if (j == a.target || !(s < ref)) continue;
+        i32 lo = a.klo, hi = a.khi;
+        while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (a.known[mid] < j) lo = mid + 1; else hi = mid; }
+        const bool known = lo < a.khi && a.known[lo] == j;
+        lo = a.tlo; hi = a.thi;
+        while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (a.types[mid] < j) lo = mid + 1; else hi = mid; }
+        const bool typed = lo < a.thi && a.types[lo] == j;
+        // scores may be negative here (caller-provided): order-preserving float -> uint key
+        unsigned u = __float_as_uint(s);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        const unsigned long long pk = ((unsigned long long)u << 32) | (unsigned)j;
+        atomicAdd(cnt + 0, 1u); atomicMin(bst + 0, pk);
+        if (!known) { atomicAdd(cnt + 1, 1u); atomicMin(bst + 1, pk); }
+        if (typed) {
+            atomicAdd(cnt + 2, 1u); atomicMin(bst + 2, pk);
+            if (!known) { atomicAdd(cnt + 3, 1u); atomicMin(bst + 3, pk); }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        if (cnt[threadIdx.x]) atomicAdd(a.counts + threadIdx.x, (unsigned long long)cnt[threadIdx.x]);
+        if (bst[threadIdx.x] != ~0ull) atomicMin(a.best + threadIdx.x, bst[threadIdx.x]);
+    }
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v, i64 n) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+extern bool okb_pick_layout(int D, int &vw, int &nv);
+
+static int check_score_model(okb_ctx *c, const okb_model *m) {
+    if (!m || !m->ent || !m->rel) OKB_FAIL(c, OKB_ERR_ARG, "model tables missing");
+    if (m->model == OKB_TRANSR) OKB_FAIL(c, OKB_ERR_ARG, "TransR scoring is handled by transr.cu");
+    if (m->ent_dim != m->rel_dim) OKB_FAIL(c, OKB_ERR_ARG, "TransE/H/D need ent_dim == rel_dim");
+    if (m->model != OKB_TRANSE && !m->rel_aux) OKB_FAIL(c, OKB_ERR_ARG, "rel_aux table missing");
+    if (m->model == OKB_TRANSD && !m->ent_aux) OKB_FAIL(c, OKB_ERR_ARG, "ent_aux table missing");
+    return 0;
+}
+
+extern "C" {
+
+int okb_predict(okb_ctx *c, const okb_model *m, const int64_t *h, const int64_t *t, const int64_t *r, INT n, float *out,
+                void *stream) {
+    if (m && m->model == OKB_TRANSR) { extern int okb_transr_predict(okb_ctx *, const okb_model *, const int64_t *, const int64_t *, const int64_t *, INT, float *, void *); return okb_transr_predict(c, m, h, t, r, n, out, stream); }
+    int rc = check_score_model(c, m);
+    if (rc) return rc;
+    if (n <= 0) return 0;
+    PredArgs a;
+    a.m = *m; a.h = h; a.t = t; a.r = r; a.out = out; a.n = n; a.E = (i32)c->E; a.R = (i32)c->R;
+    predict_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    OKB_LAUNCHED(1);
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT cand_lo, INT cand_hi, int64_t *counts,
+             uint64_t *best, void *stream) {
+    if (m && m->model == OKB_TRANSR) { extern int okb_transr_rank(okb_ctx *, const okb_model *, INT, INT, int, INT, INT, int64_t *, uint64_t *, void *); return okb_transr_rank(c, m, q_lo, q_hi, heads, cand_lo, cand_hi, counts, best, stream); }
+    int rc = check_score_model(c, m);
+    if (rc) return rc;
+    if (!c->d_test_h || !c->have_types) OKB_FAIL(c, OKB_ERR_STATE, "import test and type files first");
+    if (q_lo < 0 || q_hi > c->n_test || q_lo > q_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad query range");
+    if (cand_lo < 0 || cand_hi > c->E || cand_lo >= cand_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad candidate range");
+    if (q_lo == q_hi) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int D = m->ent_dim;
+    const i64 j0 = (cand_lo / CT) * CT;
+    const i64 ncol = ((cand_hi - j0 + CT - 1) / CT) * CT;
+    const bool per_group = m->model != OKB_TRANSE;
+
+    // relation groups intersecting [q_lo, q_hi)
+    std::vector<i32> grel, gqlo, gqhi;
+    for (size_t g = 0; g < c->grp_rel.size(); g++) {
+        const i64 lo = std::max<i64>(c->grp_lo[g], q_lo), hi = std::min<i64>(c->grp_hi[g], q_hi);
+        if (lo < hi) { grel.push_back(c->grp_rel[g]); gqlo.push_back((i32)lo); gqhi.push_back((i32)hi); }
+    }
+    // chunk the groups so that candidate tables stay within a memory budget
+    const size_t tab_bytes = sizeof(float) * D * ncol;
+    const size_t budget = (size_t)4 << 30;
+    i64 gmax = per_group ? std::max<i64>(1, (i64)(budget / tab_bytes)) : (i64)grel.size();
+    gmax = std::min<i64>(gmax, 8192);
+    const size_t smem_rank = sizeof(float) * ((size_t)D * CT + ((D + 3) & ~3) + 2 * (size_t)D * QB + QB) + sizeof(i32) * 2 * QB +
+                             sizeof(int4) * QB + sizeof(unsigned) * QB * 8 + sizeof(unsigned long long) * (QB * 8 + 1) + 128;
+    if (smem_rank > 227 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension too large for the ranking tile");
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(qvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_done = true;
+    }
+    const int narr_c = m->model == OKB_TRANSD ? 2 : 1, narr_q = m->model == OKB_TRANSD ? 4 : 2;
+    int wpb_c = 4, wpb_q = 4;
+    while (wpb_c > 1 && sizeof(float) * ((size_t)wpb_c * 32 * (D + 1) * narr_c + D) > 100 * 1024) wpb_c >>= 1;
+    while (wpb_q > 1 && sizeof(float) * (size_t)wpb_q * 32 * (D + 1) * narr_q > 100 * 1024) wpb_q >>= 1;
+    const size_t smem_cand = sizeof(float) * ((size_t)wpb_c * 32 * (D + 1) * narr_c + D);
+    const size_t smem_q = sizeof(float) * (size_t)wpb_q * 32 * (D + 1) * narr_q;
+    if (smem_q > 227 * 1024 || smem_cand > 227 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension too large for the ranking prep kernels");
+
+    for (size_t g0 = 0; g0 < grel.size(); g0 += gmax) {
+        const i64 G = std::min<i64>(gmax, (i64)grel.size() - g0);
+        const i64 cq_lo = gqlo[g0], cq_hi = gqhi[g0 + G - 1], nq = cq_hi - cq_lo;
+        const i64 ntab = per_group ? G : 1;
+        // workspace layout
+        size_t off = 0;
+        auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+        const size_t o_cand = take(tab_bytes * ntab), o_rv = take(sizeof(float) * G * 2 * D), o_qa = take(sizeof(float) * nq * D),
+                     o_qt = take(sizeof(float) * nq * D), o_ref = take(sizeof(float) * nq), o_tf = take((size_t)G * ncol),
+                     o_grel = take(sizeof(i32) * G), o_gqlo = take(sizeof(i32) * G), o_gqhi = take(sizeof(i32) * G),
+                     o_qg = take(sizeof(i32) * nq);
+        if (c->rank_ws.ensure(off)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (ranking workspace)");
+        char *ws = c->rank_ws.as<char>();
+        std::vector<i32> rel_lo(G), rel_hi(G), qg(nq);
+        for (i64 g = 0; g < G; g++) {
+            rel_lo[g] = (i32)(gqlo[g0 + g] - cq_lo); rel_hi[g] = (i32)(gqhi[g0 + g] - cq_lo);
+            for (i32 q = rel_lo[g]; q < rel_hi[g]; q++) qg[q] = (i32)g;
+        }
+        OKB_CUDA(c, cudaMemcpyAsync(ws + o_grel, grel.data() + g0, sizeof(i32) * G, cudaMemcpyHostToDevice, s));
+        OKB_CUDA(c, cudaMemcpyAsync(ws + o_gqlo, rel_lo.data(), sizeof(i32) * G, cudaMemcpyHostToDevice, s));
+        OKB_CUDA(c, cudaMemcpyAsync(ws + o_gqhi, rel_hi.data(), sizeof(i32) * G, cudaMemcpyHostToDevice, s));
+        OKB_CUDA(c, cudaMemcpyAsync(ws + o_qg, qg.data(), sizeof(i32) * nq, cudaMemcpyHostToDevice, s));
+        OKB_CUDA(c, cudaStreamSynchronize(s));            // host vectors above go out of scope
+        OKB_CUDA(c, cudaMemsetAsync(ws + o_tf, 0, (size_t)G * ncol, s));
+
+        relvec_kernel<<<(unsigned)((G + 63) / 64), 64, 0, s>>>(*m, (const i32 *)(ws + o_grel), (float *)(ws + o_rv), (i32)G);
+        CandArgs ca;
+        ca.m = *m; ca.rv = (const float *)(ws + o_rv); ca.out = (float *)(ws + o_cand);
+        ca.j0 = (i32)j0; ca.ncol = (i32)ncol; ca.E = (i32)c->E; ca.ntab = (i32)ntab;
+        cand_kernel<<<dim3((unsigned)(ncol / (32 * wpb_c)), (unsigned)ntab), 32 * wpb_c, smem_cand, s>>>(ca);
+        QArgs qa;
+        qa.m = *m; qa.th = c->d_test_h; qa.tt = c->d_test_t; qa.tr = c->d_test_r; qa.q_group = (const i32 *)(ws + o_qg);
+        qa.rv = (const float *)(ws + o_rv); qa.qa = (float *)(ws + o_qa); qa.qt = (float *)(ws + o_qt); qa.ref = (float *)(ws + o_ref);
+        qa.q_lo = (i32)cq_lo; qa.nq = (i32)nq;
+        qvec_kernel<<<(unsigned)((nq + 32 * wpb_q - 1) / (32 * wpb_q)), 32 * wpb_q, smem_q, s>>>(qa);
+        typeflag_kernel<<<dim3(8, (unsigned)G), 128, 0, s>>>((const i32 *)(ws + o_grel), c->head_type.d_lef, c->head_type.d_rig,
+                                                            c->head_type.d_ids, c->tail_type.d_lef, c->tail_type.d_rig,
+                                                            c->tail_type.d_ids, (unsigned char *)(ws + o_tf), (i32)j0, (i32)ncol);
+        RankArgs ra;
+        ra.cand = (const float *)(ws + o_cand); ra.rv = (const float *)(ws + o_rv);
+        ra.qa = (const float *)(ws + o_qa); ra.qt = (const float *)(ws + o_qt); ra.ref = (const float *)(ws + o_ref);
+        ra.tflag = (const unsigned char *)(ws + o_tf);
+        ra.th = c->d_test_h; ra.tt = c->d_test_t; ra.trun = c->d_test_run; ra.known_t = c->d_known_t; ra.known_h = c->d_known_h;
+        ra.g_qlo = (const i32 *)(ws + o_gqlo); ra.g_qhi = (const i32 *)(ws + o_gqhi);
+        ra.counts = (unsigned long long *)counts + (cq_lo - q_lo) * 8;
+        ra.best = (unsigned long long *)best + (cq_lo - q_lo) * 8;
+        ra.D = D; ra.ncol = (i32)ncol; ra.j0 = (i32)j0; ra.cand_lo = (i32)cand_lo; ra.cand_hi = (i32)cand_hi;
+        ra.q_lo = (i32)cq_lo; ra.model = m->model; ra.tab_per_group = per_group ? 1 : 0;
+        const dim3 grid((unsigned)(ncol / CT), (unsigned)G);
+        if (heads) rank_kernel<true><<<grid, CT, smem_rank, s>>>(ra);
+        else rank_kernel<false><<<grid, CT, smem_rank, s>>>(ra);
+        OKB_LAUNCHED(5);
+        OKB_CUDA(c, cudaGetLastError());
+    }
+    return 0;
+}
+
+int okb_rank_finalize(okb_ctx *c, INT q_lo, INT q_hi, const int64_t *counts, const uint64_t *best, int64_t *out, void *stream) {
+    if (q_lo < 0 || q_hi > c->n_test || q_lo > q_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad query range");
+    if (q_lo == q_hi) return 0;
+    FinArgs a;
+    a.counts = (const unsigned long long *)counts; a.best = (const unsigned long long *)best;
+    a.th = c->d_test_h; a.tt = c->d_test_t;
+    a.has_onto = c->have_onto ? 1 : 0;
+    a.sup_l = c->sup.d_lef; a.sup_r = c->sup.d_rig; a.sup_id = c->sup.d_ids;
+    a.sub_l = c->sub.d_lef; a.sub_r = c->sub.d_rig; a.sub_id = c->sub.d_ids;
+    a.out = out; a.q_lo = (i32)q_lo; a.nq = (i32)(q_hi - q_lo);
+    finalize_kernel<<<(unsigned)((a.nq * 2 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    OKB_LAUNCHED(1);
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int okb_rank_scores(okb_ctx *c, INT index, int side, const float *scores, int64_t *out, void *stream) {
+    if (!c->d_test_h || !c->have_types) OKB_FAIL(c, OKB_ERR_STATE, "import test and type files first");
+    if (index < 0 || index >= c->n_test) OKB_FAIL(c, OKB_ERR_ARG, "test index out of range");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->rank_ws.ensure(1024)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+    unsigned long long *cnt = c->rank_ws.as<unsigned long long>(), *bst = cnt + 8;
+    OKB_CUDA(c, cudaMemsetAsync(cnt, 0, 64, s));
+    OKB_CUDA(c, cudaMemsetAsync(bst, 0xff, 64, s));
+    // this entry point serves ONE (index, side); lay its 4 counters where finalize expects side `side`
+    RankScoresArgs a;
+    a.scores = scores; a.E = (i32)c->E;
+    const i32 h = c->test_h[index], t = c->test_t[index], r = c->test_r[index];
+    a.target = side ? t : h;
+    Lists &L = side ? c->tail_type : c->head_type;
+    a.types = L.d_ids; a.tlo = L.lef[r]; a.thi = L.rig[r];
+    int4 run;
+    OKB_CUDA(c, cudaMemcpy(&run, c->d_test_run + index, sizeof(int4), cudaMemcpyDeviceToHost));
+    a.known = side ? c->d_known_t : c->d_known_h;
+    a.klo = side ? run.x : run.z; a.khi = side ? run.y : run.w;
+    a.counts = cnt + (side ? 4 : 0); a.best = bst + (side ? 4 : 0);
+    rank_scores_kernel<<<148, 256, 0, s>>>(a);
+    OKB_LAUNCHED(1);
+    if (c->host_io.ensure(sizeof(i64) * 16)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+    int rc = okb_rank_finalize(c, index, index + 1, (const int64_t *)cnt, (const uint64_t *)bst, c->host_io.as<i64>(), stream);
+    if (rc) return rc;
+    OKB_CUDA(c, cudaMemcpyAsync(out, c->host_io.as<i64>() + (side ? 8 : 0), sizeof(i64) * 8, cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,656 @@
+// Fused train step for TransE / TransH / TransD: the reference's loss_def graphs
+// (TransE.py:26-51, TransH.py:33-69, TransD.py:46-84 on the batch layout of Model.py:55-74)
+// plus optimizer.minimize (distribute_training.py:94-101), as three phases:
+//
+//   plan   (integer)  gradient-row keys of the batch -> stable radix sort -> (sorted keys, perm)
+//   grad   (fused)    one warp per positive: 128-bit gathers of the h/t/r rows (+ the model's
+//                     auxiliary rows), projection, l2-normalise, L1, margin hinge against each of
+//                     its negatives, and the backward pass; rows shared between a positive and its
+//                     negatives (the uncorrupted side and the relation) are gathered ONCE and their
+//                     gradients are accumulated in registers, so a positive group emits exactly
+//                     (2 + k) entity gradient rows and (1 + kr) relation gradient rows
+//   update (fused)    one warp per distinct table row: sum its gradient rows in sorted (slot) order
+//                     — a fixed fp32 order, so runs and replicas are bit-identical — and apply SGD
+//                     or the TF1 sparse-Adam rule in the same pass
+//
+// Roofline: HBM-bound gather/scatter of fp32 rows; no dense contraction, so no tensor cores here
+// (TransR's projection lives in transr.cu).
+#include "okb_internal.h"
+
+#define FULL 0xffffffffu
+#define WARPS_PER_BLOCK 4
+
+// ------------------------------------------------------------------------------------------ plan
+struct PlanArgs {
+    const i32 *bh, *bt, *br;   // plane-major batch
+    i32 *keys;                 // [B*NE + B*NR]
+    i32 B, k, kr, NE, NR, E, R;
+};
+// Combined key space: entity row e -> e, relation row r -> E + r, unused slot -> E + R.
+__global__ void plan_keys_kernel(PlanArgs a) {
+    const i32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
+    i32 *ke = a.keys + (i64)b * a.NE;
+    i32 *kr_ = a.keys + (i64)a.B * a.NE + (i64)b * a.NR;
+    const i32 none = a.E + a.R;
+    ke[0] = ph; ke[1] = pt; kr_[0] = a.E + pr;
+    for (i32 m = 0; m < a.k; m++) {
+        const i32 at = b + (m + 1) * a.B;
+        const i32 nh = a.bh[at], nt = a.bt[at];
+        ke[2 + m] = nh != ph ? nh : (nt != pt ? nt : none);
+    }
+    for (i32 m = 0; m < a.kr; m++) {
+        const i32 nr = a.br[b + (1 + a.k + m) * a.B];
+        kr_[1 + m] = nr != pr ? a.E + nr : none;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ row fragments
+// A row of D floats is spread over a warp: lane l holds NV vectors of VW floats, vector i covering
+// elements [(i*32 + l)*VW, +VW).  VW = 4 gives the 128-bit gathers; D % VW == 0 is required.
+template <int VW> struct VecT;
+template <> struct VecT<4> { typedef float4 T; };
+template <> struct VecT<2> { typedef float2 T; };
+template <> struct VecT<1> { typedef float T; };
+
+template <int VW, int NV> struct Frag {
+    float v[VW * NV];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < VW * NV; i++) v[i] = 0.f;
+    }
+    __device__ __forceinline__ void load(const float *__restrict__ row, int D, int lane) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int e = (i * 32 + lane) * VW;
+            if (e < D) {
+                typename VecT<VW>::T x = *reinterpret_cast<const typename VecT<VW>::T *>(row + e);
+                const float *xs = reinterpret_cast<const float *>(&x);
+#pragma unroll
+                for (int j = 0; j < VW; j++) v[i * VW + j] = xs[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < VW; j++) v[i * VW + j] = 0.f;
+            }
+        }
+    }
+    __device__ __forceinline__ void store(float *__restrict__ row, int D, int lane) const {
+#pragma unroll
+        for (int i = 0; i < NV; i++) {
+            const int e = (i * 32 + lane) * VW;
+            if (e < D) {
+                typename VecT<VW>::T x;
+                float *xs = reinterpret_cast<float *>(&x);
+#pragma unroll
+                for (int j = 0; j < VW; j++) xs[j] = v[i * VW + j];
+                *reinterpret_cast<typename VecT<VW>::T *>(row + e) = x;
+            }
+        }
+    }
+};
+
+__device__ __forceinline__ float wsum(float x) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ void wsum2(float &a, float &b) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); }
+}
+__device__ __forceinline__ void wsum3(float &a, float &b, float &c) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        a += __shfl_xor_sync(FULL, a, o); b += __shfl_xor_sync(FULL, b, o); c += __shfl_xor_sync(FULL, c, o);
+    }
+}
+#define FOR_N for (int i = 0; i < N; i++)
+
+template <int N> __device__ __forceinline__ float dot(const float *a, const float *b) {
+    float s = 0.f;
+#pragma unroll
+    FOR_N s = fmaf(a[i], b[i], s);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------ model pieces
+// Relation-side state of one triple.
+template <int MODEL, int N> struct RelS {
+    float rhat[N];      // l2n(rel_embeddings[r])
+    float inv;          // rsqrt(max(|r|^2, 1e-12))
+    bool proj;          // |r|^2 > 1e-12 (normalisation differentiates through the norm)
+    float aux[N];       // TransH: n_hat = l2n(normal_vectors[r]);  TransD: rel_transfer[r]
+    float inv_n;        // TransH only
+    bool proj_n;
+};
+// Entity-side state of one (entity, relation) pair.
+template <int MODEL, int N> struct EntS {
+    float raw[N];       // ent_embeddings[e]
+    float aux[N];       // TransD: ent_transfer[e]
+    float hat[N];       // l2n(transfer(e))
+    float inv, a;       // a = e.n_hat (TransH) / e.e_t (TransD)
+    bool proj;
+};
+
+#define EPS_NORM 1e-12f
+
+template <int MODEL, int VW, int NV>
+__device__ __forceinline__ void rel_forward(RelS<MODEL, VW * NV> &R, const okb_model &m, i32 r, int lane) {
+    constexpr int N = VW * NV;
+    const int D = m.rel_dim;
+    Frag<VW, NV> f;
+    f.load(m.rel + (i64)r * D, D, lane);
+    float ss = wsum(dot<N>(f.v, f.v));
+    R.proj = ss > EPS_NORM;
+    R.inv = rsqrtf(fmaxf(ss, EPS_NORM));
+#pragma unroll
+    FOR_N R.rhat[i] = f.v[i] * R.inv;
+    if (MODEL == OKB_TRANSH) {
+        f.load(m.rel_aux + (i64)r * D, D, lane);
+        float sn = wsum(dot<N>(f.v, f.v));
+        R.proj_n = sn > EPS_NORM;
+        R.inv_n = rsqrtf(fmaxf(sn, EPS_NORM));
+#pragma unroll
+        FOR_N R.aux[i] = f.v[i] * R.inv_n;
+    } else if (MODEL == OKB_TRANSD) {
+        f.load(m.rel_aux + (i64)r * D, D, lane);
+#pragma unroll
+        FOR_N R.aux[i] = f.v[i];
+    }
+}
+
+template <int MODEL, int VW, int NV>
+__device__ __forceinline__ void ent_forward(EntS<MODEL, VW * NV> &S, const RelS<MODEL, VW * NV> &R, const okb_model &m,
+                                            i32 e, int lane) {
+    constexpr int N = VW * NV;
+    const int D = m.ent_dim;
+    Frag<VW, NV> f;
+    f.load(m.ent + (i64)e * D, D, lane);
+#pragma unroll
+    FOR_N S.raw[i] = f.v[i];
+    float p[N];
+    if (MODEL == OKB_TRANSE) {
+#pragma unroll
+        FOR_N p[i] = S.raw[i];
+        S.a = 0.f;
+    } else if (MODEL == OKB_TRANSH) {                      // TransH.py:12-14: e - (e.n_hat) n_hat
+        S.a = wsum(dot<N>(S.raw, R.aux));
+#pragma unroll
+        FOR_N p[i] = S.raw[i] - S.a * R.aux[i];
+    } else {                                               // TransD.py:23-25: e + (e.e_t) r_t
+        f.load(m.ent_aux + (i64)e * D, D, lane);
+#pragma unroll
+        FOR_N S.aux[i] = f.v[i];
+        S.a = wsum(dot<N>(S.raw, S.aux));
+#pragma unroll
+        FOR_N p[i] = S.raw[i] + S.a * R.aux[i];
+    }
+    float ss = wsum(dot<N>(p, p));
+    S.proj = ss > EPS_NORM;
+    S.inv = rsqrtf(fmaxf(ss, EPS_NORM));
+#pragma unroll
+    FOR_N S.hat[i] = p[i] * S.inv;
+}
+
+// score = sum_d |h_hat + r_hat - t_hat| (association as in TransE.py:15); g = sign of the summand
+template <int MODEL, int N>
+__device__ __forceinline__ float score_fw(const EntS<MODEL, N> &H, const EntS<MODEL, N> &T, const RelS<MODEL, N> &R, float *g) {
+    float s = 0.f;
+#pragma unroll
+    FOR_N {
+        const float u = (H.hat[i] + R.rhat[i]) - T.hat[i];
+        s += fabsf(u);
+        g[i] = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);       // tf.abs gradient: sign(u), 0 at 0
+    }
+    return wsum(s);
+}
+
+// Gradient accumulators of one table-row group: part 0 = main table, part 1 = auxiliary table.
+template <int MODEL, int N> struct EntG {
+    float d[N];
+    float da[MODEL == OKB_TRANSD ? N : 1];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        FOR_N d[i] = 0.f;
+        if (MODEL == OKB_TRANSD) {
+#pragma unroll
+            FOR_N da[i] = 0.f;
+        }
+    }
+};
+template <int MODEL, int N> struct RelG {
+    float d[N];
+    float da[MODEL == OKB_TRANSE ? 1 : N];
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        FOR_N d[i] = 0.f;
+        if (MODEL != OKB_TRANSE) {
+#pragma unroll
+            FOR_N da[i] = 0.f;
+        }
+    }
+};
+
+// Backward of c * score(H, T, R) into the three accumulators.
+template <int MODEL, int N>
+__device__ __forceinline__ void score_bw(const EntS<MODEL, N> &H, const EntS<MODEL, N> &T, const RelS<MODEL, N> &R,
+                                         const float *g, float c, EntG<MODEL, N> &gh, EntG<MODEL, N> &gt, RelG<MODEL, N> &gr) {
+    // through l2_normalize: gx = inv * (gy - y_hat (gy . y_hat))   [no projection term when clamped]
+    float d1 = dot<N>(g, H.hat), d2 = dot<N>(g, T.hat), d3 = dot<N>(g, R.rhat);
+    wsum3(d1, d2, d3);
+    if (!H.proj) d1 = 0.f;
+    if (!T.proj) d2 = 0.f;
+    if (!R.proj) d3 = 0.f;
+    float GH[N], GT[N];
+#pragma unroll
+    FOR_N {
+        GH[i] = H.inv * (g[i] - H.hat[i] * d1);
+        GT[i] = -T.inv * (g[i] - T.hat[i] * d2);
+        gr.d[i] += c * (R.inv * (g[i] - R.rhat[i] * d3));
+    }
+    if (MODEL == OKB_TRANSE) {
+#pragma unroll
+        FOR_N { gh.d[i] += c * GH[i]; gt.d[i] += c * GT[i]; }
+    } else if (MODEL == OKB_TRANSH) {
+        // e' = e - (e.n) n  =>  de = G - n (n.G);  dn_hat = -[(e.n) G + (G.n) e]
+        float bh = dot<N>(GH, R.aux), bt = dot<N>(GT, R.aux);
+        wsum2(bh, bt);
+        float dn[N];
+#pragma unroll
+        FOR_N {
+            gh.d[i] += c * (GH[i] - R.aux[i] * bh);
+            gt.d[i] += c * (GT[i] - R.aux[i] * bt);
+            dn[i] = -(H.a * GH[i] + bh * H.raw[i] + T.a * GT[i] + bt * T.raw[i]);
+        }
+        float d4 = wsum(dot<N>(dn, R.aux));
+        if (!R.proj_n) d4 = 0.f;
+#pragma unroll
+        FOR_N gr.da[i] += c * (R.inv_n * (dn[i] - R.aux[i] * d4));
+    } else {
+        // e' = e + (e.e_t) r_t  =>  de = G + (G.r_t) e_t;  de_t = (G.r_t) e;  dr_t = (e.e_t) G
+        float bh = dot<N>(GH, R.aux), bt = dot<N>(GT, R.aux);
+        wsum2(bh, bt);
+#pragma unroll
+        FOR_N {
+            gh.d[i] += c * (GH[i] + bh * H.aux[i]);
+            gh.da[i] += c * (bh * H.raw[i]);
+            gt.d[i] += c * (GT[i] + bt * T.aux[i]);
+            gt.da[i] += c * (bt * T.raw[i]);
+            gr.da[i] += c * (H.a * GH[i] + T.a * GT[i]);
+        }
+    }
+}
+
+template <int VW, int NV> __device__ __forceinline__ void put(float *dst, const float *src, int D, int lane) {
+    Frag<VW, NV> f;
+#pragma unroll
+    for (int i = 0; i < VW * NV; i++) f.v[i] = src[i];
+    f.store(dst, D, lane);
+}
+template <int MODEL, int VW, int NV>
+__device__ __forceinline__ void put_ent(float *row, const EntG<MODEL, VW * NV> &g, int D, int lane) {
+    put<VW, NV>(row, g.d, D, lane);
+    if (MODEL == OKB_TRANSD) put<VW, NV>(row + D, g.da, D, lane);
+}
+template <int MODEL, int VW, int NV>
+__device__ __forceinline__ void put_rel(float *row, const RelG<MODEL, VW * NV> &g, int D, int lane) {
+    put<VW, NV>(row, g.d, D, lane);
+    if (MODEL != OKB_TRANSE) put<VW, NV>(row + D, g.da, D, lane);
+}
+
+struct GradArgs {
+    okb_model m;
+    const i32 *bh, *bt, *br;
+    float *gent, *grel, *loss_terms;
+    float margin, w;           // w = 1 / (B * (k + kr))   (reduce_mean, TransE.py:51)
+    i32 B, k, kr, NE, NR, b_lo, b_hi;
+};
+
+// ------------------------------------------------------------------------------------------ grad
+template <int MODEL, int VW, int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) grad_kernel(GradArgs a) {
+    constexpr int N = VW * NV;
+    const int lane = threadIdx.x & 31;
+    const i32 b = a.b_lo + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (b >= a.b_hi) return;
+    const int D = a.m.ent_dim;
+    const int ce = MODEL == OKB_TRANSD ? 2 * D : D, cr = MODEL == OKB_TRANSE ? D : 2 * D;
+    const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
+
+    RelS<MODEL, N> Rp;
+    EntS<MODEL, N> Hp, Tp;
+    rel_forward<MODEL, VW, NV>(Rp, a.m, pr, lane);
+    ent_forward<MODEL, VW, NV>(Hp, Rp, a.m, ph, lane);
+    ent_forward<MODEL, VW, NV>(Tp, Rp, a.m, pt, lane);
+    float gp[N];
+    const float sp = score_fw<MODEL, N>(Hp, Tp, Rp, gp);
+
+    EntG<MODEL, N> accH, accT;
+    RelG<MODEL, N> accR;
+    accH.zero(); accT.zero(); accR.zero();
+    float *ge = a.gent + (i64)b * a.NE * ce, *gr = a.grel + (i64)b * a.NR * cr;
+    float hinge_sum = 0.f;
+    i32 active = 0;
+
+    for (i32 m = 0; m < a.k; m++) {                        // entity negatives (Base.cpp:113-131)
+        const i32 at = b + (m + 1) * a.B;
+        const i32 nh = a.bh[at], nt = a.bt[at];
+        EntG<MODEL, N> gnew;
+        gnew.zero();
+        float gn[N];
+        if (nh != ph) {                                    // head replaced; (t, r) rows shared
+            EntS<MODEL, N> Hn;
+            ent_forward<MODEL, VW, NV>(Hn, Rp, a.m, nh, lane);
+            const float sn = score_fw<MODEL, N>(Hn, Tp, Rp, gn);
+            const float x = sp - sn + a.margin;
+            if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hn, Tp, Rp, gn, -a.w, gnew, accT, accR); }
+        } else if (nt != pt) {                             // tail replaced; (h, r) rows shared
+            EntS<MODEL, N> Tn;
+            ent_forward<MODEL, VW, NV>(Tn, Rp, a.m, nt, lane);
+            const float sn = score_fw<MODEL, N>(Hp, Tn, Rp, gn);
+            const float x = sp - sn + a.margin;
+            if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tn, Rp, gn, -a.w, accH, gnew, accR); }
+        } else {                                           // degenerate: negative == positive
+            const float x = a.margin;
+            if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rp, gp, -a.w, accH, accT, accR); }
+        }
+        put_ent<MODEL, VW, NV>(ge + (i64)(2 + m) * ce, gnew, D, lane);
+    }
+    for (i32 m = 0; m < a.kr; m++) {                       // relation negatives (Base.cpp:133-139)
+        const i32 nr = a.br[b + (1 + a.k + m) * a.B];
+        RelG<MODEL, N> gnew;
+        gnew.zero();
+        float gn[N];
+        if (nr != pr) {
+            RelS<MODEL, N> Rn;
+            rel_forward<MODEL, VW, NV>(Rn, a.m, nr, lane);
+            if (MODEL == OKB_TRANSE) {
+                const float sn = score_fw<MODEL, N>(Hp, Tp, Rn, gn);
+                const float x = sp - sn + a.margin;
+                if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rn, gn, -a.w, accH, accT, gnew); }
+            } else {                                       // projections depend on the relation: redo both sides
+                EntS<MODEL, N> Hn, Tn;
+                ent_forward<MODEL, VW, NV>(Hn, Rn, a.m, ph, lane);
+                ent_forward<MODEL, VW, NV>(Tn, Rn, a.m, pt, lane);
+                const float sn = score_fw<MODEL, N>(Hn, Tn, Rn, gn);
+                const float x = sp - sn + a.margin;
+                if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hn, Tn, Rn, gn, -a.w, accH, accT, gnew); }
+            }
+        } else {
+            const float x = a.margin;
+            if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rp, gp, -a.w, accH, accT, accR); }
+        }
+        put_rel<MODEL, VW, NV>(gr + (i64)(1 + m) * cr, gnew, D, lane);
+    }
+    if (active) score_bw<MODEL, N>(Hp, Tp, Rp, gp, a.w * (float)active, accH, accT, accR);
+    put_ent<MODEL, VW, NV>(ge, accH, D, lane);
+    put_ent<MODEL, VW, NV>(ge + ce, accT, D, lane);
+    put_rel<MODEL, VW, NV>(gr, accR, D, lane);
+    if (lane == 0) a.loss_terms[b] = hinge_sum;
+}
+
+// ------------------------------------------------------------------------------------------ update
+struct UpdArgs {
+    okb_model m;
+    okb_hyper hp;
+    const i32 *skeys, *perm;   // sorted keys / slot of each sorted position
+    const float *gent, *grel;
+    i32 *rowseg;               // Adam: first sorted position of each table row, -1 if untouched
+    i32 n, n_ent_slots, E, R, ce, cr;
+};
+
+// Sum the gradient rows of the segment starting at sorted position `i` (fixed slot order).
+template <int VW, int NV>
+__device__ __forceinline__ void seg_sum(const UpdArgs &a, i32 i, i32 key, bool is_ent, int D, int part, int lane, float *acc) {
+    constexpr int N = VW * NV;
+#pragma unroll
+    FOR_N acc[i] = 0.f;
+    const i32 cols = is_ent ? a.ce : a.cr;
+    for (i32 j = i; j < a.n && a.skeys[j] == key; j++) {
+        const i32 slot = a.perm[j];
+        const float *row = is_ent ? a.gent + (i64)slot * cols : a.grel + (i64)(slot - a.n_ent_slots) * cols;
+        Frag<VW, NV> f;
+        f.load(row + part * D, D, lane);
+#pragma unroll
+        for (int q = 0; q < N; q++) acc[q] += f.v[q];
+    }
+}
+
+// SGD: one warp per sorted position; only segment heads work.  row -= lr * sum  (sparse apply).
+template <int VW, int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
+    constexpr int N = VW * NV;
+    const int lane = threadIdx.x & 31;
+    const i32 i = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (i >= a.n) return;
+    const i32 key = a.skeys[i];
+    if (key >= a.E + a.R || (i > 0 && a.skeys[i - 1] == key)) return;
+    const bool is_ent = key < a.E;
+    const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
+    const i32 row = is_ent ? key : key - a.E;
+    const int parts = (is_ent ? a.ce : a.cr) / D;
+    for (int p = 0; p < parts; p++) {
+        float acc[N];
+        seg_sum<VW, NV>(a, i, key, is_ent, D, p, lane, acc);
+        float *tab = is_ent ? (p ? a.m.ent_aux : a.m.ent) : (p ? a.m.rel_aux : a.m.rel);
+        Frag<VW, NV> f;
+        f.load(tab + (i64)row * D, D, lane);
+#pragma unroll
+        for (int q = 0; q < N; q++) f.v[q] -= a.hp.lr * acc[q];
+        f.store(tab + (i64)row * D, D, lane);
+    }
+}
+
+__global__ void mark_heads_kernel(const i32 *__restrict__ skeys, i32 *__restrict__ rowseg, i32 n, i32 rows) {
+    const i32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const i32 key = skeys[i];
+    if (key < rows && (i == 0 || skeys[i - 1] != key)) rowseg[key] = i;
+}
+
+// TF1 AdamOptimizer._apply_sparse_shared: m and v decay over the WHOLE variable and the variable
+// moves everywhere each step; only the (1-beta)*g terms are sparse.  One warp per table row.
+template <int VW, int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) adam_kernel(UpdArgs a) {
+    constexpr int N = VW * NV;
+    const int lane = threadIdx.x & 31;
+    const i32 key = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (key >= a.E + a.R) return;
+    const bool is_ent = key < a.E;
+    const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
+    const i32 row = is_ent ? key : key - a.E;
+    const int parts = (is_ent ? a.ce : a.cr) / D;
+    const i32 seg = a.rowseg[key];
+    const float b1 = a.hp.beta1, b2 = a.hp.beta2;
+    for (int p = 0; p < parts; p++) {
+        float g[N];
+        if (seg >= 0) seg_sum<VW, NV>(a, seg, key, is_ent, D, p, lane, g);
+        else {
+#pragma unroll
+            for (int q = 0; q < N; q++) g[q] = 0.f;
+        }
+        float *tab = is_ent ? (p ? a.m.ent_aux : a.m.ent) : (p ? a.m.rel_aux : a.m.rel);
+        float *mt = is_ent ? (p ? a.m.m_ent_aux : a.m.m_ent) : (p ? a.m.m_rel_aux : a.m.m_rel);
+        float *vt = is_ent ? (p ? a.m.v_ent_aux : a.m.v_ent) : (p ? a.m.v_rel_aux : a.m.v_rel);
+        Frag<VW, NV> x, mm, vv;
+        const i64 off = (i64)row * D;
+        x.load(tab + off, D, lane); mm.load(mt + off, D, lane); vv.load(vt + off, D, lane);
+#pragma unroll
+        for (int q = 0; q < N; q++) {
+            const float mq = mm.v[q] * b1 + g[q] * (1.f - b1);
+            const float vq = vv.v[q] * b2 + (g[q] * g[q]) * (1.f - b2);
+            mm.v[q] = mq; vv.v[q] = vq;
+            x.v[q] -= a.hp.lr * mq / (sqrtf(vq) + a.hp.eps);
+        }
+        x.store(tab + off, D, lane); mm.store(mt + off, D, lane); vv.store(vt + off, D, lane);
+    }
+    __syncwarp();
+    if (lane == 0 && seg >= 0) a.rowseg[key] = -1;
+}
+
+// mean hinge over B*(k+kr) pairs, fixed summation order (one block)
+__global__ void __launch_bounds__(1024) loss_kernel(const float *__restrict__ terms, float *__restrict__ out, i32 B, float w) {
+    __shared__ float sh[32];
+    float s = 0.f;
+    for (i32 i = threadIdx.x; i < B; i += 1024) s += terms[i];
+    s = wsum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = wsum(sh[threadIdx.x]);
+        if (threadIdx.x == 0) out[0] = s * w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ dispatch
+// Lane layout for a row of D floats: the widest vector (<= 128 bit) dividing D that still keeps
+// most lanes busy, and 1, 2 or 4 vectors per lane (D <= 512 for D % 4 == 0).
+bool okb_pick_layout(int D, int &vw, int &nv) {
+    vw = (D % 4 == 0 && D > 64) ? 4 : ((D % 2 == 0 && D > 32) ? 2 : 1);
+    for (;;) {
+        int n = (D + 32 * vw - 1) / (32 * vw);
+        nv = n <= 1 ? 1 : (n <= 2 ? 2 : 4);
+        if (n <= 4) return true;
+        if (vw < 4 && D % (vw * 2) == 0) vw *= 2; else return false;
+    }
+}
+
+#define DISPATCH_LAYOUT(vw, nv, CALL)                                                    \
+    do {                                                                                 \
+        if (vw == 4 && nv == 1) { CALL(4, 1); } else if (vw == 4 && nv == 2) { CALL(4, 2); } \
+        else if (vw == 4 && nv == 4) { CALL(4, 4); } else if (vw == 2 && nv == 1) { CALL(2, 1); } \
+        else if (vw == 2 && nv == 2) { CALL(2, 2); } else if (vw == 2 && nv == 4) { CALL(2, 4); } \
+        else if (vw == 1 && nv == 1) { CALL(1, 1); } else if (vw == 1 && nv == 2) { CALL(1, 2); } \
+        else { CALL(1, 4); }                                                             \
+    } while (0)
+
+static int check_model(okb_ctx *c, const okb_model *m, int &vw, int &nv) {
+    if (!m || !m->ent || !m->rel) OKB_FAIL(c, OKB_ERR_ARG, "model tables missing");
+    if (m->model == OKB_TRANSR) OKB_FAIL(c, OKB_ERR_ARG, "TransR is handled by transr.cu");
+    if (m->model != OKB_TRANSE && m->model != OKB_TRANSH && m->model != OKB_TRANSD) OKB_FAIL(c, OKB_ERR_ARG, "unknown model");
+    if (m->ent_dim != m->rel_dim) OKB_FAIL(c, OKB_ERR_ARG, "TransE/H/D need ent_dim == rel_dim");
+    if (m->model != OKB_TRANSE && !m->rel_aux) OKB_FAIL(c, OKB_ERR_ARG, "rel_aux table missing");
+    if (m->model == OKB_TRANSD && !m->ent_aux) OKB_FAIL(c, OKB_ERR_ARG, "ent_aux table missing");
+    if (!okb_pick_layout(m->ent_dim, vw, nv)) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension not supported (need D <= 512 with D % 4 == 0, D <= 256 even, or D <= 128)");
+    return 0;
+}
+static void group_cols(const okb_model *m, i32 &ce, i32 &cr) {
+    ce = m->model == OKB_TRANSD ? 2 * m->ent_dim : m->ent_dim;
+    cr = m->model == OKB_TRANSE ? m->rel_dim : 2 * m->rel_dim;
+}
+
+extern "C" {
+
+int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT B, INT k, INT kr, INT *er, INT *ec, INT *rr, INT *rc) {
+    if (m->model == OKB_TRANSR) { extern int okb_transr_grad_sizes(okb_ctx *, const okb_model *, INT, INT, INT, INT *, INT *, INT *, INT *); return okb_transr_grad_sizes(c, m, B, k, kr, er, ec, rr, rc); }
+    i32 ce, cr;
+    group_cols(m, ce, cr);
+    *er = B * (2 + k); *ec = ce; *rr = B * (1 + kr); *rc = cr;
+    return 0;
+}
+
+int okb_plan(okb_ctx *c, INT step, void *stream) {
+    if (step < 0 || step >= c->steps) OKB_FAIL(c, OKB_ERR_ARG, "step out of range (sample first)");
+    cudaStream_t s = (cudaStream_t)stream;
+    const i64 B = c->B, NE = 2 + c->K, NR = 1 + c->KR, n = B * (NE + NR), S = B * (1 + c->K + c->KR);
+    if (c->keys_ent.ensure(sizeof(i32) * n * 2) || c->perm_ent.ensure(sizeof(i32) * n))
+        OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (plan)");
+    PlanArgs a;
+    const i32 *base = c->batch.as<i32>() + step * 3 * S;
+    a.bh = base; a.bt = base + S; a.br = base + 2 * S;
+    a.keys = c->keys_ent.as<i32>();
+    a.B = (i32)B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)NE; a.NR = (i32)NR; a.E = (i32)c->E; a.R = (i32)c->R;
+    plan_keys_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a);
+    OKB_LAUNCHED(1);
+    c->plan_ne = B * NE; c->plan_nr = B * NR;
+    c->ent_bits = bits_for(c->E + c->R + 1);
+    return okb_sort_pairs(c, a.keys, a.keys + n, c->perm_ent.as<i32>(), n, c->ent_bits, s);
+}
+
+int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, float *gent, float *grel,
+             float *loss_terms, void *stream) {
+    if (m->model == OKB_TRANSR) { extern int okb_transr_grad(okb_ctx *, const okb_model *, const okb_hyper *, INT, INT, INT, float *, float *, float *, void *); return okb_transr_grad(c, m, hp, step, b_lo, b_hi, gent, grel, loss_terms, stream); }
+    int vw, nv;
+    int rc = check_model(c, m, vw, nv);
+    if (rc) return rc;
+    if (step < 0 || step >= c->steps) OKB_FAIL(c, OKB_ERR_ARG, "step out of range (sample first)");
+    if (b_lo < 0 || b_hi > c->B || b_lo > b_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad positive range");
+    if (b_lo == b_hi) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const i64 S = c->B * (1 + c->K + c->KR);
+    GradArgs a;
+    a.m = *m;
+    const i32 *base = c->batch.as<i32>() + step * 3 * S;
+    a.bh = base; a.bt = base + S; a.br = base + 2 * S;
+    a.gent = gent; a.grel = grel; a.loss_terms = loss_terms;
+    a.margin = hp->margin; a.w = 1.0f / (float)(c->B * (c->K + c->KR));
+    a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)(2 + c->K); a.NR = (i32)(1 + c->KR);
+    a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi;
+    const unsigned grid = (unsigned)((b_hi - b_lo + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+#define CALL_GRAD(VW, NV)                                                                              \
+    if (m->model == OKB_TRANSE) grad_kernel<OKB_TRANSE, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a);      \
+    else if (m->model == OKB_TRANSH) grad_kernel<OKB_TRANSH, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a); \
+    else grad_kernel<OKB_TRANSD, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
+    DISPATCH_LAYOUT(vw, nv, CALL_GRAD);
+    OKB_LAUNCHED(1);
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
+               const float *loss_terms, float *loss_out, void *stream) {
+    (void)step;
+    if (m->model == OKB_TRANSR) { extern int okb_transr_update(okb_ctx *, const okb_model *, const okb_hyper *, const float *, const float *, const float *, float *, void *); return okb_transr_update(c, m, hp, gent, grel, loss_terms, loss_out, stream); }
+    int vw, nv;
+    int rc = check_model(c, m, vw, nv);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const i64 n = c->plan_ne + c->plan_nr;
+    if (n == 0) OKB_FAIL(c, OKB_ERR_STATE, "okb_plan has not run");
+    UpdArgs a;
+    a.m = *m; a.hp = *hp;
+    a.skeys = c->keys_ent.as<i32>() + n; a.perm = c->perm_ent.as<i32>();
+    a.gent = gent; a.grel = grel;
+    a.n = (i32)n; a.n_ent_slots = (i32)c->plan_ne; a.E = (i32)c->E; a.R = (i32)c->R;
+    group_cols(m, a.ce, a.cr);
+    a.rowseg = nullptr;
+    if (m->optimizer == OKB_ADAM) {
+        if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
+        const i64 rows = c->E + c->R;
+        const bool fresh = c->rowseg_e.cap < sizeof(i32) * rows;
+        if (c->rowseg_e.ensure(sizeof(i32) * rows)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowseg)");
+        if (fresh) OKB_CUDA(c, cudaMemsetAsync(c->rowseg_e.p, 0xff, c->rowseg_e.cap, s));
+        a.rowseg = c->rowseg_e.as<i32>();
+        mark_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.skeys, a.rowseg, a.n, (i32)rows);
+        const unsigned grid = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+#define CALL_ADAM(VW, NV) adam_kernel<VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
+        DISPATCH_LAYOUT(vw, nv, CALL_ADAM);
+        OKB_LAUNCHED(2);
+    } else {
+        const unsigned grid = (unsigned)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+#define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
+        DISPATCH_LAYOUT(vw, nv, CALL_SGD);
+        OKB_LAUNCHED(1);
+    }
+    if (loss_out) {
+        loss_kernel<<<1, 1024, 0, s>>>(loss_terms, loss_out, (i32)c->B, 1.0f / (float)(c->B * (c->K + c->KR)));
+        OKB_LAUNCHED(1);
+    }
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, float *loss_out, void *stream) {
+    INT er, ec, rr, rcn;
+    int rc = okb_grad_sizes(c, m, c->B, c->K, c->KR, &er, &ec, &rr, &rcn);
+    if (rc) return rc;
+    if (c->gent.ensure(sizeof(float) * er * ec) || c->grel.ensure(sizeof(float) * rr * rcn) ||
+        c->lossterms.ensure(sizeof(float) * c->B))
+        OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (gradient rows)");
+    if ((rc = okb_plan(c, step, stream))) return rc;
+    if ((rc = okb_grad(c, m, hp, step, 0, c->B, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), stream))) return rc;
+    return okb_update(c, m, hp, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), loss_out, stream);
+}
+
+}  // extern "C"
