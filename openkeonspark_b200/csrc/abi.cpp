@@ -51,6 +51,8 @@ int okb_destroy(okb_ctx *c) {
 }
 const char *okb_last_error(okb_ctx *c) { return c ? c->err.c_str() : "null context"; }
 int okb_set_device(okb_ctx *c, int device) { OKB_CUDA(c, cudaSetDevice(device)); return 0; }
+// debugging aid: returns (and clears) the CUDA runtime's last error of this library's runtime instance
+const char *okb_debug_cuda_error(void) { return cudaGetErrorString(cudaGetLastError()); }
 
 // ------------------------------------------------------------------ reference-compatible layer
 void setInPath(char *path) {
@@ -66,15 +68,15 @@ void setBern(INT con) { okb_set_bern(g_ctx_get(), con); }
 INT getEntityTotal(void) { return g_ctx_get()->E; }
 INT getRelationTotal(void) { return g_ctx_get()->R; }
 INT getTripleTotal(void) { return g_ctx_get()->n_all; }
-INT getTrainTotal(void) { return g_ctx_get()->n; }
+INT getTrainTotal(void) { okb_ctx *c = g_ctx_get(); return c->legacy_train_total >= 0 ? c->legacy_train_total : c->n; }
 INT getTrainTotal_(void) { return g_ctx_get()->n_raw; }
 INT getBatchTotal(void) { return g_ctx_get()->new_batch; }
 INT getTestTotal(void) { return g_ctx_get()->n_test; }
 INT getValidTotal(void) { return g_ctx_get()->n_valid; }
 void randReset(void) { MUST(okb_rand_reset(g_ctx_get()), "randReset"); }
 // Reader.h:36-39: a missing file prints a message and returns, leaving the totals at 0.
-void importTrainFiles(void) { int rc = okb_import_train_files(g_ctx_get()); if (rc && rc != OKB_ERR_IO) die(g_ctx_get(), "importTrainFiles"); }
-void importTestFiles(void) { int rc = okb_import_test_files(g_ctx_get()); if (rc && rc != OKB_ERR_IO) die(g_ctx_get(), "importTestFiles"); }
+void importTrainFiles(void) { int rc = okb_import_train_files(g_ctx_get()); g_ctx_get()->legacy_train_total = -1; if (rc && rc != OKB_ERR_IO) die(g_ctx_get(), "importTrainFiles"); }
+void importTestFiles(void) { int rc = okb_import_test_files(g_ctx_get()); if (!rc) g_ctx_get()->legacy_train_total = g_ctx_get()->n_raw; if (rc && rc != OKB_ERR_IO) die(g_ctx_get(), "importTestFiles"); }
 void importTypeFiles(void) { int rc = okb_import_type_files(g_ctx_get()); if (rc && rc != OKB_ERR_IO) die(g_ctx_get(), "importTypeFiles"); }
 void importOntologyFiles(void) { int rc = okb_import_ontology_files(g_ctx_get()); if (rc && rc != OKB_ERR_IO) die(g_ctx_get(), "importOntologyFiles"); }
 

@@ -399,13 +399,11 @@ int okb_import_type_files(okb_ctx *c) {
 }
 int okb_import_ontology_files(okb_ctx *c) {
     printf("Reading %sontology_constrain.txt\n", c->in_path.c_str());
-    c->sup.lef.assign(c->E, 0); c->sup.rig.assign(c->E, 0); c->sup.ids.clear();
-    c->sub = c->sup;
+    auto clear = [&](Lists &L) { L.lef.assign(c->E, 0); L.rig.assign(c->E, 0); L.ids.clear(); };
+    clear(c->sup); clear(c->sub);
     int rc = read_lists(c, c->in_path + "ontology_constrain.txt", c->E, true, c->sup, c->sub);
-    if (rc == OKB_ERR_IO) {      // Reader.h:384-388: a missing file leaves empty lists (every error class = 3)
-        c->sup.lef.assign(c->E, 0); c->sup.rig.assign(c->E, 0); c->sup.ids.clear();
-        c->sub = c->sup;
-    }
+    if (rc == OKB_ERR_IO) { clear(c->sup); clear(c->sub); }   // Reader.h:384-388: a missing file leaves empty lists (every class = 3)
+    else if (rc) return rc;
     c->have_onto = true;
     return okb_upload_lists(c);
 }

@@ -31,6 +31,7 @@ struct okb_ctx {
     i64 W = 1, bern = 0;
     // ---------------- totals
     i64 E = 0, R = 0, n_raw = 0, n = 0, new_batch = 0, n_test = 0, n_valid = 0, n_all = 0;
+    i64 legacy_train_total = -1;      // Reader.h:227 re-reads trainTotal from the file header in importTestFiles
     // ---------------- host index (kept for the tiny host-side paths: TC negatives, thresholds)
     std::vector<i32> raw_h, raw_t, raw_r;              // train2id.txt order
     std::vector<i32> byh_r, byh_t, byt_r, byt_h, byht_t, byht_r;   // secondary key / value of the 3 sorted copies
