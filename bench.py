@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline metric (train triples/s, + link-prediction queries/s) on B200.
+
+    python bench.py [--gpus N --steps K --warmup W]              this repo's CUDA path
+    python bench.py --impl reference [--steps K --warmup W]      the reference's CPU path, same config
+
+Workload (BASELINE.json configs[1]): TransH dim=100, Adam, margin 1, ent_neg_rate 1, FB15K-shaped
+synthetic graph (14,951 entities / 1,345 relations / 483,142 train triples), nbatches=100 so
+B = 4,831 positives per step per GPU (weak scaling: the global batch is N x 4,831 = the reference
+batch at workThreads = 8N).  One "step" = sampling() + loss_def + optimizer (distribute_training.py:
+274-282): GPU sampler -> plan (keys + radix sort) -> fused grad kernel -> fused segmented-reduce +
+TF1-Adam update.
+
+Prints ONE JSON line (see the README of the contract in DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+MODEL, DIM, OPT, NBATCHES, NEG, MARGIN, ALPHA, BERN, W_PER_GPU = "TransH", 100, "Adam", 100, 1, 1.0, 0.001, 0, 8
+SHAPE = "fb15k"
+METRIC = "train triples/s (+ link-pred queries/s)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def make_graph():
+    from openkeonspark_b200 import datagen
+    return datagen.make_shape(SHAPE, seed=0)
+
+
+def params_for(g, rng):
+    from openkeonspark_b200 import datagen
+    return {"ent_embeddings": datagen.xavier_normal(rng, g.E, DIM), "rel_embeddings": datagen.xavier_normal(rng, g.R, DIM),
+            "normal_vectors": datagen.xavier_normal(rng, g.R, DIM)}
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out = self.p.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_path(g, steps, warmup, B, threads):
+    """The reference's serial loop on host cores: sampling() by the reference's own Base.so
+    (oracle/_ref, compiled from /root/reference/base/Base.cpp; the C restatement if absent) followed
+    by the TF-graph step restated in torch-CPU (TensorFlow 1.x is not installable).  Returns
+    (triples/s, description, seconds per step)."""
+    import tempfile
+
+    import torch
+    from openkeonspark_b200 import datagen
+    from oracle import harness, models_ref
+    torch.set_num_threads(threads)
+    d = tempfile.mkdtemp() + "/"
+    datagen.write_dataset(g, d)
+    kind = "port"
+    if os.path.exists(harness.REF_SO):
+        ref = harness.RefLib().init(d, bern=BERN, W=min(threads, 8), test=False)
+        sample = lambda: ref.sampling(B, NEG, 0)
+        native = "reference Base.so sampling() at workThreads=%d" % min(threads, 8)
+    else:
+        orc = harness.COracle().load(d, test=False)
+        orc.set_streams(np.arange(1, 9, dtype=np.uint64), BERN)
+        sample = lambda: orc.sampling(B, NEG, 0)
+        native = "C restatement of sampling() (1 thread)"
+    tr = models_ref.Trainer(MODEL, params_for(g, np.random.default_rng(0)), margin=MARGIN, lr=ALPHA, opt=OPT)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        h, t, r, _ = sample()
+        tr.step(h, t, r, B, NEG, 0)
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    desc = "%d steps of B=%d: %s + torch-CPU fp32 restatement of TransH loss_def/Adam (%d threads)" % (steps, B, native, threads)
+    return B / sec, desc, sec, kind
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    g = make_graph()
+    cores = os.cpu_count() or 1
+    B = g.train.shape[0] // NBATCHES
+    steps = max(1, min(args.steps, 40))          # bounded sample: each CPU step is ~0.1-1 s
+    val, desc, sec, kind = cpu_reference_path(g, steps, min(args.warmup, 3), B, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "triples/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "TransH dim=100 Adam k=1 margin=1, FB15K-shaped 14951/1345/483142, B=4831 (nbatches=100)"},
+            "cpu_baseline": {"value": val, "unit": "triples/s", "cores": cores, "kind": kind, "sample": desc},
+            "e2e": {"value": val, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="okb200")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lp-queries", type=int, default=4096)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import openkeonspark_b200 as okb
+    from openkeonspark_b200 import _native, parallel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    g = make_graph()
+    con = okb.Config(private_context=True)
+    con.set_nbatches(NBATCHES)
+    con.set_ent_neg_rate(NEG)
+    con.set_margin(MARGIN)
+    con.set_alpha(ALPHA)
+    con.set_opt_method(OPT)
+    con.set_dimension(DIM)
+    con.set_bern(BERN)
+    con.workThreads = W_PER_GPU * world
+    con.test_head = 1
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        con.init_from_arrays(g.E, g.R, g.train, g.valid, g.test)
+    B_local = con.batch_size                     # 4831
+    if world > 1:                                # weak scaling: the global batch grows with N
+        con.batch_size = B_local * world
+        con._alloc_batch()
+    con.set_model_and_session(okb.TransH)
+    con.set_parameters(params_for(g, np.random.default_rng(0)))
+    seeds = np.arange(1, con.workThreads + 1, dtype=np.uint64) * np.uint64(2654435761)
+    con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), con.workThreads)
+    if world > 1:
+        parallel.attach(con)
+    lib = _native.load()
+
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one_step():
+        con.sampling_device()
+        con.train_step_device(0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+
+    # ---------------- timed region: K steps, each bracketed by CUDA events, L2 flushed between steps
+    clocks = ClockSampler(local) if rank == 0 else None
+    con.ctx.call("okb_prof_enable", 1)
+    launches0 = lib.okb_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        if flush is not None:
+            flush.fill_(1)
+        a.record()
+        one_step()
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.okb_launch_count() - launches0
+    con.ctx.call("okb_prof_enable", 0)
+    clk = clocks.stop() if clocks else None
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    prof = {}
+    for name, kid in (("sample", 0), ("plan", 1), ("grad", 2), ("update", 3)):
+        ms, cnt = ctypes.c_double(), ctypes.c_int64()
+        con.ctx.call("okb_prof_read", kid, ctypes.byref(ms), ctypes.byref(cnt))
+        prof[name] = (ms.value, cnt.value)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = con.batch_size * args.steps / (ms_total * 1e-3)      # global positives per second
+
+    # ---------------- e2e: the reference-shaped loop through the public API with HOST buffers
+    # con.sampling() fills the numpy batch_h/t/r/y (D2H); con.train_step(...) feeds them back (H2D) and
+    # returns the loss as a Python float (D2H) — distribute_training.py:274-282.
+    e2e_steps = max(10, min(args.steps, 100))
+    for _ in range(3):
+        con.sampling(); con.train_step(con.batch_h, con.batch_t, con.batch_r, con.batch_y)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        con.sampling()
+        con.train_step(con.batch_h, con.batch_t, con.batch_r, con.batch_y)
+    barrier()
+    e2e_sec = time.perf_counter() - t0
+    t = torch.tensor([e2e_sec], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    S = con.batch_seq_size
+    e2e = {"value": con.batch_size * e2e_steps / float(t.item()), "unit": "triples/s", "h2d_bytes_per_step": 3 * 8 * S,
+           "d2h_bytes_per_step": 3 * 8 * S + 4 * S + 4, "steps": e2e_steps}
+
+    # ---------------- roofline of the dominant kernel
+    # Algorithmic bytes per launch: Adam update = 6*4 B per table element (var, m, v read+write)
+    # over ALL rows (TF1 dense-decay semantics) + one read of every gradient row;
+    # grad kernel = gather of (2+k) entity rows + 2 relation-side rows per positive + the gradient rows it writes.
+    peak, peak_src = peaks()
+    D, k = DIM, NEG
+    n_tab = (g.E + 2 * g.R) * D
+    ne_rows, nr_rows = con.batch_size * (2 + k), con.batch_size
+    bytes_update = 24 * n_tab + 4 * (ne_rows * D + nr_rows * 2 * D)
+    bytes_grad = (con.batch_size // world) * 4 * D * ((2 + k) + 2) * 2
+    kern = {}
+    for name, nbytes in (("update", bytes_update), ("grad", bytes_grad)):
+        ms, cnt = prof[name]
+        if cnt:
+            kern[name] = {"ms": ms / cnt, "gbs": nbytes / (ms / cnt * 1e-3) / 1e9, "bytes": nbytes}
+    dom = max(kern, key=lambda n: kern[n]["ms"]) if kern else None
+    roofline = None
+    if dom:
+        roofline = {"kernel": "adam_kernel" if dom == "update" else "grad_kernel", "bound": "hbm", "achieved": kern[dom]["gbs"],
+                    "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kern[dom]["bytes"], "avg_launch_ms": kern[dom]["ms"],
+                    "step_breakdown_ms": {n: (prof[n][0] / prof[n][1] if prof[n][1] else None) for n in prof}}
+
+    # ---------------- secondary metric: filtered link-prediction queries/s (both sides)
+    lp = None
+    try:
+        nq = min(args.lp_queries, con.testTotal)
+        rec_fn = (lambda: con._world.link_prediction(con, 0, nq)) if world > 1 else (lambda: con.link_prediction_records(0, nq))
+        rec_fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rec_fn()
+        b.record()
+        barrier()
+        lp_ms = a.elapsed_time(b)
+        t = torch.tensor([lp_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        lp = {"queries_per_s": 2 * nq / (float(t.item()) * 1e-3), "queries": 2 * nq, "ms": float(t.item()),
+              "what": "filtered+raw+type-constrained ranks, head and tail side, all %d candidates%s" % (g.E, " sharded over %d GPUs" % world if world > 1 else "")}
+    except Exception as e:  # noqa: BLE001  (the secondary metric must not kill the headline line)
+        lp = {"error": str(e)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        val, desc, sec, kind = cpu_reference_path(g, 12, 2, B_local, cores)
+        cpu = {"value": val, "unit": "triples/s", "cores": cores, "kind": kind, "sample": desc}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": "TransH dim=100 Adam k=1 margin=1, FB15K-shaped 14951/1345/483142, B=%d per GPU (nbatches=100), global batch %d, workThreads=%d"
+                           % (B_local, con.batch_size, con.workThreads),
+                           "l2": "not flushed" if flush is None else "flushed between timed steps (256 MiB fill, outside the per-step events)",
+                           "timing": "per-step CUDA events summed; max over ranks", "parallelism": "dp%d" % world},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "link_prediction": lp, "wall_s_timed_region_incl_flush": t_wall}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,9 @@ int okb_import_train_arrays(okb_ctx *c, INT n_ent, INT n_rel, const INT *h, cons
                             INT n, INT new_batch_total);
 int okb_import_test_arrays(okb_ctx *c, const INT *th, const INT *tt, const INT *tr, INT n_test,
                            const INT *vh, const INT *vt, const INT *vr, INT n_valid);
+/* Build the type constraints from the loaded train+valid+test triples, as the reference's n_n()
+ * generator does before every run (main_spark.py:209-290), without going through type_constrain.txt. */
+int okb_build_type_constraints(okb_ctx *c);
 /* what: 0 entities, 1 relations, 2 train rows (file), 3 train dedup, 4 test, 5 valid, 6 all triples,
  *       7 new-batch total */
 INT okb_total(okb_ctx *c, int what);
@@ -197,6 +200,14 @@ int okb_test_list(okb_ctx *c, int which, INT *h, INT *t, INT *r);
 INT okb_n_interval(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg);            /* Test.h:390-407 */
 INT *okb_tpfp(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg, const REAL *score_pos_test,
               const REAL *score_neg_test);                                                        /* Test.h:410-444 */
+
+/* Optional per-kernel timing with CUDA events recorded on the launching stream, around:
+ * id 0 sampler, 1 plan (keys + radix sort), 2 grad kernel, 3 update kernel (SGD / Adam), 4 rank kernel,
+ * 5 rank preparation.  okb_prof_read synchronises, returns the summed milliseconds and the number of
+ * launches since the last read, and clears the list. */
+int okb_prof_enable(okb_ctx *c, int on);
+int okb_prof_read(okb_ctx *c, int id, double *total_ms, INT *count);
+const char *okb_debug_cuda_error(void);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 INT okb_launch_count(void);

@@ -147,6 +147,7 @@ class Config(object):
             self.ctx.call("okb_import_test_arrays", _addr(a[0]), _addr(a[1]), _addr(a[2]), a[0].size,
                           _addr(b[0]), _addr(b[1]), _addr(b[2]), b[0].size)
             self.testTotal, self.validTotal = self.ctx.total(4), self.ctx.total(5)
+            self.ctx.call("okb_build_type_constraints")       # what main_spark.n_n() writes to type_constrain.txt
 
     def _after_train_import(self):
         self.relTotal = self.ctx.total(1)
@@ -156,6 +157,10 @@ class Config(object):
         self.validTotal = self.ctx.total(5)
         self.bt = self.ctx.total(7)
         self.set_mini_batch()
+        self._alloc_batch()
+
+    def _alloc_batch(self):
+        """(Re)allocate the caller-visible numpy batch buffers (Config.py:172-180)."""
         self.batch_seq_size = self.batch_size * (1 + self.negative_ent + self.negative_rel)
         self.batch_h = np.zeros(self.batch_seq_size, dtype=np.int64)
         self.batch_t = np.zeros(self.batch_seq_size, dtype=np.int64)

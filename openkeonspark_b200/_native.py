@@ -48,6 +48,7 @@ _SIGS = {
     "okb_import_ontology_files": (_int, [_vp]),
     "okb_import_train_arrays": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64]),
     "okb_import_test_arrays": (_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64]),
+    "okb_build_type_constraints": (_int, [_vp]),
     "okb_total": (_i64, [_vp, _int]),
     "okb_rand_reset": (_int, [_vp]),
     "okb_set_streams": (_int, [_vp, _vp, _i64]),
@@ -71,6 +72,9 @@ _SIGS = {
     "okb_test_list": (_int, [_vp, _int, _vp, _vp, _vp]),
     "okb_n_interval": (_i64, [_vp, _i64, _vp, _vp]),
     "okb_tpfp": (_vp, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "okb_prof_enable": (_int, [_vp, _int]),
+    "okb_prof_read": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    "okb_debug_cuda_error": (C.c_char_p, []),
     "okb_launch_count": (_i64, []),
 }
 

@@ -51,6 +51,24 @@ int okb_destroy(okb_ctx *c) {
 }
 const char *okb_last_error(okb_ctx *c) { return c ? c->err.c_str() : "null context"; }
 int okb_set_device(okb_ctx *c, int device) { OKB_CUDA(c, cudaSetDevice(device)); return 0; }
+int okb_prof_enable(okb_ctx *c, int on) { c->prof_on = on != 0; return 0; }
+int okb_prof_read(okb_ctx *c, int id, double *total_ms, INT *count) {
+    if (id < 0 || id >= 8) OKB_FAIL(c, OKB_ERR_ARG, "bad kernel id");
+    std::vector<cudaEvent_t> &v = c->prof_ev[id];
+    double tot = 0;
+    INT n = 0;
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+        OKB_CUDA(c, cudaEventSynchronize(v[i + 1]));
+        float ms = 0;
+        OKB_CUDA(c, cudaEventElapsedTime(&ms, v[i], v[i + 1]));
+        tot += ms; n++;
+    }
+    for (cudaEvent_t e : v) cudaEventDestroy(e);
+    v.clear();
+    if (total_ms) *total_ms = tot;
+    if (count) *count = n;
+    return 0;
+}
 // debugging aid: returns (and clears) the CUDA runtime's last error of this library's runtime instance
 const char *okb_debug_cuda_error(void) { return cudaGetErrorString(cudaGetLastError()); }
 

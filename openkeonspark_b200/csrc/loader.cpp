@@ -397,6 +397,33 @@ int okb_import_type_files(okb_ctx *c) {
     c->have_types = true;
     return okb_upload_lists(c);
 }
+// Type constraints derived from the loaded graph exactly as the reference's n_n() writes them
+// (main_spark.py:209-290): per relation, the set of heads / tails seen in train + valid + test.
+int okb_build_type_constraints(okb_ctx *c) {
+    if (c->all_hrt.empty()) OKB_FAIL(c, OKB_ERR_STATE, "import train and test data first");
+    Packer pk(c->E, c->R);
+    const u64 me = (1ull << pk.be) - 1, mr = (1ull << pk.br) - 1;
+    std::vector<u64> hk, tk;                              // (r, h) and (r, t) pairs
+    hk.reserve(c->all_hrt.size()); tk.reserve(c->all_hrt.size());
+    for (u64 k : c->all_hrt) {
+        const u64 h = k >> (pk.br + pk.be), r = (k >> pk.be) & mr, t = k & me;
+        hk.push_back((r << pk.be) | h); tk.push_back((r << pk.be) | t);
+    }
+    auto build = [&](std::vector<u64> &v, Lists &L) {
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        L.lef.assign(c->R, 0); L.rig.assign(c->R, 0); L.ids.resize(v.size());
+        size_t i = 0;
+        for (i64 r = 0; r < c->R; r++) {
+            L.lef[r] = (i32)i;
+            while (i < v.size() && (i64)(v[i] >> pk.be) == r) { L.ids[i] = (i32)(v[i] & me); i++; }
+            L.rig[r] = (i32)i;
+        }
+    };
+    build(hk, c->head_type); build(tk, c->tail_type);
+    c->have_types = true;
+    return okb_upload_lists(c);
+}
 int okb_import_ontology_files(okb_ctx *c) {
     printf("Reading %sontology_constrain.txt\n", c->in_path.c_str());
     auto clear = [&](Lists &L) { L.lef.assign(c->E, 0); L.rig.assign(c->E, 0); L.ids.clear(); };

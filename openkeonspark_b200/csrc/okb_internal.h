@@ -66,6 +66,9 @@ struct okb_ctx {
     DevBuf rank_ws, host_io;
     i64 plan_ne = 0, plan_nr = 0;
     int ent_bits = 0, rel_bits = 0;
+    // ---------------- optional per-kernel timing (CUDA events on the launching stream; bench.py)
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev[8];   // begin/end pairs per kernel id
     // legacy result buffers
     i64 res8[8];
     std::vector<i64> tpfp;
@@ -74,6 +77,21 @@ struct okb_ctx {
 #define OKB_FAIL(c, code, msg) do { (c)->err = (msg); return (code); } while (0)
 #define OKB_CUDA(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
     (c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return OKB_ERR_CUDA; } } while (0)
+
+// kernel ids for okb_prof_*
+enum { PROF_SAMPLE = 0, PROF_PLAN = 1, PROF_GRAD = 2, PROF_UPDATE = 3, PROF_RANK = 4, PROF_RANK_PREP = 5 };
+static inline void prof_mark(okb_ctx *c, int id, cudaStream_t s) {
+    if (!c->prof_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    c->prof_ev[id].push_back(e);
+}
+struct ProfScope {                     // records an event pair around the launches in its scope
+    okb_ctx *c; int id; cudaStream_t s;
+    ProfScope(okb_ctx *c_, int id_, cudaStream_t s_) : c(c_), id(id_), s(s_) { prof_mark(c, id, s); }
+    ~ProfScope() { prof_mark(c, id, s); }
+};
 
 extern i64 g_launches;                // kernels launched by this library
 #define OKB_LAUNCHED(n) (g_launches += (n))

@@ -203,7 +203,8 @@ int okb_sample(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT s
     a.per = (i32)(B / c->W + (B % c->W ? 1 : 0));
     a.bern = (i32)c->bern; a.steps = (i32)steps; a.stream_lo = (i32)stream_lo; a.stream_hi = (i32)stream_hi;
     const i64 total = B * steps;
-    sample_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a);
+    { ProfScope ps(c, PROF_SAMPLE, s);
+    sample_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a); }
     advance_kernel<<<(unsigned)((c->W + 63) / 64), 64, 0, s>>>(c->d_state, a.W, a.B, a.per, 1 + 2 * (u64)k + (u64)kr,
                                                               a.steps, 0, a.W);   // every rank advances ALL streams
     OKB_LAUNCHED(2);

@@ -604,8 +604,9 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         ra.D = D; ra.ncol = (i32)ncol; ra.j0 = (i32)j0; ra.cand_lo = (i32)cand_lo; ra.cand_hi = (i32)cand_hi;
         ra.q_lo = (i32)cq_lo; ra.model = m->model; ra.tab_per_group = per_group ? 1 : 0;
         const dim3 grid((unsigned)(ncol / CT), (unsigned)G);
+        { ProfScope ps(c, PROF_RANK, s);
         if (heads) rank_kernel<true><<<grid, CT, smem_rank, s>>>(ra);
-        else rank_kernel<false><<<grid, CT, smem_rank, s>>>(ra);
+        else rank_kernel<false><<<grid, CT, smem_rank, s>>>(ra); }
         OKB_LAUNCHED(5);
         OKB_CUDA(c, cudaGetLastError());
     }

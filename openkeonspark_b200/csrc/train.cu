@@ -556,6 +556,7 @@ int okb_plan(okb_ctx *c, INT step, void *stream) {
     const i64 B = c->B, NE = 2 + c->K, NR = 1 + c->KR, n = B * (NE + NR), S = B * (1 + c->K + c->KR);
     if (c->keys_ent.ensure(sizeof(i32) * n * 2) || c->perm_ent.ensure(sizeof(i32) * n))
         OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (plan)");
+    ProfScope ps(c, PROF_PLAN, s);
     PlanArgs a;
     const i32 *base = c->batch.as<i32>() + step * 3 * S;
     a.bh = base; a.bt = base + S; a.br = base + 2 * S;
@@ -592,7 +593,7 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
     if (m->model == OKB_TRANSE) grad_kernel<OKB_TRANSE, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a);      \
     else if (m->model == OKB_TRANSH) grad_kernel<OKB_TRANSH, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a); \
     else grad_kernel<OKB_TRANSD, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
-    DISPATCH_LAYOUT(vw, nv, CALL_GRAD);
+    { ProfScope ps(c, PROF_GRAD, s); DISPATCH_LAYOUT(vw, nv, CALL_GRAD); }
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
     return 0;
@@ -625,12 +626,12 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         mark_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.skeys, a.rowseg, a.n, (i32)rows);
         const unsigned grid = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
 #define CALL_ADAM(VW, NV) adam_kernel<VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
-        DISPATCH_LAYOUT(vw, nv, CALL_ADAM);
+        { ProfScope ps(c, PROF_UPDATE, s); DISPATCH_LAYOUT(vw, nv, CALL_ADAM); }
         OKB_LAUNCHED(2);
     } else {
         const unsigned grid = (unsigned)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
 #define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
-        DISPATCH_LAYOUT(vw, nv, CALL_SGD);
+        { ProfScope ps(c, PROF_UPDATE, s); DISPATCH_LAYOUT(vw, nv, CALL_SGD); }
         OKB_LAUNCHED(1);
     }
     if (loss_out) {

@@ -105,7 +105,7 @@ class Trainer:
             v.grad = None
         loss = loss_fn(self.model, self.P, bh, bt, br, B, k, kr, self.margin)
         loss.backward()
-        return float(loss), {n: (v.grad if v.grad is not None else torch.zeros_like(v)) for n, v in self.P.items()}
+        return float(loss.detach()), {n: (v.grad if v.grad is not None else torch.zeros_like(v)) for n, v in self.P.items()}
 
     def step(self, bh, bt, br, B, k, kr):
         loss, g = self.grads(bh, bt, br, B, k, kr)
