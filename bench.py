@@ -205,8 +205,7 @@ def main():
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def one_step():
-        con.sampling_device()
-        con.train_step_device(0)
+        con.next_step_device()       # sampler + plan amortised over con.plan_ahead steps, then grad + update
 
     def barrier():
         if world > 1:

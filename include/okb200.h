@@ -165,6 +165,9 @@ typedef struct {
 int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT batch_size, INT neg_ent, INT neg_rel,
                    INT *ent_rows, INT *ent_cols, INT *rel_rows, INT *rel_cols);
 int okb_plan(okb_ctx *c, INT step, void *cuda_stream);
+/* Plan steps [step_lo, step_hi) of the last okb_sample with ONE radix sort (sampling and planning do not
+ * depend on the parameters, so whole chunks of steps are prepared ahead of the train kernels). */
+int okb_plan_steps(okb_ctx *c, INT step_lo, INT step_hi, void *cuda_stream);
 int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi,
              float *grad_ent, float *grad_rel, float *loss_terms, void *cuda_stream);
 int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *grad_ent,

@@ -74,6 +74,8 @@ class Config(object):
         self._step = 0
         self._adam = None
         self._world = None            # parallel.DataParallel when running under torch.distributed
+        self.plan_ahead = 64          # steps sampled + planned per launch chunk (integer work, parameter-independent)
+        self._chunk_pos = self._chunk_len = 0
 
     # ------------------------------------------------------------------ init (Config.py:74-186)
     def init_link_prediction(self):
@@ -260,6 +262,22 @@ class Config(object):
     def sampling_device(self, steps=1):
         """Sample `steps` consecutive batches, leaving them resident in HBM (no host copy)."""
         self.ctx.call("okb_sample", self.batch_size, self.negative_ent, self.negative_rel, steps, 0, self.workThreads, _stream())
+        self._chunk_pos = self._chunk_len = 0
+
+    def next_step_device(self):
+        """One iteration of the train loop (sampling() + train_op, distribute_training.py:274-282).
+        Sampling and gradient-row planning do not depend on the parameters, so they are done for
+        `plan_ahead` consecutive steps in one launch each; the batches are exactly the ones that many
+        consecutive sampling() calls would have produced."""
+        if self._chunk_pos >= self._chunk_len:
+            n = self.batch_size * (3 + self.negative_ent + self.negative_rel)
+            C = max(1, min(int(self.plan_ahead), (1 << 24) // n))
+            self.sampling_device(C)
+            self.ctx.call("okb_plan_steps", 0, C, _stream())
+            self._chunk_pos, self._chunk_len = 0, C
+        loss = self.train_step_device(self._chunk_pos)
+        self._chunk_pos += 1
+        return loss
 
     # ------------------------------------------------------------------ parameters (Config.py:379-422)
     def get_parameter_lists(self):
@@ -400,6 +418,7 @@ class Config(object):
         if h.size != self.batch_seq_size:
             raise OkbError("batch has %d rows, expected batch_seq_size=%d" % (h.size, self.batch_seq_size))
         self.ctx.call("okb_batch_from_host", self.batch_size, self.negative_ent, self.negative_rel, _addr(h), _addr(t), _addr(r), _stream())
+        self._chunk_pos = self._chunk_len = 0
         return float(self.train_step_device(0).item())
 
     def run(self):
@@ -410,8 +429,7 @@ class Config(object):
             t0 = time.time()
             acc = torch.zeros(1, dtype=torch.float32, device=self._loss_dev.device)
             for batch in range(self.nbatches):
-                self.sampling_device()
-                loss = self.train_step_device(0)
+                loss = self.next_step_device()
                 acc += loss
                 if self.log_every and (self._step % self.log_every == 0):
                     print("Global step: {} Epoch: {} Batch: {} loss: {}".format(self._step, epoch, batch, float(loss.item())))

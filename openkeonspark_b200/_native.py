@@ -59,6 +59,7 @@ _SIGS = {
     "okb_batch_from_host": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "okb_grad_sizes": (_int, [_vp, C.POINTER(okb_model), _i64, _i64, _i64] + [C.POINTER(_i64)] * 4),
     "okb_plan": (_int, [_vp, _i64, _vp]),
+    "okb_plan_steps": (_int, [_vp, _i64, _i64, _vp]),
     "okb_grad": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "okb_update": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _vp, _vp, _vp, _vp, _vp]),
     "okb_train_step": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _vp, _vp]),

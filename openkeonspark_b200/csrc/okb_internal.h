@@ -64,7 +64,8 @@ struct okb_ctx {
     // ---------------- plan / workspace
     DevBuf keys_ent, keys_rel, perm_ent, perm_rel, sort_tmp, hist, gent, grel, flags, lossterms, rowseg_e, rowseg_r;
     DevBuf rank_ws, host_io;
-    i64 plan_ne = 0, plan_nr = 0;
+    i64 plan_ne = 0, plan_nr = 0, plan_lo = 0, plan_hi = 0;   // steps [plan_lo, plan_hi) of the sampled batches are planned
+    bool rowhead_ready = false;       // Adam: per-step row -> first sorted position map built for the planned chunk
     int ent_bits = 0, rel_bits = 0;
     // ---------------- optional per-kernel timing (CUDA events on the launching stream; bench.py)
     bool prof_on = false;

@@ -194,6 +194,7 @@ int okb_sample(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT s
     const i64 S = B * (1 + k + kr);
     if (c->batch.ensure(sizeof(i32) * 3 * S * steps)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (batch)");
     c->B = B; c->K = k; c->KR = kr; c->steps = steps;
+    c->plan_lo = c->plan_hi = 0;                            // new batches: any previous plan is stale
     SampleArgs a;
     a.raw = c->d_raw; a.run = c->d_run; a.run_ht = c->d_run_ht;
     a.byh_t = c->d_byh_t; a.byt_h = c->d_byt_h; a.byht_r = c->d_byht_r;
@@ -244,6 +245,7 @@ int okb_batch_from_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const IN
     if (c->batch.ensure(sizeof(i32) * 3 * S)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (batch)");
     if (c->host_io.ensure(sizeof(i64) * 3 * S)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
     c->B = B; c->K = k; c->KR = kr; c->steps = 1;
+    c->plan_lo = c->plan_hi = 0;
     i64 *dh = c->host_io.as<i64>(), *dt = dh + S, *dr = dt + S;
     OKB_CUDA(c, cudaMemcpyAsync(dh, h, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
     OKB_CUDA(c, cudaMemcpyAsync(dt, t, sizeof(i64) * S, cudaMemcpyHostToDevice, s));

@@ -15,35 +15,58 @@
 //
 // Roofline: HBM-bound gather/scatter of fp32 rows; no dense contraction, so no tensor cores here
 // (TransR's projection lives in transr.cu).
+#include <algorithm>
+
 #include "okb_internal.h"
 
 #define FULL 0xffffffffu
 #define WARPS_PER_BLOCK 4
+// grad kernel: one warp per block so that residency is quantised in single warps: <= 120 registers
+// -> 17 warps per SM -> B = 4831 positives fit in 2 waves instead of 2.04 (= 3)
+#ifndef GRAD_WARPS
+#define GRAD_WARPS 1
+#endif
+#ifndef GRAD_MIN_BLOCKS
+#define GRAD_MIN_BLOCKS 17
+#endif
 
 // ------------------------------------------------------------------------------------------ plan
 struct PlanArgs {
-    const i32 *bh, *bt, *br;   // plane-major batch
-    i32 *keys;                 // [B*NE + B*NR]
-    i32 B, k, kr, NE, NR, E, R;
+    const i32 *batch;          // [steps][3][S] plane-major batches
+    i32 *keys;                 // [C][B*NE + B*NR] composite keys
+    i32 B, k, kr, NE, NR, E, R, S, step_lo, C;
 };
-// Combined key space: entity row e -> e, relation row r -> E + r, unused slot -> E + R.
+// Combined key space of one step: entity row e -> e, relation row r -> E + r, unused slot -> E + R.
+// Several steps are planned by ONE sort: step c (relative) adds c * (E + R + 1), so the sorted array
+// is the concatenation of the per-step sorted arrays.
 __global__ void plan_keys_kernel(PlanArgs a) {
-    const i32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
-    const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
-    i32 *ke = a.keys + (i64)b * a.NE;
-    i32 *kr_ = a.keys + (i64)a.B * a.NE + (i64)b * a.NR;
-    const i32 none = a.E + a.R;
-    ke[0] = ph; ke[1] = pt; kr_[0] = a.E + pr;
+    const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (i64)a.C * a.B) return;
+    const i32 c = (i32)(tid / a.B), b = (i32)(tid % a.B);
+    const i32 *bh = a.batch + (i64)(a.step_lo + c) * 3 * a.S, *bt = bh + a.S, *br = bt + a.S;
+    const i32 ph = bh[b], pt = bt[b], pr = br[b];
+    const i32 n = a.B * (a.NE + a.NR), ks = a.E + a.R + 1, off = c * ks;
+    i32 *ke = a.keys + (i64)c * n + (i64)b * a.NE;
+    i32 *kr_ = a.keys + (i64)c * n + (i64)a.B * a.NE + (i64)b * a.NR;
+    const i32 none = off + a.E + a.R;
+    ke[0] = off + ph; ke[1] = off + pt; kr_[0] = off + a.E + pr;
     for (i32 m = 0; m < a.k; m++) {
         const i32 at = b + (m + 1) * a.B;
-        const i32 nh = a.bh[at], nt = a.bt[at];
-        ke[2 + m] = nh != ph ? nh : (nt != pt ? nt : none);
+        const i32 nh = bh[at], nt = bt[at];
+        ke[2 + m] = nh != ph ? off + nh : (nt != pt ? off + nt : none);
     }
     for (i32 m = 0; m < a.kr; m++) {
-        const i32 nr = a.br[b + (1 + a.k + m) * a.B];
-        kr_[1 + m] = nr != pr ? a.E + nr : none;
+        const i32 nr = br[b + (1 + a.k + m) * a.B];
+        kr_[1 + m] = nr != pr ? off + a.E + nr : none;
     }
+}
+// back to per-step keys / slots
+__global__ void plan_fixup_kernel(i32 *__restrict__ skeys, i32 *__restrict__ perm, i32 n, i32 ks, i64 total) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const i32 c = (i32)(i / n);
+    skeys[i] -= c * ks;
+    perm[i] -= c * n;
 }
 
 // ------------------------------------------------------------------------------------------ row fragments
@@ -65,7 +88,7 @@ template <int VW, int NV> struct Frag {
         for (int i = 0; i < NV; i++) {
             const int e = (i * 32 + lane) * VW;
             if (e < D) {
-                typename VecT<VW>::T x = *reinterpret_cast<const typename VecT<VW>::T *>(row + e);
+                typename VecT<VW>::T x = __ldg(reinterpret_cast<const typename VecT<VW>::T *>(row + e));
                 const float *xs = reinterpret_cast<const float *>(&x);
 #pragma unroll
                 for (int j = 0; j < VW; j++) v[i * VW + j] = xs[j];
@@ -309,10 +332,10 @@ struct GradArgs {
 
 // ------------------------------------------------------------------------------------------ grad
 template <int MODEL, int VW, int NV>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) grad_kernel(GradArgs a) {
+__global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(GradArgs a) {
     constexpr int N = VW * NV;
     const int lane = threadIdx.x & 31;
-    const i32 b = a.b_lo + blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const i32 b = a.b_lo + blockIdx.x * GRAD_WARPS + (threadIdx.x >> 5);
     if (b >= a.b_hi) return;
     const int D = a.m.ent_dim;
     const int ce = MODEL == OKB_TRANSD ? 2 * D : D, cr = MODEL == OKB_TRANSE ? D : 2 * D;
@@ -391,23 +414,43 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) grad_kernel(GradArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------ update
+// one parameter table for the flat Adam pass; vec_end: cumulative vector count over the table list
+struct DenseTab { float *x, *m, *v; const float *grad; i64 vec_end; i32 D, key_off, cols, part, slot_off; };
 struct UpdArgs {
     okb_model m;
     okb_hyper hp;
-    const i32 *skeys, *perm;   // sorted keys / slot of each sorted position
-    const float *gent, *grel;
-    i32 *rowseg;               // Adam: first sorted position of each table row, -1 if untouched
-    i32 n, n_ent_slots, E, R, ce, cr;
+    const i32 *skeys, *perm;   // sorted keys / slot of each sorted position (this step)
+    const float *gent, *grel, *loss_terms;
+    float *loss_out;
+    const int2 *rowhead;       // Adam: [first, end) sorted positions of each table row in this step's plan; first = -1 if untouched
+    DenseTab tab[4];
+    i32 n, n_ent_slots, E, R, ce, cr, B, step_stamp, ntab, work_blocks;
+    float w;
 };
 
-// Sum the gradient rows of the segment starting at sorted position `i` (fixed slot order).
+// mean hinge over B*(k+kr) pairs in a fixed order, by the extra last block of the update launch
+__device__ __forceinline__ void loss_block(const UpdArgs &a) {
+    __shared__ float sh[32];
+    if (!a.loss_out) return;
+    float s = 0.f;
+    for (i32 i = threadIdx.x; i < a.B; i += blockDim.x) s += a.loss_terms[i];
+    s = wsum(s);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = wsum(threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f);
+        if (threadIdx.x == 0) a.loss_out[0] = s * a.w;
+    }
+}
+
+// Sum the gradient rows of the segment starting at sorted position `pos` (fixed slot order).
 template <int VW, int NV>
-__device__ __forceinline__ void seg_sum(const UpdArgs &a, i32 i, i32 key, bool is_ent, int D, int part, int lane, float *acc) {
+__device__ __forceinline__ void seg_sum(const UpdArgs &a, i32 pos, i32 key, bool is_ent, int D, int part, int lane, float *acc) {
     constexpr int N = VW * NV;
 #pragma unroll
-    FOR_N acc[i] = 0.f;
+    for (int q = 0; q < N; q++) acc[q] = 0.f;
     const i32 cols = is_ent ? a.ce : a.cr;
-    for (i32 j = i; j < a.n && a.skeys[j] == key; j++) {
+    for (i32 j = pos; j < a.n && a.skeys[j] == key; j++) {
         const i32 slot = a.perm[j];
         const float *row = is_ent ? a.gent + (i64)slot * cols : a.grel + (i64)(slot - a.n_ent_slots) * cols;
         Frag<VW, NV> f;
@@ -417,10 +460,12 @@ __device__ __forceinline__ void seg_sum(const UpdArgs &a, i32 i, i32 key, bool i
     }
 }
 
-// SGD: one warp per sorted position; only segment heads work.  row -= lr * sum  (sparse apply).
+// SGD: one warp per sorted position; only segment heads work.  row -= lr * sum of its gradient rows
+// (GradientDescentOptimizer's sparse apply: duplicates accumulate).
 template <int VW, int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
     constexpr int N = VW * NV;
+    if ((i32)blockIdx.x == a.work_blocks) { loss_block(a); return; }
     const int lane = threadIdx.x & 31;
     const i32 i = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (i >= a.n) return;
@@ -431,76 +476,77 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
     const i32 row = is_ent ? key : key - a.E;
     const int parts = (is_ent ? a.ce : a.cr) / D;
     for (int p = 0; p < parts; p++) {
-        float acc[N];
-        seg_sum<VW, NV>(a, i, key, is_ent, D, p, lane, acc);
-        float *tab = is_ent ? (p ? a.m.ent_aux : a.m.ent) : (p ? a.m.rel_aux : a.m.rel);
-        Frag<VW, NV> f;
-        f.load(tab + (i64)row * D, D, lane);
-#pragma unroll
-        for (int q = 0; q < N; q++) f.v[q] -= a.hp.lr * acc[q];
-        f.store(tab + (i64)row * D, D, lane);
-    }
-}
-
-__global__ void mark_heads_kernel(const i32 *__restrict__ skeys, i32 *__restrict__ rowseg, i32 n, i32 rows) {
-    const i32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const i32 key = skeys[i];
-    if (key < rows && (i == 0 || skeys[i - 1] != key)) rowseg[key] = i;
-}
-
-// TF1 AdamOptimizer._apply_sparse_shared: m and v decay over the WHOLE variable and the variable
-// moves everywhere each step; only the (1-beta)*g terms are sparse.  One warp per table row.
-template <int VW, int NV>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) adam_kernel(UpdArgs a) {
-    constexpr int N = VW * NV;
-    const int lane = threadIdx.x & 31;
-    const i32 key = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (key >= a.E + a.R) return;
-    const bool is_ent = key < a.E;
-    const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
-    const i32 row = is_ent ? key : key - a.E;
-    const int parts = (is_ent ? a.ce : a.cr) / D;
-    const i32 seg = a.rowseg[key];
-    const float b1 = a.hp.beta1, b2 = a.hp.beta2;
-    for (int p = 0; p < parts; p++) {
         float g[N];
-        if (seg >= 0) seg_sum<VW, NV>(a, seg, key, is_ent, D, p, lane, g);
-        else {
-#pragma unroll
-            for (int q = 0; q < N; q++) g[q] = 0.f;
-        }
+        seg_sum<VW, NV>(a, i, key, is_ent, D, p, lane, g);
         float *tab = is_ent ? (p ? a.m.ent_aux : a.m.ent) : (p ? a.m.rel_aux : a.m.rel);
-        float *mt = is_ent ? (p ? a.m.m_ent_aux : a.m.m_ent) : (p ? a.m.m_rel_aux : a.m.m_rel);
-        float *vt = is_ent ? (p ? a.m.v_ent_aux : a.m.v_ent) : (p ? a.m.v_rel_aux : a.m.v_rel);
-        Frag<VW, NV> x, mm, vv;
         const i64 off = (i64)row * D;
-        x.load(tab + off, D, lane); mm.load(mt + off, D, lane); vv.load(vt + off, D, lane);
+        Frag<VW, NV> x;
+        x.load(tab + off, D, lane);
 #pragma unroll
-        for (int q = 0; q < N; q++) {
-            const float mq = mm.v[q] * b1 + g[q] * (1.f - b1);
-            const float vq = vv.v[q] * b2 + (g[q] * g[q]) * (1.f - b2);
-            mm.v[q] = mq; vv.v[q] = vq;
-            x.v[q] -= a.hp.lr * mq / (sqrtf(vq) + a.hp.eps);
-        }
-        x.store(tab + off, D, lane); mm.store(mt + off, D, lane); vv.store(vt + off, D, lane);
+        for (int q = 0; q < N; q++) x.v[q] -= a.hp.lr * g[q];
+        x.store(tab + off, D, lane);
     }
-    __syncwarp();
-    if (lane == 0 && seg >= 0) a.rowseg[key] = -1;
 }
 
-// mean hinge over B*(k+kr) pairs, fixed summation order (one block)
-__global__ void __launch_bounds__(1024) loss_kernel(const float *__restrict__ terms, float *__restrict__ out, i32 B, float w) {
-    __shared__ float sh[32];
-    float s = 0.f;
-    for (i32 i = threadIdx.x; i < B; i += 1024) s += terms[i];
-    s = wsum(s);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        s = wsum(sh[threadIdx.x]);
-        if (threadIdx.x == 0) out[0] = s * w;
+// TF1 AdamOptimizer._apply_sparse_shared: m and v decay over the WHOLE variable and every row moves
+// each step; only the (1-beta) g terms are sparse.  One flat, vectorised pass over all tables:
+// thread -> one VW-wide vector of one row; rows touched this step (rowhead >= 0) first sum their
+// gradient rows in sorted slot order (every thread of the row walks the same segment, reading its
+// own columns: coalesced), then the same Adam arithmetic runs everywhere.
+//   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; x <- x - lr_t m / (sqrt(v) + eps)
+template <int VW>
+__global__ void __launch_bounds__(256) adam_kernel(UpdArgs a) {
+    if ((i32)blockIdx.x == a.work_blocks) { loss_block(a); return; }
+    typedef typename VecT<VW>::T V;
+    const i64 total = a.tab[a.ntab - 1].vec_end;
+    const i64 stride = (i64)a.work_blocks * blockDim.x;
+    const float b1 = a.hp.beta1, b2 = a.hp.beta2, lr = a.hp.lr, eps = a.hp.eps;
+    for (i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += stride) {
+        int t = 0;
+        while (v >= a.tab[t].vec_end) t++;
+        const DenseTab &T = a.tab[t];
+        const unsigned lv = (unsigned)(v - (t ? a.tab[t - 1].vec_end : 0));     // < 2^31 vectors per table
+        const unsigned vpr = (unsigned)T.D / VW;                                // vectors per row
+        const unsigned row = lv / vpr, col = (lv - row * vpr) * VW;
+        const i64 e = (i64)lv * VW;
+        // issue every independent load before the first dependent use
+        const int2 seg = __ldg(a.rowhead + T.key_off + row);
+        V xv = *reinterpret_cast<const V *>(T.x + e), mv = *reinterpret_cast<const V *>(T.m + e), vv = *reinterpret_cast<const V *>(T.v + e);
+        float g[VW];
+#pragma unroll
+        for (int q = 0; q < VW; q++) g[q] = 0.f;
+        const float *gbase = T.grad + T.part * T.D + col;
+        for (i32 j = seg.x; j < seg.y; j += 2) {               // seg.x = -1, seg.y = -1 when untouched
+            const bool two = j + 1 < seg.y;
+            const i32 s0 = __ldg(a.perm + j) - T.slot_off, s1 = two ? __ldg(a.perm + j + 1) - T.slot_off : 0;
+            const V g0 = __ldg(reinterpret_cast<const V *>(gbase + (i64)s0 * T.cols));
+            V g1 = g0;
+            if (two) g1 = __ldg(reinterpret_cast<const V *>(gbase + (i64)s1 * T.cols));
+            const float *p0 = reinterpret_cast<const float *>(&g0), *p1 = reinterpret_cast<const float *>(&g1);
+#pragma unroll
+            for (int q = 0; q < VW; q++) { g[q] += p0[q]; if (two) g[q] += p1[q]; }
+        }
+        float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+        for (int q = 0; q < VW; q++) {
+            const float mq = ms[q] * b1 + g[q] * (1.f - b1);
+            const float vq = vs[q] * b2 + (g[q] * g[q]) * (1.f - b2);
+            ms[q] = mq; vs[q] = vq;
+            xs[q] -= lr * mq / (sqrtf(vq) + eps);
+        }
+        *reinterpret_cast<V *>(T.x + e) = xv; *reinterpret_cast<V *>(T.m + e) = mv; *reinterpret_cast<V *>(T.v + e) = vv;
     }
+}
+
+// rowhead[c][key] = [first, end) positions (within step c) of the sorted entries of table row `key`
+__global__ void mark_heads_kernel(const i32 *__restrict__ skeys, int2 *__restrict__ rowhead, i32 n, i32 rows, i64 total) {
+    const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const i32 c = (i32)(i / n), pos = (i32)(i - (i64)c * n);
+    const i32 key = skeys[i];
+    if (key >= rows) return;
+    if (pos == 0 || skeys[i - 1] != key) rowhead[(i64)c * rows + key].x = pos;
+    if (pos == n - 1 || skeys[i + 1] != key) rowhead[(i64)c * rows + key].y = pos + 1;
 }
 
 // ------------------------------------------------------------------------------------------ dispatch
@@ -550,23 +596,37 @@ int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT B, INT k, INT kr, INT *er
     return 0;
 }
 
-int okb_plan(okb_ctx *c, INT step, void *stream) {
-    if (step < 0 || step >= c->steps) OKB_FAIL(c, OKB_ERR_ARG, "step out of range (sample first)");
+// Plan steps [step_lo, step_hi) of the sampled batches with ONE radix sort.
+int okb_plan_steps(okb_ctx *c, INT step_lo, INT step_hi, void *stream) {
+    if (step_lo < 0 || step_hi > c->steps || step_lo >= step_hi) OKB_FAIL(c, OKB_ERR_ARG, "step range out of range (sample first)");
     cudaStream_t s = (cudaStream_t)stream;
     const i64 B = c->B, NE = 2 + c->K, NR = 1 + c->KR, n = B * (NE + NR), S = B * (1 + c->K + c->KR);
-    if (c->keys_ent.ensure(sizeof(i32) * n * 2) || c->perm_ent.ensure(sizeof(i32) * n))
+    const i64 C = step_hi - step_lo, ks = c->E + c->R + 1, total = C * n;
+    if (total > 0x3fffffffLL || C * ks > 0x7fffffffLL) OKB_FAIL(c, OKB_ERR_ARG, "too many steps planned at once");
+    if (c->keys_ent.ensure(sizeof(i32) * total * 2) || c->perm_ent.ensure(sizeof(i32) * total))
         OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (plan)");
     ProfScope ps(c, PROF_PLAN, s);
     PlanArgs a;
-    const i32 *base = c->batch.as<i32>() + step * 3 * S;
-    a.bh = base; a.bt = base + S; a.br = base + 2 * S;
+    a.batch = c->batch.as<i32>();
     a.keys = c->keys_ent.as<i32>();
     a.B = (i32)B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)NE; a.NR = (i32)NR; a.E = (i32)c->E; a.R = (i32)c->R;
-    plan_keys_kernel<<<(unsigned)((B + 127) / 128), 128, 0, s>>>(a);
+    a.S = (i32)S; a.step_lo = (i32)step_lo; a.C = (i32)C;
+    plan_keys_kernel<<<(unsigned)((C * B + 127) / 128), 128, 0, s>>>(a);
     OKB_LAUNCHED(1);
-    c->plan_ne = B * NE; c->plan_nr = B * NR;
-    c->ent_bits = bits_for(c->E + c->R + 1);
-    return okb_sort_pairs(c, a.keys, a.keys + n, c->perm_ent.as<i32>(), n, c->ent_bits, s);
+    c->plan_ne = B * NE; c->plan_nr = B * NR; c->plan_lo = step_lo; c->plan_hi = step_hi;
+    c->rowhead_ready = false;
+    int rc = okb_sort_pairs(c, a.keys, a.keys + total, c->perm_ent.as<i32>(), total, bits_for(C * ks), s);
+    if (rc) return rc;
+    if (C > 1) {
+        plan_fixup_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(a.keys + total, c->perm_ent.as<i32>(), (i32)n, (i32)ks, total);
+        OKB_LAUNCHED(1);
+    }
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+int okb_plan(okb_ctx *c, INT step, void *stream) {
+    if (step >= c->plan_lo && step < c->plan_hi) return 0;      // already planned as part of a chunk
+    return okb_plan_steps(c, step, step + 1, stream);
 }
 
 int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, float *gent, float *grel,
@@ -588,11 +648,11 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
     a.margin = hp->margin; a.w = 1.0f / (float)(c->B * (c->K + c->KR));
     a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)(2 + c->K); a.NR = (i32)(1 + c->KR);
     a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi;
-    const unsigned grid = (unsigned)((b_hi - b_lo + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    const unsigned grid = (unsigned)((b_hi - b_lo + GRAD_WARPS - 1) / GRAD_WARPS);
 #define CALL_GRAD(VW, NV)                                                                              \
-    if (m->model == OKB_TRANSE) grad_kernel<OKB_TRANSE, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a);      \
-    else if (m->model == OKB_TRANSH) grad_kernel<OKB_TRANSH, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a); \
-    else grad_kernel<OKB_TRANSD, VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
+    if (m->model == OKB_TRANSE) grad_kernel<OKB_TRANSE, VW, NV><<<grid, GRAD_WARPS * 32, 0, s>>>(a);      \
+    else if (m->model == OKB_TRANSH) grad_kernel<OKB_TRANSH, VW, NV><<<grid, GRAD_WARPS * 32, 0, s>>>(a); \
+    else grad_kernel<OKB_TRANSD, VW, NV><<<grid, GRAD_WARPS * 32, 0, s>>>(a)
     { ProfScope ps(c, PROF_GRAD, s); DISPATCH_LAYOUT(vw, nv, CALL_GRAD); }
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
@@ -601,41 +661,58 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
 
 int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
                const float *loss_terms, float *loss_out, void *stream) {
-    (void)step;
-    if (m->model == OKB_TRANSR) { extern int okb_transr_update(okb_ctx *, const okb_model *, const okb_hyper *, const float *, const float *, const float *, float *, void *); return okb_transr_update(c, m, hp, gent, grel, loss_terms, loss_out, stream); }
+    if (m->model == OKB_TRANSR) { extern int okb_transr_update(okb_ctx *, const okb_model *, const okb_hyper *, INT, const float *, const float *, const float *, float *, void *); return okb_transr_update(c, m, hp, step, gent, grel, loss_terms, loss_out, stream); }
     int vw, nv;
     int rc = check_model(c, m, vw, nv);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const i64 n = c->plan_ne + c->plan_nr;
-    if (n == 0) OKB_FAIL(c, OKB_ERR_STATE, "okb_plan has not run");
+    if (n == 0 || step < c->plan_lo || step >= c->plan_hi) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
+    const i64 total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
     UpdArgs a;
     a.m = *m; a.hp = *hp;
-    a.skeys = c->keys_ent.as<i32>() + n; a.perm = c->perm_ent.as<i32>();
-    a.gent = gent; a.grel = grel;
-    a.n = (i32)n; a.n_ent_slots = (i32)c->plan_ne; a.E = (i32)c->E; a.R = (i32)c->R;
+    a.skeys = c->keys_ent.as<i32>() + total + rel; a.perm = c->perm_ent.as<i32>() + rel;
+    a.gent = gent; a.grel = grel; a.loss_terms = loss_terms; a.loss_out = loss_out;
+    a.n = (i32)n; a.n_ent_slots = (i32)c->plan_ne; a.E = (i32)c->E; a.R = (i32)c->R; a.B = (i32)c->B;
+    a.w = 1.0f / (float)(c->B * (c->K + c->KR));
     group_cols(m, a.ce, a.cr);
-    a.rowseg = nullptr;
+    a.rowhead = nullptr; a.step_stamp = 0; a.ntab = 0;
+    a.work_blocks = (i32)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (m->optimizer == OKB_ADAM) {
         if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
-        const i64 rows = c->E + c->R;
-        const bool fresh = c->rowseg_e.cap < sizeof(i32) * rows;
-        if (c->rowseg_e.ensure(sizeof(i32) * rows)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowseg)");
-        if (fresh) OKB_CUDA(c, cudaMemsetAsync(c->rowseg_e.p, 0xff, c->rowseg_e.cap, s));
-        a.rowseg = c->rowseg_e.as<i32>();
-        mark_heads_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(a.skeys, a.rowseg, a.n, (i32)rows);
-        const unsigned grid = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-#define CALL_ADAM(VW, NV) adam_kernel<VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
-        { ProfScope ps(c, PROF_UPDATE, s); DISPATCH_LAYOUT(vw, nv, CALL_ADAM); }
-        OKB_LAUNCHED(2);
-    } else {
-        const unsigned grid = (unsigned)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-#define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<grid, WARPS_PER_BLOCK * 32, 0, s>>>(a)
-        { ProfScope ps(c, PROF_UPDATE, s); DISPATCH_LAYOUT(vw, nv, CALL_SGD); }
+        const i64 rows = c->E + c->R, C = c->plan_hi - c->plan_lo;
+        if (!c->rowhead_ready) {                           // once per planned chunk: integer work
+            if (c->rowseg_e.ensure(sizeof(int2) * rows * C)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowhead)");
+            OKB_CUDA(c, cudaMemsetAsync(c->rowseg_e.p, 0xff, sizeof(int2) * rows * C, s));
+            mark_heads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->keys_ent.as<i32>() + total, c->rowseg_e.as<int2>(), (i32)n, (i32)rows, total);
+            OKB_LAUNCHED(1);
+            c->rowhead_ready = true;
+        }
+        a.rowhead = c->rowseg_e.as<int2>() + (step - c->plan_lo) * rows;
+        i64 acc = 0;
+        auto add = [&](float *x, float *mm, float *vv, i64 nrows, int D, bool is_ent, int part) {
+            if (!x) return;
+            acc += nrows * D / vw;
+            DenseTab T;
+            T.x = x; T.m = mm; T.v = vv; T.grad = is_ent ? gent : grel; T.vec_end = acc; T.D = D;
+            T.key_off = is_ent ? 0 : (i32)c->E; T.cols = is_ent ? a.ce : a.cr; T.part = part;
+            T.slot_off = is_ent ? 0 : (i32)c->plan_ne;
+            a.tab[a.ntab++] = T;
+        };
+        add(m->ent, m->m_ent, m->v_ent, c->E, m->ent_dim, true, 0);
+        if (m->model == OKB_TRANSD) add(m->ent_aux, m->m_ent_aux, m->v_ent_aux, c->E, m->ent_dim, true, 1);
+        add(m->rel, m->m_rel, m->v_rel, c->R, m->rel_dim, false, 0);
+        if (m->model != OKB_TRANSE) add(m->rel_aux, m->m_rel_aux, m->v_rel_aux, c->R, m->rel_dim, false, 1);
+        a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)148 * 16);
+        ProfScope ps(c, PROF_UPDATE, s);
+        if (vw == 4) adam_kernel<4><<<a.work_blocks + 1, 256, 0, s>>>(a);
+        else if (vw == 2) adam_kernel<2><<<a.work_blocks + 1, 256, 0, s>>>(a);
+        else adam_kernel<1><<<a.work_blocks + 1, 256, 0, s>>>(a);
         OKB_LAUNCHED(1);
-    }
-    if (loss_out) {
-        loss_kernel<<<1, 1024, 0, s>>>(loss_terms, loss_out, (i32)c->B, 1.0f / (float)(c->B * (c->K + c->KR)));
+    } else {
+        ProfScope ps(c, PROF_UPDATE, s);
+#define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<a.work_blocks + 1, WARPS_PER_BLOCK * 32, 0, s>>>(a)
+        DISPATCH_LAYOUT(vw, nv, CALL_SGD);
         OKB_LAUNCHED(1);
     }
     OKB_CUDA(c, cudaGetLastError());
@@ -649,7 +726,7 @@ int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
     if (c->gent.ensure(sizeof(float) * er * ec) || c->grel.ensure(sizeof(float) * rr * rcn) ||
         c->lossterms.ensure(sizeof(float) * c->B))
         OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (gradient rows)");
-    if ((rc = okb_plan(c, step, stream))) return rc;
+    if (step < c->plan_lo || step >= c->plan_hi) { if ((rc = okb_plan(c, step, stream))) return rc; }
     if ((rc = okb_grad(c, m, hp, step, 0, c->B, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), stream))) return rc;
     return okb_update(c, m, hp, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), loss_out, stream);
 }

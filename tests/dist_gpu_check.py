@@ -1,0 +1,82 @@
+"""Run under torchrun on N GPUs of one box (not collected by pytest):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py
+
+Checks that N-rank synchronous data-parallel training leaves EVERY rank with tables bit-identical to a
+single-GPU run of the same global batch, and that candidate-sharded link prediction returns the same
+8-int records as the single-GPU ranking."""
+import ctypes
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def make(path, model, opt, W, dp):
+    import openkeonspark_b200 as okb
+    from openkeonspark_b200 import parallel
+    from conftest import make_params
+    con = okb.Config(private_context=True)
+    con.set_in_path(path)
+    con.set_nbatches(5)
+    con.set_ent_neg_rate(2)
+    con.set_rel_neg_rate(1)
+    con.set_alpha(0.01)
+    con.set_opt_method(opt)
+    con.set_dimension(100)
+    con.set_bern(1)
+    con.set_test_link_prediction(True)
+    con.set_test_head(1)
+    con.workThreads = W
+    con.init()
+    con.set_model_and_session(getattr(okb, model))
+    con.set_parameters(make_params(model, con.entTotal, con.relTotal, 100, seed=4))
+    seeds = np.arange(1, W + 1, dtype=np.uint64) * np.uint64(7919)
+    con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), W)
+    if dp:
+        parallel.attach(con)
+    return con
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    from openkeonspark_b200 import datagen
+    obj = [None]
+    if rank == 0:
+        d = tempfile.mkdtemp() + "/"
+        datagen.write_dataset(datagen.make_shape("small", seed=1, zipf=True), d, ontology=True)
+        obj = [d]
+    dist.broadcast_object_list(obj, src=0)
+    d = obj[0]
+    for model, opt in (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam")):
+        a = make(d, model, opt, 8, True)
+        b = make(d, model, opt, 8, False)
+        for it in range(4):
+            for con in (a, b):
+                con.sampling_device()
+                con.train_step_device(0)
+        pa, pb = a.get_parameters(), b.get_parameters()
+        for k in pa:
+            assert np.array_equal(pa[k], pb[k]), (model, k, rank)
+        assert float(a._loss_dev.item()) == float(b._loss_dev.item())
+        ra = a._world.link_prediction(a).cpu().numpy()
+        rb = b.link_prediction_records().cpu().numpy()
+        assert np.array_equal(ra, rb), (model, rank)
+        if rank == 0:
+            print("dp%d %s/%s: tables and link-prediction records bit-identical to single GPU" % (world, model, opt))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,8 +1,15 @@
 """Fused train step vs the CPU restatement of the TF graphs (oracle/models_ref.py).
 
-Tolerance (fp32, stated by the north star as "within a stated fp32 tolerance"): loss rtol 2e-5;
-updated parameters atol 2e-6 + rtol 1e-4 on the parameter DELTA scale.  The oracle itself is
-"parity unpinned" by the reference (TF 1.x is not installable) and is cross-checked in fp64."""
+Stated fp32 tolerances (against the fp64 run of the restatement):
+  loss .................. |dl| <= 2e-5 * |l| + 1e-6
+  SGD tables ............ max|err| <= max(4 x the fp32 CPU restatement's own error, 1e-4 * max|update| + 2e-6)
+  Adam slots m, v ....... linear / quadratic in the gradient, so they carry the gradient check:
+                          |dm| <= 1e-4 * max|m| + 1e-9 ; |dv| <= 2e-4 * max|v| + 1e-12
+  Adam tables ........... Adam normalises every element's step to ~lr regardless of |g|, so an element whose
+                          gradient is ~0 flips between -lr and +lr on fp32 rounding noise (the fp32 CPU
+                          restatement itself is up to lr away from fp64 there).  Hence: 99.5 % of elements
+                          within 1e-5, and no element further than 2 * lr * steps.
+The oracle itself is "parity unpinned" by the reference (TF 1.x is not installable)."""
 import ctypes
 
 import numpy as np
@@ -27,6 +34,9 @@ def _config(path, model, D, k, kr, opt, nbatches=6, alpha=0.01, margin=1.0, W=4,
     con.set_bern(bern)
     con.workThreads = W
     con.init()
+    # fixed streams: init() seeds from libc rand(), whose position depends on what ran before in the process
+    seeds = np.arange(1, W + 1, dtype=np.uint64) * np.uint64(2654435761)
+    con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), W)
     con.set_model_and_session(getattr(okb, model))
     return con
 
@@ -54,10 +64,17 @@ def test_train_step_parity(built, small_ds, model, opt, D, k, kr):
     exp = ref64.params()
     for name in exp:
         delta = np.abs(exp[name] - P[name]).max()
-        err = np.abs(got[name] - exp[name]).max()
+        err = np.abs(got[name] - exp[name])
         err32 = np.abs(ref32.params()[name] - exp[name]).max()
-        # the GPU must be as close to fp64 as the fp32 CPU restatement is (x4 slack) or within 1e-4 of the update size
-        assert err <= max(4 * err32, 1e-4 * delta + 2e-6), (name, err, err32, delta)
+        if opt == "SGD":
+            assert err.max() <= max(4 * err32, 1e-4 * delta + 2e-6), (name, err.max(), err32, delta)
+        else:
+            m_gpu, v_gpu = con._adam["m_" + name].cpu().numpy(), con._adam["v_" + name].cpu().numpy()
+            m_ref, v_ref = ref64.m[name].numpy(), ref64.v[name].numpy()
+            assert np.abs(m_gpu - m_ref).max() <= 1e-4 * np.abs(m_ref).max() + 1e-9, name
+            assert np.abs(v_gpu - v_ref).max() <= 2e-4 * np.abs(v_ref).max() + 1e-12, name
+            assert np.quantile(err, 0.995) <= 1e-5, (name, np.quantile(err, 0.995))
+            assert err.max() <= 2 * 0.01 * 3 + 1e-6, (name, err.max())
 
 
 def test_train_step_deterministic(built, small_ds):
@@ -97,3 +114,25 @@ def test_run_loop_reduces_loss(built, small_uniform_ds):
     con.set_train_times(6)
     losses = con.run()
     assert losses[-1] < losses[0]
+
+
+def test_chunked_lookahead_equals_step_by_step(built, small_ds):
+    """next_step_device() (64 steps sampled + planned per launch) == sampling_device()+train_step_device() per step."""
+    outs = []
+    for chunked in (False, True):
+        con = _config(small_ds, "TransD", 50, 2, 1, "Adam")
+        seeds = np.arange(1, 5, dtype=np.uint64) * 999331
+        con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), 4)
+        con.set_parameters(make_params("TransD", con.entTotal, con.relTotal, 50, seed=3))
+        con.plan_ahead = 5
+        losses = []
+        for it in range(12):
+            if chunked:
+                losses.append(float(con.next_step_device().item()))
+            else:
+                con.sampling_device()
+                losses.append(float(con.train_step_device(0).item()))
+        outs.append((losses, con.get_parameters()))
+    assert outs[0][0] == outs[1][0]
+    for name in outs[0][1]:
+        assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
