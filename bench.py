@@ -156,6 +156,8 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lp-queries", type=int, default=4096)
+    ap.add_argument("--no-kernel-events", action="store_true", help="do not record per-kernel CUDA events (no roofline object)")
+    ap.add_argument("--plan-ahead", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -212,40 +214,68 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local) if rank == 0 else None      # sampled from warm-up to the end of the timed regions
+    con.plan_ahead = args.plan_ahead
     for _ in range(args.warmup):
         one_step()
     barrier()
 
-    # ---------------- timed region: K steps, each bracketed by CUDA events, L2 flushed between steps
-    clocks = ClockSampler(local) if rank == 0 else None
-    con.ctx.call("okb_prof_enable", 1)
-    launches0 = lib.okb_launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for a, b in ev:
-        if flush is not None:
-            flush.fill_(1)
-        a.record()
-        one_step()
-        b.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    launches = lib.okb_launch_count() - launches0
-    con.ctx.call("okb_prof_enable", 0)
-    clk = clocks.stop() if clocks else None
-    ms_total = sum(a.elapsed_time(b) for a, b in ev)
-    prof = {}
-    for name, kid in (("sample", 0), ("plan", 1), ("grad", 2), ("update", 3)):
-        ms, cnt = ctypes.c_double(), ctypes.c_int64()
-        con.ctx.call("okb_prof_read", kid, ctypes.byref(ms), ctypes.byref(cnt))
-        prof[name] = (ms.value, cnt.value)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    def timed_region(kernel_events):
+        """K steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""
+        con.ctx.call("okb_prof_enable", 1 if kernel_events else 0)
+        l0 = lib.okb_launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        w0 = time.perf_counter()
+        for a, b in ev:
+            if flush is not None:
+                flush.fill_(1)
+            a.record()
+            one_step()
+            b.record()
+        barrier()
+        wall = time.perf_counter() - w0
+        con.ctx.call("okb_prof_enable", 0)
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall, lib.okb_launch_count() - l0
+
+    # ---------------- region A (headline): no per-kernel events inside the steps
+    ms_total, t_wall, launches = timed_region(False)
     ms_per_step = ms_total / args.steps
     value = con.batch_size * args.steps / (ms_total * 1e-3)      # global positives per second
+
+    # ---------------- region B (roofline): the same K steps again with a CUDA-event pair around each kernel
+    # (the extra event records cost ~10 us per step, which is why the headline is taken without them)
+    prof = {}
+    if not args.no_kernel_events:
+        ms_instr, _, _ = timed_region(True)
+        for name, kid in (("sample", 0), ("plan", 1), ("grad", 2), ("update", 3)):
+            ms, cnt = ctypes.c_double(), ctypes.c_int64()
+            con.ctx.call("okb_prof_read", kid, ctypes.byref(ms), ctypes.byref(cnt))
+            prof[name] = (ms.value, cnt.value)
+
+    # ---------------- region C: the real training loop — one library call per chunk of steps, no L2 flush
+    chunk = None
+    if world == 1:
+        n_chunks = max(1, args.steps // con.plan_ahead)
+        con.train_chunk_device()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        a.record()
+        for _ in range(n_chunks):
+            con.train_chunk_device()
+        b.record()
+        barrier()
+        ms_c = a.elapsed_time(b)
+        chunk = {"value": con.batch_size * n_chunks * con.plan_ahead / (ms_c * 1e-3), "unit": "triples/s",
+                 "ms_per_step": ms_c / (n_chunks * con.plan_ahead), "steps": n_chunks * con.plan_ahead,
+                 "wall_ms_per_step": (time.perf_counter() - w0) * 1e3 / (n_chunks * con.plan_ahead),
+                 "what": "Config.train_chunk_device(): %d steps per okb_train_steps call, tables L2-resident (no flush)" % con.plan_ahead}
+    clk = clocks.stop() if clocks else None
 
     # ---------------- e2e: the reference-shaped loop through the public API with HOST buffers
     # con.sampling() fills the numpy batch_h/t/r/y (D2H); con.train_step(...) feeds them back (H2D) and
@@ -279,7 +309,7 @@ def main():
     bytes_grad = (con.batch_size // world) * 4 * D * ((2 + k) + 2) * 2
     kern = {}
     for name, nbytes in (("update", bytes_update), ("grad", bytes_grad)):
-        ms, cnt = prof[name]
+        ms, cnt = prof.get(name, (0, 0))
         if cnt:
             kern[name] = {"ms": ms / cnt, "gbs": nbytes / (ms / cnt * 1e-3) / 1e9, "bytes": nbytes}
     dom = max(kern, key=lambda n: kern[n]["ms"]) if kern else None
@@ -288,7 +318,11 @@ def main():
         roofline = {"kernel": "adam_kernel" if dom == "update" else "grad_kernel", "bound": "hbm", "achieved": kern[dom]["gbs"],
                     "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dom]["bytes"], "avg_launch_ms": kern[dom]["ms"],
-                    "step_breakdown_ms": {n: (prof[n][0] / prof[n][1] if prof[n][1] else None) for n in prof}}
+                    "measured": "CUDA-event pair around every launch of the kernel in a second pass of the same %d steps (L2 flushed between steps)" % args.steps,
+                    "instrumented_ms_per_step": ms_instr / args.steps,
+                    "per_launch_ms": {n: (prof[n][0] / prof[n][1] if prof[n][1] else None) for n in prof},
+                    "launches_in_pass": {n: prof[n][1] for n in prof},
+                    "other_kernels": {n: {"GB/s": kern[n]["gbs"], "frac": kern[n]["gbs"] / peak, "bytes": kern[n]["bytes"]} for n in kern if n != dom}}
 
     # ---------------- secondary metric: filtered link-prediction queries/s (both sides)
     lp = None
@@ -326,7 +360,7 @@ def main():
                            "l2": "not flushed" if flush is None else "flushed between timed steps (256 MiB fill, outside the per-step events)",
                            "timing": "per-step CUDA events summed; max over ranks", "parallelism": "dp%d" % world},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                "link_prediction": lp, "wall_s_timed_region_incl_flush": t_wall}
+                "link_prediction": lp, "training_loop_chunked": chunk, "wall_s_timed_region_incl_flush": t_wall}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -174,6 +174,10 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
                const float *grad_rel, const float *loss_terms, float *loss_out, void *cuda_stream);
 int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, float *loss_out,
                    void *cuda_stream);
+/* n consecutive steps in one call (plans them with one sort if needed); hp[n] host array (Adam's lr_t differs
+ * per step), loss_out: device float[n] or NULL. */
+int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out,
+                    void *cuda_stream);
 
 /* ---- scoring = TransX.predict_def (TransE.py:53-58 ...).  h,t,r: device int64[n]; out: device
  *      float[n] (TransE: mean over d; others: sum).  Canonical evaluation order, see DESIGN.md. */

@@ -409,6 +409,25 @@ class Config(object):
         self._step += 1
         return self._loss_dev
 
+    def train_chunk_device(self, n=None):
+        """`n` iterations of the train loop in ONE library call: sample n batches, plan them with one sort,
+        then n x (grad + update).  Returns the device tensor of the n losses.  Same results as n calls of
+        next_step_device(); exists because a Python round trip per step costs more than the step."""
+        self._ensure_model()
+        cap = max(1, (1 << 24) // (self.batch_size * (3 + self.negative_ent + self.negative_rel)))
+        n = max(1, min(int(self.plan_ahead if n is None else n), cap))
+        if self._world is not None:
+            return torch.stack([self.next_step_device().clone() for _ in range(n)]).reshape(-1)
+        self.sampling_device(n)
+        m = self._cmodel()
+        hps = (okb_hyper * n)(*[self._hyper() for _ in range(n)])
+        if getattr(self, "_loss_chunk", None) is None or self._loss_chunk.numel() < n:
+            self._loss_chunk = torch.zeros(n, dtype=torch.float32, device=self.trainModel.device)
+        self.ctx.call("okb_train_steps", ctypes.byref(m), hps, 0, n, _vp(self._loss_chunk.data_ptr()), _stream())
+        self._step += n
+        self._chunk_pos = self._chunk_len = 0
+        return self._loss_chunk[:n]
+
     def train_step(self, batch_h, batch_t, batch_r, batch_y):
         """Perform a single training step on a caller-provided batch (Config.py:464-475)."""
         self._ensure_model()
@@ -428,11 +447,13 @@ class Config(object):
         for epoch in range(self.train_times):
             t0 = time.time()
             acc = torch.zeros(1, dtype=torch.float32, device=self._loss_dev.device)
-            for batch in range(self.nbatches):
-                loss = self.next_step_device()
-                acc += loss
-                if self.log_every and (self._step % self.log_every == 0):
-                    print("Global step: {} Epoch: {} Batch: {} loss: {}".format(self._step, epoch, batch, float(loss.item())))
+            batch = 0
+            while batch < self.nbatches:
+                losses_dev = self.train_chunk_device(min(self.plan_ahead, self.nbatches - batch))
+                acc += losses_dev.sum()
+                batch += losses_dev.numel()
+                if self.log_every and (self._step // self.log_every != (self._step - losses_dev.numel()) // self.log_every):
+                    print("Global step: {} Epoch: {} Batch: {} loss: {}".format(self._step, epoch, batch - 1, float(losses_dev[-1].item())))
             res = float(acc.item())
             losses.append(res)
             print("Epoch: {} loss: {} ({:.3f} s)".format(epoch, res, time.time() - t0))

@@ -63,6 +63,7 @@ _SIGS = {
     "okb_grad": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "okb_update": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _vp, _vp, _vp, _vp, _vp]),
     "okb_train_step": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _vp, _vp]),
+    "okb_train_steps": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _vp, _vp]),
     "okb_predict": (_int, [_vp, C.POINTER(okb_model), _vp, _vp, _vp, _i64, _vp, _vp]),
     "okb_rank": (_int, [_vp, C.POINTER(okb_model), _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "okb_rank_finalize": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),

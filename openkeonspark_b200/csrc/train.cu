@@ -422,7 +422,8 @@ struct UpdArgs {
     const i32 *skeys, *perm;   // sorted keys / slot of each sorted position (this step)
     const float *gent, *grel, *loss_terms;
     float *loss_out;
-    const int2 *rowhead;       // Adam: [first, end) sorted positions of each table row in this step's plan; first = -1 if untouched
+    const int4 *rowhead;       // Adam: {first, end, slot0, slot1}: sorted-position range of each table row in this step's
+                               // plan (first = -1 if untouched) with its first two gradient slots inlined
     DenseTab tab[4];
     i32 n, n_ent_slots, E, R, ce, cr, B, step_stamp, ntab, work_blocks;
     float w;
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
 // own columns: coalesced), then the same Adam arithmetic runs everywhere.
 //   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; x <- x - lr_t m / (sqrt(v) + eps)
 template <int VW>
-__global__ void __launch_bounds__(256) adam_kernel(UpdArgs a) {
+__global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
     if ((i32)blockIdx.x == a.work_blocks) { loss_block(a); return; }
     typedef typename VecT<VW>::T V;
     const i64 total = a.tab[a.ntab - 1].vec_end;
@@ -510,21 +511,27 @@ __global__ void __launch_bounds__(256) adam_kernel(UpdArgs a) {
         const unsigned row = lv / vpr, col = (lv - row * vpr) * VW;
         const i64 e = (i64)lv * VW;
         // issue every independent load before the first dependent use
-        const int2 seg = __ldg(a.rowhead + T.key_off + row);
+        const int4 seg = __ldg(a.rowhead + T.key_off + row);
         V xv = *reinterpret_cast<const V *>(T.x + e), mv = *reinterpret_cast<const V *>(T.m + e), vv = *reinterpret_cast<const V *>(T.v + e);
         float g[VW];
 #pragma unroll
         for (int q = 0; q < VW; q++) g[q] = 0.f;
-        const float *gbase = T.grad + T.part * T.D + col;
-        for (i32 j = seg.x; j < seg.y; j += 2) {               // seg.x = -1, seg.y = -1 when untouched
-            const bool two = j + 1 < seg.y;
-            const i32 s0 = __ldg(a.perm + j) - T.slot_off, s1 = two ? __ldg(a.perm + j + 1) - T.slot_off : 0;
-            const V g0 = __ldg(reinterpret_cast<const V *>(gbase + (i64)s0 * T.cols));
+        if (seg.x >= 0) {
+            const float *gbase = T.grad + T.part * T.D + col;
+            const i32 cnt = seg.y - seg.x;
+            // the first two contributions come straight from the row map: no perm[] hop for the common case
+            const V g0 = __ldg(reinterpret_cast<const V *>(gbase + (i64)(seg.z - T.slot_off) * T.cols));
             V g1 = g0;
-            if (two) g1 = __ldg(reinterpret_cast<const V *>(gbase + (i64)s1 * T.cols));
+            if (cnt > 1) g1 = __ldg(reinterpret_cast<const V *>(gbase + (i64)(seg.w - T.slot_off) * T.cols));
             const float *p0 = reinterpret_cast<const float *>(&g0), *p1 = reinterpret_cast<const float *>(&g1);
 #pragma unroll
-            for (int q = 0; q < VW; q++) { g[q] += p0[q]; if (two) g[q] += p1[q]; }
+            for (int q = 0; q < VW; q++) { g[q] += p0[q]; if (cnt > 1) g[q] += p1[q]; }
+            for (i32 j = seg.x + 2; j < seg.y; j++) {
+                const V gj = __ldg(reinterpret_cast<const V *>(gbase + (i64)(__ldg(a.perm + j) - T.slot_off) * T.cols));
+                const float *pj = reinterpret_cast<const float *>(&gj);
+#pragma unroll
+                for (int q = 0; q < VW; q++) g[q] += pj[q];
+            }
         }
         float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
 #pragma unroll
@@ -538,15 +545,20 @@ __global__ void __launch_bounds__(256) adam_kernel(UpdArgs a) {
     }
 }
 
-// rowhead[c][key] = [first, end) positions (within step c) of the sorted entries of table row `key`
-__global__ void mark_heads_kernel(const i32 *__restrict__ skeys, int2 *__restrict__ rowhead, i32 n, i32 rows, i64 total) {
+// rowhead[c][key] = {first, end, slot0, slot1}: range (within step c) of the sorted entries of table row
+// `key` and the gradient slots of its first two entries
+__global__ void mark_heads_kernel(const i32 *__restrict__ skeys, const i32 *__restrict__ perm, int4 *__restrict__ rowhead,
+                                  i32 n, i32 rows, i64 total) {
     const i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const i32 c = (i32)(i / n), pos = (i32)(i - (i64)c * n);
     const i32 key = skeys[i];
     if (key >= rows) return;
-    if (pos == 0 || skeys[i - 1] != key) rowhead[(i64)c * rows + key].x = pos;
-    if (pos == n - 1 || skeys[i + 1] != key) rowhead[(i64)c * rows + key].y = pos + 1;
+    int4 *o = rowhead + (i64)c * rows + key;
+    const bool first = pos == 0 || skeys[i - 1] != key;
+    if (first) { o->x = pos; o->z = perm[i]; }
+    else if (pos == 1 || skeys[i - 2] != key) o->w = perm[i];      // second entry of its segment
+    if (pos == n - 1 || skeys[i + 1] != key) o->y = pos + 1;
 }
 
 // ------------------------------------------------------------------------------------------ dispatch
@@ -682,13 +694,13 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
         const i64 rows = c->E + c->R, C = c->plan_hi - c->plan_lo;
         if (!c->rowhead_ready) {                           // once per planned chunk: integer work
-            if (c->rowseg_e.ensure(sizeof(int2) * rows * C)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowhead)");
-            OKB_CUDA(c, cudaMemsetAsync(c->rowseg_e.p, 0xff, sizeof(int2) * rows * C, s));
-            mark_heads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->keys_ent.as<i32>() + total, c->rowseg_e.as<int2>(), (i32)n, (i32)rows, total);
+            if (c->rowseg_e.ensure(sizeof(int4) * rows * C)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowhead)");
+            OKB_CUDA(c, cudaMemsetAsync(c->rowseg_e.p, 0xff, sizeof(int4) * rows * C, s));
+            mark_heads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->keys_ent.as<i32>() + total, c->perm_ent.as<i32>(), c->rowseg_e.as<int4>(), (i32)n, (i32)rows, total);
             OKB_LAUNCHED(1);
             c->rowhead_ready = true;
         }
-        a.rowhead = c->rowseg_e.as<int2>() + (step - c->plan_lo) * rows;
+        a.rowhead = c->rowseg_e.as<int4>() + (step - c->plan_lo) * rows;
         i64 acc = 0;
         auto add = [&](float *x, float *mm, float *vv, i64 nrows, int D, bool is_ent, int part) {
             if (!x) return;
@@ -729,6 +741,24 @@ int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
     if (step < c->plan_lo || step >= c->plan_hi) { if ((rc = okb_plan(c, step, stream))) return rc; }
     if ((rc = okb_grad(c, m, hp, step, 0, c->B, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), stream))) return rc;
     return okb_update(c, m, hp, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), loss_out, stream);
+}
+
+
+// `n` consecutive train steps (steps step_lo .. step_lo+n-1 of the sampled batches) in one call: the
+// host-side loop of distribute_training.py:267-283 without a Python round trip per step.
+// hp[i] are the per-step hyper-parameters (Adam's lr_t changes every step); loss_out[i] (device) receives
+// each step's loss, or pass NULL.
+int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out, void *stream) {
+    if (step_lo < 0 || n < 1 || step_lo + n > c->steps) OKB_FAIL(c, OKB_ERR_ARG, "step range out of range (sample first)");
+    if (step_lo < c->plan_lo || step_lo + n > c->plan_hi) {
+        int rc = okb_plan_steps(c, step_lo, step_lo + n, stream);
+        if (rc) return rc;
+    }
+    for (INT i = 0; i < n; i++) {
+        int rc = okb_train_step(c, m, hp + i, step_lo + i, loss_out ? loss_out + i : nullptr, stream);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 }  // extern "C"

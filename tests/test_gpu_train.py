@@ -133,6 +133,15 @@ def test_chunked_lookahead_equals_step_by_step(built, small_ds):
                 con.sampling_device()
                 losses.append(float(con.train_step_device(0).item()))
         outs.append((losses, con.get_parameters()))
-    assert outs[0][0] == outs[1][0]
+    # and the one-call-per-chunk C loop (Config.train_chunk_device / okb_train_steps)
+    con = _config(small_ds, "TransD", 50, 2, 1, "Adam")
+    con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), 4)
+    con.set_parameters(make_params("TransD", con.entTotal, con.relTotal, 50, seed=3))
+    losses = []
+    for n in (5, 5, 2):
+        losses += [float(x) for x in con.train_chunk_device(n).cpu().numpy()]
+    outs.append((losses, con.get_parameters()))
+    assert outs[0][0] == outs[1][0] == outs[2][0]
     for name in outs[0][1]:
         assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
+        assert np.array_equal(outs[0][1][name], outs[2][1][name]), name
