@@ -163,11 +163,13 @@ class Config(object):
 
     def _alloc_batch(self):
         """(Re)allocate the caller-visible numpy batch buffers (Config.py:172-180)."""
-        self.batch_seq_size = self.batch_size * (1 + self.negative_ent + self.negative_rel)
-        self.batch_h = np.zeros(self.batch_seq_size, dtype=np.int64)
-        self.batch_t = np.zeros(self.batch_seq_size, dtype=np.int64)
-        self.batch_r = np.zeros(self.batch_seq_size, dtype=np.int64)
-        self.batch_y = np.zeros(self.batch_seq_size, dtype=np.float32)
+        self.batch_seq_size = S = self.batch_size * (1 + self.negative_ent + self.negative_rel)
+        # page-locked and contiguous, so sampling()/train_step() move the three id arrays with ONE DMA each way
+        self._batch_pinned = torch.zeros(3 * S, dtype=torch.int64).pin_memory()
+        self._batch_y_pinned = torch.zeros(S, dtype=torch.float32).pin_memory()
+        ids = self._batch_pinned.numpy()
+        self.batch_h, self.batch_t, self.batch_r = ids[:S], ids[S:2 * S], ids[2 * S:]
+        self.batch_y = self._batch_y_pinned.numpy()
         self.batch_h_addr = self.batch_h.__array_interface__["data"][0]
         self.batch_t_addr = self.batch_t.__array_interface__["data"][0]
         self.batch_r_addr = self.batch_r.__array_interface__["data"][0]

@@ -231,9 +231,13 @@ int okb_batch_to_host(okb_ctx *c, INT step, INT *h, INT *t, INT *r, REAL *y, voi
     float *dy = (float *)(dr + S);
     widen_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(c->batch.as<i32>() + step * 3 * S, dh, dt, dr, dy, (i32)S, (i32)c->B);
     OKB_LAUNCHED(1);
-    OKB_CUDA(c, cudaMemcpyAsync(h, dh, sizeof(i64) * S, cudaMemcpyDeviceToHost, s));
-    OKB_CUDA(c, cudaMemcpyAsync(t, dt, sizeof(i64) * S, cudaMemcpyDeviceToHost, s));
-    OKB_CUDA(c, cudaMemcpyAsync(r, dr, sizeof(i64) * S, cudaMemcpyDeviceToHost, s));
+    if (t == h + S && r == t + S) {                        // caller's three arrays are one block: one copy
+        OKB_CUDA(c, cudaMemcpyAsync(h, dh, sizeof(i64) * 3 * S, cudaMemcpyDeviceToHost, s));
+    } else {
+        OKB_CUDA(c, cudaMemcpyAsync(h, dh, sizeof(i64) * S, cudaMemcpyDeviceToHost, s));
+        OKB_CUDA(c, cudaMemcpyAsync(t, dt, sizeof(i64) * S, cudaMemcpyDeviceToHost, s));
+        OKB_CUDA(c, cudaMemcpyAsync(r, dr, sizeof(i64) * S, cudaMemcpyDeviceToHost, s));
+    }
     if (y) OKB_CUDA(c, cudaMemcpyAsync(y, dy, sizeof(float) * S, cudaMemcpyDeviceToHost, s));
     OKB_CUDA(c, cudaStreamSynchronize(s));
     return 0;
@@ -247,12 +251,19 @@ int okb_batch_from_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const IN
     c->B = B; c->K = k; c->KR = kr; c->steps = 1;
     c->plan_lo = c->plan_hi = 0;
     i64 *dh = c->host_io.as<i64>(), *dt = dh + S, *dr = dt + S;
-    OKB_CUDA(c, cudaMemcpyAsync(dh, h, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
-    OKB_CUDA(c, cudaMemcpyAsync(dt, t, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
-    OKB_CUDA(c, cudaMemcpyAsync(dr, r, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
+    if (t == h + S && r == t + S) {
+        OKB_CUDA(c, cudaMemcpyAsync(dh, h, sizeof(i64) * 3 * S, cudaMemcpyHostToDevice, s));
+    } else {
+        OKB_CUDA(c, cudaMemcpyAsync(dh, h, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
+        OKB_CUDA(c, cudaMemcpyAsync(dt, t, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
+        OKB_CUDA(c, cudaMemcpyAsync(dr, r, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
+    }
     narrow_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(dh, dt, dr, c->batch.as<i32>(), (i32)S);
     OKB_LAUNCHED(1);
-    OKB_CUDA(c, cudaStreamSynchronize(s));
+    // no synchronisation needed: the copies are stream-ordered before the kernel; pageable sources are
+    // staged by the driver before the call returns, pinned sources must stay untouched until the step ran
+    // (Config.train_step reads the loss back, which synchronises)
+    OKB_CUDA(c, cudaGetLastError());
     return 0;
 }
 
