@@ -49,6 +49,32 @@ struct PredArgs {
     i32 E, R;
 };
 
+#define TRANSR_MAXD 256
+// TransR.py:77-87: every row is projected by the matrix of predict_r[0] (r0), its own r only picks rel_embeddings
+__device__ float pred_one_transr(const okb_model &m, i64 h, i64 t, i64 r, i64 r0) {
+    const int De = m.ent_dim, Dr = m.rel_dim;
+    const float *eh = m.ent + h * De, *et = m.ent + t * De, *er = m.rel + r * Dr, *M = m.rel_aux + r0 * (i64)De * Dr;
+    float hp[TRANSR_MAXD], tp[TRANSR_MAXD];
+    float sh = 0.f, st = 0.f;
+    for (int k = 0; k < Dr; k++) {
+        float a = 0.f, b = 0.f;
+        for (int d = 0; d < De; d++) {
+            const float mk = M[(i64)d * Dr + k];
+            a = __fadd_rn(a, __fmul_rn(eh[d], mk));
+            b = __fadd_rn(b, __fmul_rn(et[d], mk));
+        }
+        hp[k] = a; tp[k] = b;
+    }
+    for (int k = 0; k < Dr; k++) { sh = __fadd_rn(sh, __fmul_rn(hp[k], hp[k])); st = __fadd_rn(st, __fmul_rn(tp[k], tp[k])); }
+    const float ih = c_inv_norm(sh), it = c_inv_norm(st), ir = c_inv_norm(c_dot(er, 1, er, 1, Dr));
+    float s = 0.f;
+    for (int k = 0; k < Dr; k++) {
+        const float a = __fadd_rn(__fmul_rn(hp[k], ih), __fmul_rn(er[k], ir));
+        s = __fadd_rn(s, fabsf(__fsub_rn(a, __fmul_rn(tp[k], it))));
+    }
+    return s;
+}
+
 __device__ float pred_one(const okb_model &m, i64 h, i64 t, i64 r) {
     const int D = m.ent_dim;
     const float *eh = m.ent + h * D, *et = m.ent + t * D, *er = m.rel + r * D;
@@ -107,7 +133,7 @@ __global__ void __launch_bounds__(128) predict_kernel(PredArgs a) {
     if (i >= a.n) return;
     const i64 h = a.h[i], t = a.t[i], r = a.r[i];
     if (h < 0 || h >= a.E || t < 0 || t >= a.E || r < 0 || r >= a.R) { a.out[i] = __int_as_float(0x7fc00000); return; }
-    a.out[i] = pred_one(a.m, h, t, r);
+    a.out[i] = a.m.model == OKB_TRANSR ? pred_one_transr(a.m, h, t, r, a.r[0]) : pred_one(a.m, h, t, r);
 }
 
 // ------------------------------------------------------------------------------------------ rank: preparation
@@ -115,7 +141,7 @@ __global__ void __launch_bounds__(128) predict_kernel(PredArgs a) {
 __global__ void relvec_kernel(okb_model m, const i32 *__restrict__ grp_rel, float *__restrict__ rv, i32 G) {
     const i32 g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
-    const int D = m.ent_dim;
+    const int D = m.rel_dim;
     const i64 r = grp_rel[g];
     const float *er = m.rel + r * D;
     float *o = rv + (i64)g * 2 * D;
@@ -131,18 +157,27 @@ __global__ void relvec_kernel(okb_model m, const i32 *__restrict__ grp_rel, floa
     }
 }
 
-// In-place canonical transfer + l2-normalise of one entity row held in shared memory (lane-private,
-// unit stride), given the group's auxiliary vector `aux` and (TransD) the entity's transfer row.
-__device__ __forceinline__ void canon_row(int model, float *row, const float *aux, const float *et_row, int D) {
+// Canonical transfer + l2-normalise of one entity row held in shared memory (lane-private, unit
+// stride).  `in` has Din floats; the result (D floats) is left in `out` (== in except for TransR, whose
+// projection e . M_r changes the dimension).  aux: TransH n_hat / TransD rel_transfer; et_row: TransD
+// ent_transfer[e]; Msm: TransR matrix of the group, row-major [Din][D] in shared memory.
+__device__ __forceinline__ void canon_row(int model, const float *in, float *out, const float *aux, const float *et_row,
+                                          const float *Msm, int Din, int D) {
     if (model == OKB_TRANSH) {
-        const float dh = c_dot(row, 1, aux, 1, D);
-        for (int d = 0; d < D; d++) row[d] = __fsub_rn(row[d], __fmul_rn(dh, aux[d]));
+        const float dh = c_dot(in, 1, aux, 1, D);
+        for (int d = 0; d < D; d++) out[d] = __fsub_rn(in[d], __fmul_rn(dh, aux[d]));
     } else if (model == OKB_TRANSD) {
-        const float ch = c_dot(row, 1, et_row, 1, D);
-        for (int d = 0; d < D; d++) row[d] = __fadd_rn(row[d], __fmul_rn(ch, aux[d]));
+        const float ch = c_dot(in, 1, et_row, 1, D);
+        for (int d = 0; d < D; d++) out[d] = __fadd_rn(in[d], __fmul_rn(ch, aux[d]));
+    } else if (model == OKB_TRANSR) {
+        for (int k = 0; k < D; k++) {
+            float a = 0.f;
+            for (int d = 0; d < Din; d++) a = __fadd_rn(a, __fmul_rn(in[d], Msm[d * D + k]));
+            out[k] = a;
+        }
     }
-    const float inv = c_inv_norm(c_dot(row, 1, row, 1, D));
-    for (int d = 0; d < D; d++) row[d] = __fmul_rn(row[d], inv);
+    const float inv = c_inv_norm(c_dot(out, 1, out, 1, D));
+    for (int d = 0; d < D; d++) out[d] = __fmul_rn(out[d], inv);
 }
 
 // Candidate tables: out[tab][d][j - j0] for entities j in [j0, j0 + ncol) (ncol multiple of CT, zero padded).
@@ -151,36 +186,45 @@ __device__ __forceinline__ void canon_row(int model, float *row, const float *au
 struct CandArgs {
     okb_model m;
     const float *rv;           // [G][2][D]
+    const i32 *grp_rel;        // relation of each group (TransR: selects M_r)
     float *out;                // [ntab][D][ncol]
     i32 j0, ncol, E, ntab;
 };
+// dynamic shared memory: per warp 32 input rows [Din+1] (+32 rows of a second array: TransD ent_transfer /
+// TransR projected output [D+1]); per block the group's aux vector [D] (+ TransR: M_r [Din*D])
 __global__ void __launch_bounds__(128) cand_kernel(CandArgs a) {
-    const int wpb = blockDim.x >> 5;
     extern __shared__ float sm[];
-    const int D = a.m.ent_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int stride = D + 1;
-    const bool need_et = a.m.model == OKB_TRANSD;
-    float *rows = sm + (size_t)w * 32 * stride * (need_et ? 2 : 1);
-    float *ets = rows + 32 * stride;
-    float *aux = sm + (size_t)wpb * 32 * stride * (need_et ? 2 : 1);   // [D] per block
+    const int wpb = blockDim.x >> 5;
+    const int Din = a.m.ent_dim, D = a.m.rel_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sin = Din + 1, s2 = (a.m.model == OKB_TRANSR ? D : Din) + 1;
+    const bool second = a.m.model == OKB_TRANSD || a.m.model == OKB_TRANSR;
+    const size_t per_warp = (size_t)32 * sin + (second ? (size_t)32 * s2 : 0);
+    float *rows = sm + (size_t)w * per_warp;
+    float *rows2 = rows + 32 * sin;
+    float *aux = sm + (size_t)wpb * per_warp;              // [D]
+    float *Msm = aux + ((D + 3) & ~3);                     // [Din*D] (TransR)
     const i32 tab = blockIdx.y;
     const i32 jbase = a.j0 + (blockIdx.x * wpb + w) * 32;
-    if (a.m.model != OKB_TRANSE) {
+    if (a.m.model == OKB_TRANSH || a.m.model == OKB_TRANSD)
         for (int d = threadIdx.x; d < D; d += blockDim.x) aux[d] = a.rv[((i64)tab * 2 + 1) * D + d];
+    if (a.m.model == OKB_TRANSR) {
+        const float *M = a.m.rel_aux + (i64)a.grp_rel[tab] * Din * D;
+        for (int d = threadIdx.x; d < Din * D; d += blockDim.x) Msm[d] = M[d];
     }
-    for (int idx = lane; idx < 32 * D; idx += 32) {
-        const int rr = idx / D, d = idx - rr * D;
+    for (int idx = lane; idx < 32 * Din; idx += 32) {
+        const int rr = idx / Din, d = idx - rr * Din;
         const i32 j = jbase + rr;
-        rows[rr * stride + d] = j < a.E ? a.m.ent[(i64)j * D + d] : 0.f;
-        if (need_et) ets[rr * stride + d] = j < a.E ? a.m.ent_aux[(i64)j * D + d] : 0.f;
+        rows[rr * sin + d] = j < a.E ? a.m.ent[(i64)j * Din + d] : 0.f;
+        if (a.m.model == OKB_TRANSD) rows2[rr * s2 + d] = j < a.E ? a.m.ent_aux[(i64)j * Din + d] : 0.f;
     }
     __syncthreads();
     const i32 j = jbase + lane;
-    if (j < a.E) canon_row(a.m.model, rows + lane * stride, aux, ets + lane * stride, D);
+    float *res = a.m.model == OKB_TRANSR ? rows2 + lane * s2 : rows + lane * sin;
+    if (j < a.E) canon_row(a.m.model, rows + lane * sin, res, aux, rows2 + lane * s2, Msm, Din, D);
     __syncwarp();
     const i32 col = jbase - a.j0 + lane;
     if (col < a.ncol)
-        for (int d = 0; d < D; d++) a.out[((i64)tab * D + d) * a.ncol + col] = j < a.E ? rows[lane * stride + d] : 0.f;
+        for (int d = 0; d < D; d++) a.out[((i64)tab * D + d) * a.ncol + col] = j < a.E ? res[d] : 0.f;
 }
 
 // Query vectors for test triples [q_lo, q_hi): qa[q][d] = fl(h_hat[d] + r_hat[d]) (tail side),
@@ -189,35 +233,42 @@ struct QArgs {
     okb_model m;
     const i32 *th, *tt, *tr;
     const i32 *q_group;        // group index of each query (relative to chunk)
+    const i32 *grp_rel;
     const float *rv;
     float *qa, *qt, *ref;
     i32 q_lo, nq;
 };
+// dynamic shared memory per warp: H, T input rows [32][Din+1]; a second pair (TransD: ent_transfer rows,
+// TransR: projected outputs [32][D+1]).  TransR reads M_r from global memory (queries of a warp may span groups).
 __global__ void __launch_bounds__(128) qvec_kernel(QArgs a) {
     extern __shared__ float sm[];
-    const int D = a.m.ent_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int stride = D + 1;
-    const bool need_et = a.m.model == OKB_TRANSD;
+    const int Din = a.m.ent_dim, D = a.m.rel_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sin = Din + 1, s2 = (a.m.model == OKB_TRANSR ? D : Din) + 1;
+    const bool second = a.m.model == OKB_TRANSD || a.m.model == OKB_TRANSR;
     const int wpb = blockDim.x >> 5;
-    float *H = sm + (size_t)w * 32 * stride * (need_et ? 4 : 2), *T = H + 32 * stride, *EH = T + 32 * stride, *ET = EH + 32 * stride;
+    const size_t per_warp = (size_t)2 * 32 * sin + (second ? (size_t)2 * 32 * s2 : 0);
+    float *H = sm + (size_t)w * per_warp, *T = H + 32 * sin, *H2 = T + 32 * sin, *T2 = H2 + 32 * s2;
     const i32 qbase = (blockIdx.x * wpb + w) * 32;
     for (int rr = 0; rr < 32; rr++) {
         const i32 q = qbase + rr;
         if (q >= a.nq) break;
         const i64 h = a.th[a.q_lo + q], t = a.tt[a.q_lo + q];
-        for (int d = lane; d < D; d += 32) {
-            H[rr * stride + d] = a.m.ent[h * D + d];
-            T[rr * stride + d] = a.m.ent[t * D + d];
-            if (need_et) { EH[rr * stride + d] = a.m.ent_aux[h * D + d]; ET[rr * stride + d] = a.m.ent_aux[t * D + d]; }
+        for (int d = lane; d < Din; d += 32) {
+            H[rr * sin + d] = a.m.ent[h * Din + d];
+            T[rr * sin + d] = a.m.ent[t * Din + d];
+            if (a.m.model == OKB_TRANSD) { H2[rr * s2 + d] = a.m.ent_aux[h * Din + d]; T2[rr * s2 + d] = a.m.ent_aux[t * Din + d]; }
         }
     }
     __syncwarp();
     const i32 q = qbase + lane;
     if (q >= a.nq) return;
-    const float *rv = a.rv + (i64)a.q_group[q] * 2 * D;
-    float *h = H + lane * stride, *t = T + lane * stride;
-    canon_row(a.m.model, h, rv + D, EH + lane * stride, D);
-    canon_row(a.m.model, t, rv + D, ET + lane * stride, D);
+    const i32 g = a.q_group[q];
+    const float *rv = a.rv + (i64)g * 2 * D;
+    const float *M = a.m.model == OKB_TRANSR ? a.m.rel_aux + (i64)a.grp_rel[g] * Din * D : nullptr;
+    float *h = a.m.model == OKB_TRANSR ? H2 + lane * s2 : H + lane * sin;
+    float *t = a.m.model == OKB_TRANSR ? T2 + lane * s2 : T + lane * sin;
+    canon_row(a.m.model, H + lane * sin, h, rv + D, H2 + lane * s2, M, Din, D);
+    canon_row(a.m.model, T + lane * sin, t, rv + D, T2 + lane * s2, M, Din, D);
     float s = 0.f;
     for (int d = 0; d < D; d++) {
         const float x = __fadd_rn(h[d], rv[d]);
@@ -487,8 +538,8 @@ extern bool okb_pick_layout(int D, int &vw, int &nv);
 
 static int check_score_model(okb_ctx *c, const okb_model *m) {
     if (!m || !m->ent || !m->rel) OKB_FAIL(c, OKB_ERR_ARG, "model tables missing");
-    if (m->model == OKB_TRANSR) OKB_FAIL(c, OKB_ERR_ARG, "TransR scoring is handled by transr.cu");
-    if (m->ent_dim != m->rel_dim) OKB_FAIL(c, OKB_ERR_ARG, "TransE/H/D need ent_dim == rel_dim");
+    if (m->model != OKB_TRANSR && m->ent_dim != m->rel_dim) OKB_FAIL(c, OKB_ERR_ARG, "TransE/H/D need ent_dim == rel_dim");
+    if (m->model == OKB_TRANSR && m->rel_dim > TRANSR_MAXD) OKB_FAIL(c, OKB_ERR_ARG, "TransR rel_dim > 256 not supported");
     if (m->model != OKB_TRANSE && !m->rel_aux) OKB_FAIL(c, OKB_ERR_ARG, "rel_aux table missing");
     if (m->model == OKB_TRANSD && !m->ent_aux) OKB_FAIL(c, OKB_ERR_ARG, "ent_aux table missing");
     return 0;
@@ -498,7 +549,6 @@ extern "C" {
 
 int okb_predict(okb_ctx *c, const okb_model *m, const int64_t *h, const int64_t *t, const int64_t *r, INT n, float *out,
                 void *stream) {
-    if (m && m->model == OKB_TRANSR) { extern int okb_transr_predict(okb_ctx *, const okb_model *, const int64_t *, const int64_t *, const int64_t *, INT, float *, void *); return okb_transr_predict(c, m, h, t, r, n, out, stream); }
     int rc = check_score_model(c, m);
     if (rc) return rc;
     if (n <= 0) return 0;
@@ -512,7 +562,6 @@ int okb_predict(okb_ctx *c, const okb_model *m, const int64_t *h, const int64_t 
 
 int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT cand_lo, INT cand_hi, int64_t *counts,
              uint64_t *best, void *stream) {
-    if (m && m->model == OKB_TRANSR) { extern int okb_transr_rank(okb_ctx *, const okb_model *, INT, INT, int, INT, INT, int64_t *, uint64_t *, void *); return okb_transr_rank(c, m, q_lo, q_hi, heads, cand_lo, cand_hi, counts, best, stream); }
     int rc = check_score_model(c, m);
     if (rc) return rc;
     if (!c->d_test_h || !c->have_types) OKB_FAIL(c, OKB_ERR_STATE, "import test and type files first");
@@ -520,7 +569,7 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
     if (cand_lo < 0 || cand_hi > c->E || cand_lo >= cand_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad candidate range");
     if (q_lo == q_hi) return 0;
     cudaStream_t s = (cudaStream_t)stream;
-    const int D = m->ent_dim;
+    const int D = m->rel_dim, Din = m->ent_dim;              // D: dimension the L1 distance runs over
     const i64 j0 = (cand_lo / CT) * CT;
     const i64 ncol = ((cand_hi - j0 + CT - 1) / CT) * CT;
     const bool per_group = m->model != OKB_TRANSE;
@@ -547,12 +596,15 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         cudaFuncSetAttribute(qvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
-    const int narr_c = m->model == OKB_TRANSD ? 2 : 1, narr_q = m->model == OKB_TRANSD ? 4 : 2;
+    const bool second = m->model == OKB_TRANSD || m->model == OKB_TRANSR;
+    const size_t s2 = (m->model == OKB_TRANSR ? D : Din) + 1;
+    const size_t warp_c = (size_t)32 * (Din + 1) + (second ? 32 * s2 : 0), warp_q = 2 * warp_c;
+    const size_t blk_c = ((D + 3) & ~3) + (m->model == OKB_TRANSR ? (size_t)Din * D : 0);
     int wpb_c = 4, wpb_q = 4;
-    while (wpb_c > 1 && sizeof(float) * ((size_t)wpb_c * 32 * (D + 1) * narr_c + D) > 100 * 1024) wpb_c >>= 1;
-    while (wpb_q > 1 && sizeof(float) * (size_t)wpb_q * 32 * (D + 1) * narr_q > 100 * 1024) wpb_q >>= 1;
-    const size_t smem_cand = sizeof(float) * ((size_t)wpb_c * 32 * (D + 1) * narr_c + D);
-    const size_t smem_q = sizeof(float) * (size_t)wpb_q * 32 * (D + 1) * narr_q;
+    while (wpb_c > 1 && sizeof(float) * (wpb_c * warp_c + blk_c) > 160 * 1024) wpb_c >>= 1;
+    while (wpb_q > 1 && sizeof(float) * wpb_q * warp_q > 100 * 1024) wpb_q >>= 1;
+    const size_t smem_cand = sizeof(float) * (wpb_c * warp_c + blk_c);
+    const size_t smem_q = sizeof(float) * wpb_q * warp_q;
     if (smem_q > 227 * 1024 || smem_cand > 227 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension too large for the ranking prep kernels");
 
     for (size_t g0 = 0; g0 < grel.size(); g0 += gmax) {
@@ -582,11 +634,12 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
 
         relvec_kernel<<<(unsigned)((G + 63) / 64), 64, 0, s>>>(*m, (const i32 *)(ws + o_grel), (float *)(ws + o_rv), (i32)G);
         CandArgs ca;
-        ca.m = *m; ca.rv = (const float *)(ws + o_rv); ca.out = (float *)(ws + o_cand);
+        ca.m = *m; ca.rv = (const float *)(ws + o_rv); ca.out = (float *)(ws + o_cand); ca.grp_rel = (const i32 *)(ws + o_grel);
         ca.j0 = (i32)j0; ca.ncol = (i32)ncol; ca.E = (i32)c->E; ca.ntab = (i32)ntab;
         cand_kernel<<<dim3((unsigned)(ncol / (32 * wpb_c)), (unsigned)ntab), 32 * wpb_c, smem_cand, s>>>(ca);
         QArgs qa;
         qa.m = *m; qa.th = c->d_test_h; qa.tt = c->d_test_t; qa.tr = c->d_test_r; qa.q_group = (const i32 *)(ws + o_qg);
+        qa.grp_rel = (const i32 *)(ws + o_grel);
         qa.rv = (const float *)(ws + o_rv); qa.qa = (float *)(ws + o_qa); qa.qt = (float *)(ws + o_qt); qa.ref = (float *)(ws + o_ref);
         qa.q_lo = (i32)cq_lo; qa.nq = (i32)nq;
         qvec_kernel<<<(unsigned)((nq + 32 * wpb_q - 1) / (32 * wpb_q)), 32 * wpb_q, smem_q, s>>>(qa);

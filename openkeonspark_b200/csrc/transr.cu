@@ -6,6 +6,4 @@ extern "C" {
 int okb_transr_grad_sizes(okb_ctx *c, const okb_model *, INT, INT, INT, INT *, INT *, INT *, INT *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR train path not built yet"); }
 int okb_transr_grad(okb_ctx *c, const okb_model *, const okb_hyper *, INT, INT, INT, float *, float *, float *, void *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR train path not built yet"); }
 int okb_transr_update(okb_ctx *c, const okb_model *, const okb_hyper *, INT, const float *, const float *, const float *, float *, void *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR train path not built yet"); }
-int okb_transr_predict(okb_ctx *c, const okb_model *, const int64_t *, const int64_t *, const int64_t *, INT, float *, void *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR scoring not built yet"); }
-int okb_transr_rank(okb_ctx *c, const okb_model *, INT, INT, int, INT, INT, int64_t *, uint64_t *, void *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR ranking not built yet"); }
 }

@@ -9,12 +9,14 @@ from conftest import make_params
 pytestmark = pytest.mark.gpu
 
 
-def _config(path, model, D, test_head=1):
+def _config(path, model, D, test_head=1, Dr=None):
     import openkeonspark_b200 as okb
     con = okb.Config(private_context=True)
     con.set_in_path(path)
     con.set_nbatches(4)
     con.set_dimension(D)
+    if Dr is not None:
+        con.set_rel_dimension(Dr)
     con.set_test_link_prediction(True)
     con.set_test_triple_classification(True)
     con.set_test_head(test_head)
@@ -23,7 +25,7 @@ def _config(path, model, D, test_head=1):
     return con
 
 
-@pytest.mark.parametrize("model", ["TransE", "TransH", "TransD"])
+@pytest.mark.parametrize("model", ["TransE", "TransH", "TransD", "TransR"])
 @pytest.mark.parametrize("D", [50, 100, 33])
 def test_predict_bit_exact(built, small_ds, model, D):
     from oracle.harness import COracle
@@ -40,7 +42,7 @@ def test_predict_bit_exact(built, small_ds, model, D):
     assert np.array_equal(got.reshape(-1).view(np.uint32), exp.view(np.uint32))
 
 
-@pytest.mark.parametrize("model", ["TransE", "TransH", "TransD"])
+@pytest.mark.parametrize("model", ["TransE", "TransH", "TransD", "TransR"])
 @pytest.mark.parametrize("D,test_head", [(50, 1), (100, 0)])
 def test_link_prediction_records_bit_exact(built, small_ds, model, D, test_head):
     """GPU all-entity ranking == oracle testHead/testTail fed the oracle's own canonical scores."""
@@ -129,3 +131,26 @@ def test_triple_classification_matches_oracle(built, small_ds):
     # negatives must be type-constrained and unknown (Corrupt.h:118-137)
     for h, t, r in list(zip(con.test_neg_h, con.test_neg_t, con.test_neg_r))[:50]:
         assert not orc.find(h, t, r)
+
+
+def test_transr_rectangular_matrix(built, small_ds):
+    """TransR with ent_size != rel_size (set_ent_dimension / set_rel_dimension, Config.py:286-296)."""
+    from oracle.harness import COracle
+    con = _config(small_ds, "TransR", 40, 1, Dr=24)
+    P = make_params("TransR", con.entTotal, con.relTotal, 40, seed=5, Dr=24)
+    con.set_parameters(P)
+    orc = COracle(small_ds)
+    rng = np.random.default_rng(1)
+    h, t = rng.integers(0, orc.E, 300), rng.integers(0, orc.E, 300)
+    r = np.full(300, 7)
+    r[1:] = rng.integers(0, orc.R, 299)          # mixed relations: the matrix of r[0] is used for every row (TransR.py:83)
+    got = con.test_step(h, t, r).reshape(-1)
+    assert np.array_equal(got.view(np.uint32), orc.predict("TransR", P, h, t, r).view(np.uint32))
+    rec = con.link_prediction_records().cpu().numpy()
+    th, tt, tr = orc.get_list(0)
+    ents = np.arange(orc.E)
+    for i in range(0, orc.n_test, 17):
+        s = orc.predict("TransR", P, np.full(orc.E, th[i]), ents, np.full(orc.E, tr[i]))
+        assert np.array_equal(rec[i, 1], orc.rank(1, i, s)), i
+        s = orc.predict("TransR", P, ents, np.full(orc.E, tt[i]), np.full(orc.E, tr[i]))
+        assert np.array_equal(rec[i, 0], orc.rank(0, i, s)), i
