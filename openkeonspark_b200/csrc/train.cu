@@ -425,7 +425,7 @@ struct UpdArgs {
     const int4 *rowhead;       // Adam: {first, end, slot0, slot1}: sorted-position range of each table row in this step's
                                // plan (first = -1 if untouched) with its first two gradient slots inlined
     DenseTab tab[4];
-    i32 n, n_ent_slots, E, R, ce, cr, B, step_stamp, ntab, work_blocks;
+    i32 n, n_ent_slots, E, R, ce, cr, B, key_limit, ntab, work_blocks;
     float w;
 };
 
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
     const i32 i = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (i >= a.n) return;
     const i32 key = a.skeys[i];
-    if (key >= a.E + a.R || (i > 0 && a.skeys[i - 1] == key)) return;
+    if (key >= a.key_limit || (i > 0 && a.skeys[i - 1] == key)) return;
     const bool is_ent = key < a.E;
     const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
     const i32 row = is_ent ? key : key - a.E;
@@ -583,9 +583,19 @@ bool okb_pick_layout(int D, int &vw, int &nv) {
         else { CALL(1, 4); }                                                             \
     } while (0)
 
+int okb_transr_check(okb_ctx *c, const okb_model *m);
+int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const i32 *batch, const i32 *skeys, const i32 *perm,
+                           const int4 *rowhead, i64 n, INT b_lo, INT b_hi, float *gent, float *grel, float *loss_terms, cudaStream_t s);
+int okb_transr_launch_rel_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const int4 *rowhead, const float *grel, cudaStream_t s);
+
 static int check_model(okb_ctx *c, const okb_model *m, int &vw, int &nv) {
     if (!m || !m->ent || !m->rel) OKB_FAIL(c, OKB_ERR_ARG, "model tables missing");
-    if (m->model == OKB_TRANSR) OKB_FAIL(c, OKB_ERR_ARG, "TransR is handled by transr.cu");
+    if (m->model == OKB_TRANSR) {                          // entity rows go through the generic kernels, the rest through transr.cu
+        int rc = okb_transr_check(c, m);
+        if (rc) return rc;
+        if (!okb_pick_layout(m->ent_dim, vw, nv)) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension not supported");
+        return 0;
+    }
     if (m->model != OKB_TRANSE && m->model != OKB_TRANSH && m->model != OKB_TRANSD) OKB_FAIL(c, OKB_ERR_ARG, "unknown model");
     if (m->ent_dim != m->rel_dim) OKB_FAIL(c, OKB_ERR_ARG, "TransE/H/D need ent_dim == rel_dim");
     if (m->model != OKB_TRANSE && !m->rel_aux) OKB_FAIL(c, OKB_ERR_ARG, "rel_aux table missing");
@@ -596,15 +606,27 @@ static int check_model(okb_ctx *c, const okb_model *m, int &vw, int &nv) {
 static void group_cols(const okb_model *m, i32 &ce, i32 &cr) {
     ce = m->model == OKB_TRANSD ? 2 * m->ent_dim : m->ent_dim;
     cr = m->model == OKB_TRANSE ? m->rel_dim : 2 * m->rel_dim;
+    if (m->model == OKB_TRANSR) cr = m->rel_dim + m->ent_dim * m->rel_dim;     // [d rel | d M_r], one row per RELATION
+}
+
+// per-step map table row -> {first, end, slot0, slot1} in the sorted plan, built once per planned chunk
+static int ensure_rowhead(okb_ctx *c, cudaStream_t s) {
+    if (c->rowhead_ready) return 0;
+    const i64 n = c->plan_ne + c->plan_nr, C = c->plan_hi - c->plan_lo, total = C * n, rows = c->E + c->R;
+    if (c->rowseg_e.ensure(sizeof(int4) * rows * C)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowhead)");
+    OKB_CUDA(c, cudaMemsetAsync(c->rowseg_e.p, 0xff, sizeof(int4) * rows * C, s));
+    mark_heads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->keys_ent.as<i32>() + total, c->perm_ent.as<i32>(), c->rowseg_e.as<int4>(), (i32)n, (i32)rows, total);
+    OKB_LAUNCHED(1);
+    c->rowhead_ready = true;
+    return 0;
 }
 
 extern "C" {
 
 int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT B, INT k, INT kr, INT *er, INT *ec, INT *rr, INT *rc) {
-    if (m->model == OKB_TRANSR) { extern int okb_transr_grad_sizes(okb_ctx *, const okb_model *, INT, INT, INT, INT *, INT *, INT *, INT *); return okb_transr_grad_sizes(c, m, B, k, kr, er, ec, rr, rc); }
     i32 ce, cr;
     group_cols(m, ce, cr);
-    *er = B * (2 + k); *ec = ce; *rr = B * (1 + kr); *rc = cr;
+    *er = B * (2 + k); *ec = ce; *rr = m->model == OKB_TRANSR ? c->R : B * (1 + kr); *rc = cr;
     return 0;
 }
 
@@ -643,7 +665,6 @@ int okb_plan(okb_ctx *c, INT step, void *stream) {
 
 int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, float *gent, float *grel,
              float *loss_terms, void *stream) {
-    if (m->model == OKB_TRANSR) { extern int okb_transr_grad(okb_ctx *, const okb_model *, const okb_hyper *, INT, INT, INT, float *, float *, float *, void *); return okb_transr_grad(c, m, hp, step, b_lo, b_hi, gent, grel, loss_terms, stream); }
     int vw, nv;
     int rc = check_model(c, m, vw, nv);
     if (rc) return rc;
@@ -652,6 +673,14 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
     if (b_lo == b_hi) return 0;
     cudaStream_t s = (cudaStream_t)stream;
     const i64 S = c->B * (1 + c->K + c->KR);
+    if (m->model == OKB_TRANSR) {                          // relation-bucketed kernel; needs the plan's relation segments
+        if (step < c->plan_lo || step >= c->plan_hi) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
+        if ((rc = ensure_rowhead(c, s))) return rc;
+        const i64 n = c->plan_ne + c->plan_nr, total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
+        return okb_transr_launch_grad(c, m, hp, c->batch.as<i32>() + step * 3 * S, c->keys_ent.as<i32>() + total + rel,
+                                      c->perm_ent.as<i32>() + rel, c->rowseg_e.as<int4>() + (step - c->plan_lo) * (c->E + c->R), n,
+                                      b_lo, b_hi, gent, grel, loss_terms, s);
+    }
     GradArgs a;
     a.m = *m;
     const i32 *base = c->batch.as<i32>() + step * 3 * S;
@@ -673,10 +702,10 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
 
 int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
                const float *loss_terms, float *loss_out, void *stream) {
-    if (m->model == OKB_TRANSR) { extern int okb_transr_update(okb_ctx *, const okb_model *, const okb_hyper *, INT, const float *, const float *, const float *, float *, void *); return okb_transr_update(c, m, hp, step, gent, grel, loss_terms, loss_out, stream); }
     int vw, nv;
     int rc = check_model(c, m, vw, nv);
     if (rc) return rc;
+    const bool is_tr = m->model == OKB_TRANSR;
     cudaStream_t s = (cudaStream_t)stream;
     const i64 n = c->plan_ne + c->plan_nr;
     if (n == 0 || step < c->plan_lo || step >= c->plan_hi) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
@@ -688,18 +717,13 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
     a.n = (i32)n; a.n_ent_slots = (i32)c->plan_ne; a.E = (i32)c->E; a.R = (i32)c->R; a.B = (i32)c->B;
     a.w = 1.0f / (float)(c->B * (c->K + c->KR));
     group_cols(m, a.ce, a.cr);
-    a.rowhead = nullptr; a.step_stamp = 0; a.ntab = 0;
+    a.rowhead = nullptr; a.ntab = 0;
+    a.key_limit = is_tr ? (i32)c->E : (i32)(c->E + c->R);
     a.work_blocks = (i32)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (m->optimizer == OKB_ADAM) {
         if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
-        const i64 rows = c->E + c->R, C = c->plan_hi - c->plan_lo;
-        if (!c->rowhead_ready) {                           // once per planned chunk: integer work
-            if (c->rowseg_e.ensure(sizeof(int4) * rows * C)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowhead)");
-            OKB_CUDA(c, cudaMemsetAsync(c->rowseg_e.p, 0xff, sizeof(int4) * rows * C, s));
-            mark_heads_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(c->keys_ent.as<i32>() + total, c->perm_ent.as<i32>(), c->rowseg_e.as<int4>(), (i32)n, (i32)rows, total);
-            OKB_LAUNCHED(1);
-            c->rowhead_ready = true;
-        }
+        const i64 rows = c->E + c->R;
+        if ((rc = ensure_rowhead(c, s))) return rc;
         a.rowhead = c->rowseg_e.as<int4>() + (step - c->plan_lo) * rows;
         i64 acc = 0;
         auto add = [&](float *x, float *mm, float *vv, i64 nrows, int D, bool is_ent, int part) {
@@ -713,8 +737,8 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         };
         add(m->ent, m->m_ent, m->v_ent, c->E, m->ent_dim, true, 0);
         if (m->model == OKB_TRANSD) add(m->ent_aux, m->m_ent_aux, m->v_ent_aux, c->E, m->ent_dim, true, 1);
-        add(m->rel, m->m_rel, m->v_rel, c->R, m->rel_dim, false, 0);
-        if (m->model != OKB_TRANSE) add(m->rel_aux, m->m_rel_aux, m->v_rel_aux, c->R, m->rel_dim, false, 1);
+        if (!is_tr) add(m->rel, m->m_rel, m->v_rel, c->R, m->rel_dim, false, 0);
+        if (!is_tr && m->model != OKB_TRANSE) add(m->rel_aux, m->m_rel_aux, m->v_rel_aux, c->R, m->rel_dim, false, 1);
         a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)148 * 16);
         ProfScope ps(c, PROF_UPDATE, s);
         if (vw == 4) adam_kernel<4><<<a.work_blocks + 1, 256, 0, s>>>(a);
@@ -726,6 +750,10 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
 #define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<a.work_blocks + 1, WARPS_PER_BLOCK * 32, 0, s>>>(a)
         DISPATCH_LAYOUT(vw, nv, CALL_SGD);
         OKB_LAUNCHED(1);
+    }
+    if (is_tr) {                                          // rel_embeddings + transfer_matrix rows (gradients already per relation)
+        if ((rc = ensure_rowhead(c, s))) return rc;
+        if ((rc = okb_transr_launch_rel_update(c, m, hp, c->rowseg_e.as<int4>() + (step - c->plan_lo) * (c->E + c->R), grel, s))) return rc;
     }
     OKB_CUDA(c, cudaGetLastError());
     return 0;

@@ -1,9 +1,380 @@
-// TransR (TransR.py:16-87): per-relation projection e' = e . M_r — placeholder entry points
-// until the grouped-GEMM path lands; they fail loudly rather than fall back.
+// TransR train step (TransR.py:36-75): entities are mapped into relation space by the positive's
+// matrix, e' = e . M_r with M_r = transfer_matrix[r] viewed as [ent_size, rel_size]; with
+// negative_rel == 0 the negatives use the POSITIVE's matrix (TransR.py:57-60).
+//
+// The reference gathers one 40 KB matrix per batch row (B x De x Dr floats materialised per step) and
+// runs a batched [1,De]x[De,Dr] matmul.  Here the batch is bucketed by relation — the plan's sorted
+// relation-key segments already list each relation's positives — and ONE CTA owns one relation: M_r is
+// staged in shared memory once, the CTA walks its positives in chunks, and per chunk runs the three small
+// dense contractions on register-tiled fp32 FMAs out of shared memory:
+//     P  = A . M_r        (projection, forward)
+//     dA = G . M_r^T      (gradient of the gathered entity rows)
+//     dM += A^T . G       (gradient of the matrix, accumulated in registers across chunks)
+// so the matrix gradient is produced already reduced per relation (one [De,Dr] row per relation per
+// step instead of one per positive) in a fixed order: deterministic, no atomics.
+// The roof that binds at FB15K batch sizes is M_r traffic, not flops.
+#include <algorithm>
+
 #include "okb_internal.h"
 
-extern "C" {
-int okb_transr_grad_sizes(okb_ctx *c, const okb_model *, INT, INT, INT, INT *, INT *, INT *, INT *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR train path not built yet"); }
-int okb_transr_grad(okb_ctx *c, const okb_model *, const okb_hyper *, INT, INT, INT, float *, float *, float *, void *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR train path not built yet"); }
-int okb_transr_update(okb_ctx *c, const okb_model *, const okb_hyper *, INT, const float *, const float *, const float *, float *, void *) { OKB_FAIL(c, OKB_ERR_ARG, "TransR train path not built yet"); }
+#define FULL 0xffffffffu
+#define TR_THREADS 256
+#define TR_ROWS 48            // gathered entity rows per chunk (positives per chunk = TR_ROWS / (2 + k))
+#define TR_MAXT 4             // dM tiles (4x4) per thread: De*Dr <= 16 * 256 * 4
+#define EPS_NORM 1e-12f
+
+struct TrArgs {
+    okb_model m;
+    const i32 *bh, *bt, *br;  // plane-major batch
+    const i32 *skeys, *perm;  // this step's plan
+    const int4 *rowhead;      // [E + R]: {first, end, slot0, slot1}
+    float *gent, *grel, *loss_terms;
+    float margin, w;
+    i32 B, k, NE, E, R, n, nes, b_lo, b_hi, CH;
+};
+
+__device__ __forceinline__ float wsum_t(float x) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+__global__ void __launch_bounds__(TR_THREADS) transr_bucket_kernel(TrArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int De = a.m.ent_dim, Dr = a.m.rel_dim, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int De4 = De >> 2, Dr4 = Dr >> 2, per = 2 + a.k;
+    const i32 r = blockIdx.x;
+    const int4 seg = a.rowhead[a.E + r];
+    if (seg.x < 0) return;
+    float *Msh = sm;                                   // [De][Dr]
+    float *A = Msh + De * Dr;                          // [TR_ROWS][De]
+    float *P = A + TR_ROWS * De;                       // [TR_ROWS][Dr]  projected, then normalised
+    float *G = P + TR_ROWS * Dr;                       // [TR_ROWS][Dr]  gradient w.r.t. the projected rows
+    float *Rg = G + TR_ROWS * Dr;                      // [CH][Dr]       per-positive gradient w.r.t. r_hat
+    float *rhat = Rg + a.CH * Dr;                      // [Dr]
+    float *rsum = rhat + Dr;                           // [Dr]
+    float *inv = rsum + Dr;                            // [TR_ROWS]
+    i32 *proj = (i32 *)(inv + TR_ROWS);                // [TR_ROWS]
+    i32 *rowid = proj + TR_ROWS;                       // [TR_ROWS] entity id of each gathered row
+    i32 *posb = rowid + TR_ROWS;                       // [CH] batch index of each positive in the chunk
+    i32 *side = posb + a.CH;                           // [CH][k]  0: head replaced, 1: tail replaced, 2: same triple
+    __shared__ float s_invr;
+    __shared__ int s_projr;
+
+    const float4 *Mg = reinterpret_cast<const float4 *>(a.m.rel_aux + (i64)r * De * Dr);
+    for (int i = tid; i < De * Dr4; i += TR_THREADS) reinterpret_cast<float4 *>(Msh)[i] = __ldg(Mg + i);
+    if (warp == 0) {                                   // r_hat = l2n(rel_embeddings[r])
+        float ss = 0.f;
+        for (int k = lane; k < Dr; k += 32) { const float v = a.m.rel[(i64)r * Dr + k]; ss += v * v; }
+        ss = wsum_t(ss);
+        const float iv = rsqrtf(fmaxf(ss, EPS_NORM));
+        for (int k = lane; k < Dr; k += 32) rhat[k] = a.m.rel[(i64)r * Dr + k] * iv;
+        if (lane == 0) { s_invr = iv; s_projr = ss > EPS_NORM; }
+    }
+    float accM[TR_MAXT][16];
+#pragma unroll
+    for (int q = 0; q < TR_MAXT; q++)
+#pragma unroll
+        for (int e = 0; e < 16; e++) accM[q][e] = 0.f;
+    float racc = 0.f;                                   // thread k < Dr: sum over positives of d loss / d r_hat[k]
+    const int ntM = De4 * Dr4;
+
+    for (i32 base = seg.x; base < seg.y; base += a.CH) {
+        const int np = min(a.CH, seg.y - base);         // positives in this chunk
+        const int rows = np * per, rows4 = (rows + 3) & ~3;
+        __syncthreads();
+        if (tid < np) {
+            const i32 b = a.perm[base + tid] - a.nes;   // relation slots are numbered nes + b  (NR == 1)
+            posb[tid] = b;
+            const i32 ph = a.bh[b], pt = a.bt[b];
+            rowid[tid * per] = ph; rowid[tid * per + 1] = pt;
+            for (int m = 0; m < a.k; m++) {
+                const i32 at = b + (m + 1) * a.B;
+                const i32 nh = a.bh[at], nt = a.bt[at];
+                const int sd = nh != ph ? 0 : (nt != pt ? 1 : 2);
+                side[tid * a.k + m] = sd;
+                rowid[tid * per + 2 + m] = sd == 0 ? nh : (sd == 1 ? nt : ph);
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < rows4 * De4; i += TR_THREADS) {            // gather the entity rows (128-bit)
+            const int row = i / De4, q = i - row * De4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows) v = __ldg(reinterpret_cast<const float4 *>(a.m.ent + (i64)rowid[row] * De) + q);
+            reinterpret_cast<float4 *>(A)[row * De4 + q] = v;
+        }
+        __syncthreads();
+        // ---- P = A . M   (4x4 register tiles)
+        for (int t = tid; t < (rows4 >> 2) * Dr4; t += TR_THREADS) {
+            const int tr = t / Dr4, tc = t - tr * Dr4;
+            float acc[4][4] = {};
+            for (int i = 0; i < De; i += 4) {
+                float4 av[4], mv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    av[q] = reinterpret_cast<const float4 *>(A)[(tr * 4 + q) * De4 + (i >> 2)];
+                    mv[q] = reinterpret_cast<const float4 *>(Msh)[(i + q) * Dr4 + tc];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    acc[q][0] += av[q].x * mv[0].x + av[q].y * mv[1].x + av[q].z * mv[2].x + av[q].w * mv[3].x;
+                    acc[q][1] += av[q].x * mv[0].y + av[q].y * mv[1].y + av[q].z * mv[2].y + av[q].w * mv[3].y;
+                    acc[q][2] += av[q].x * mv[0].z + av[q].y * mv[1].z + av[q].z * mv[2].z + av[q].w * mv[3].z;
+                    acc[q][3] += av[q].x * mv[0].w + av[q].y * mv[1].w + av[q].z * mv[2].w + av[q].w * mv[3].w;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                reinterpret_cast<float4 *>(P)[(tr * 4 + q) * Dr4 + tc] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+        }
+        __syncthreads();
+        // ---- normalise the projected rows (tf.nn.l2_normalize, TransR.py:19-23)
+        for (int row = warp; row < rows; row += TR_THREADS / 32) {
+            float ss = 0.f;
+            for (int k = lane; k < Dr; k += 32) { const float v = P[row * Dr + k]; ss += v * v; }
+            ss = wsum_t(ss);
+            const float iv = rsqrtf(fmaxf(ss, EPS_NORM));
+            for (int k = lane; k < Dr; k += 32) P[row * Dr + k] *= iv;
+            if (lane == 0) { inv[row] = iv; proj[row] = ss > EPS_NORM; }
+        }
+        __syncthreads();
+        // ---- scores, hinge and the gradient w.r.t. the projected rows: one warp per positive
+        for (int c = warp; c < np; c += TR_THREADS / 32) {
+            const int r0 = c * per;
+            const float *Ph = P + r0 * Dr, *Pt = P + (r0 + 1) * Dr;
+            float gh[4] = {0.f, 0.f, 0.f, 0.f}, gt[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f}, gp[4];
+            float sp = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int k = lane + 32 * i;
+                const float u = k < Dr ? (Ph[k] + rhat[k]) - Pt[k] : 0.f;
+                sp += fabsf(u);
+                gp[i] = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+            }
+            sp = wsum_t(sp);
+            // adds coef * (d score / d projected row) for the three roles of a triple with sign vector g
+            auto backward = [&](const float *Hrow, const float *Trow, int hrow_i, int trow_i, const float *g, float coef,
+                                float *dh, float *dt) {
+                float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = lane + 32 * i;
+                    if (k < Dr) { d1 += g[i] * Hrow[k]; d2 += g[i] * Trow[k]; }
+                }
+                d1 = wsum_t(d1); d2 = wsum_t(d2);
+                if (!proj[hrow_i]) d1 = 0.f;
+                if (!proj[trow_i]) d2 = 0.f;
+                const float ih = inv[hrow_i] * coef, it = inv[trow_i] * coef;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = lane + 32 * i;
+                    if (k < Dr) {
+                        dh[i] += ih * (g[i] - Hrow[k] * d1);
+                        dt[i] -= it * (g[i] - Trow[k] * d2);
+                        gr[i] += coef * g[i];
+                    }
+                }
+            };
+            float hinge = 0.f;
+            int active = 0;
+            for (int m = 0; m < a.k; m++) {
+                const int sd = side[c * a.k + m], nrow = r0 + 2 + m;
+                const float *Pn = P + nrow * Dr;
+                const float *Hrow = sd == 0 ? Pn : Ph, *Trow = sd == 1 ? Pn : Pt;
+                float gn[4], gnew[4] = {0.f, 0.f, 0.f, 0.f};
+                float sn = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = lane + 32 * i;
+                    const float u = k < Dr ? (Hrow[k] + rhat[k]) - Trow[k] : 0.f;
+                    sn += fabsf(u);
+                    gn[i] = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+                }
+                sn = wsum_t(sn);
+                const float x = sp - sn + a.margin;
+                if (x >= 0.f) {
+                    hinge += x; active++;
+                    if (sd == 0) backward(Hrow, Trow, nrow, r0 + 1, gn, -a.w, gnew, gt);
+                    else if (sd == 1) backward(Hrow, Trow, r0, nrow, gn, -a.w, gh, gnew);
+                    else backward(Hrow, Trow, r0, r0 + 1, gn, -a.w, gh, gt);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) { const int k = lane + 32 * i; if (k < Dr) G[nrow * Dr + k] = gnew[i]; }
+            }
+            if (active) backward(Ph, Pt, r0, r0 + 1, gp, a.w * (float)active, gh, gt);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int k = lane + 32 * i;
+                if (k < Dr) { G[r0 * Dr + k] = gh[i]; G[(r0 + 1) * Dr + k] = gt[i]; Rg[c * Dr + k] = gr[i]; }
+            }
+            if (lane == 0) a.loss_terms[posb[c]] = hinge;
+        }
+        for (int i = tid + rows * Dr; i < rows4 * Dr; i += TR_THREADS) G[i] = 0.f;      // padding rows
+        __syncthreads();
+        // ---- dA = G . M^T  -> entity gradient rows of this chunk
+        for (int t = tid; t < (rows4 >> 2) * De4; t += TR_THREADS) {
+            const int tr = t / De4, ti = t - tr * De4;       // this thread: rows 4tr..4tr+3, columns ti + q*De4
+            float acc[4][4] = {};
+            for (int k = 0; k < Dr4; k++) {
+                float4 gv[4], mv[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    gv[q] = reinterpret_cast<const float4 *>(G)[(tr * 4 + q) * Dr4 + k];
+                    mv[q] = reinterpret_cast<const float4 *>(Msh)[(ti + q * De4) * Dr4 + k];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++) acc[q][e] += dot4(gv[q], mv[e]);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int row = tr * 4 + q;
+                if (row < rows) {
+                    const int c = row / per, j = row - c * per;
+                    float *dst = a.gent + ((i64)posb[c] * a.NE + j) * De;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) dst[ti + e * De4] = acc[q][e];
+                }
+            }
+        }
+        // ---- dM += A^T . G
+#pragma unroll
+        for (int q = 0; q < TR_MAXT; q++) {
+            const int t = tid + q * TR_THREADS;
+            if (t < ntM) {
+                const int ti = t / Dr4, tk = t - ti * Dr4;
+                for (int row = 0; row < rows; row++) {
+                    const float4 av = reinterpret_cast<const float4 *>(A)[row * De4 + ti];
+                    const float4 gv = reinterpret_cast<const float4 *>(G)[row * Dr4 + tk];
+                    const float as[4] = {av.x, av.y, av.z, av.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+#pragma unroll
+                        for (int f = 0; f < 4; f++) accM[q][e * 4 + f] += as[e] * gs[f];
+                }
+            }
+        }
+        if (tid < Dr) for (int c = 0; c < np; c++) racc += Rg[c * Dr + tid];       // fixed order over positives
+    }
+    // ---- gradient rows of this relation: [d rel_embeddings (Dr) | d M_r (De*Dr)]
+    float *out = a.grel + (i64)r * (Dr + De * Dr);
+    if (tid < Dr) rsum[tid] = racc;
+    __syncthreads();
+    if (tid < Dr) {
+        float d = 0.f;
+        for (int k = 0; k < Dr; k++) d += rsum[k] * rhat[k];
+        out[tid] = s_invr * (rsum[tid] - (s_projr ? rhat[tid] * d : 0.f));
+    }
+#pragma unroll
+    for (int q = 0; q < TR_MAXT; q++) {
+        const int t = tid + q * TR_THREADS;
+        if (t < ntM) {
+            const int ti = t / Dr4, tk = t - ti * Dr4;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                reinterpret_cast<float4 *>(out + Dr + (ti * 4 + e) * Dr)[tk] =
+                    make_float4(accM[q][e * 4 + 0], accM[q][e * 4 + 1], accM[q][e * 4 + 2], accM[q][e * 4 + 3]);
+        }
+    }
+}
+
+// rel_embeddings and transfer_matrix rows: gradients arrive already reduced per relation.
+//   SGD : touched relations only, x -= lr g.      Adam: every relation (TF1 dense decay), g = 0 if untouched.
+struct TrUpdArgs {
+    okb_model m;
+    okb_hyper hp;
+    const int4 *rowhead;
+    const float *grel;
+    i32 E, R, adam;
+};
+__global__ void __launch_bounds__(256) transr_rel_update_kernel(TrUpdArgs a) {
+    const i32 r = blockIdx.x;
+    const int De = a.m.ent_dim, Dr = a.m.rel_dim;
+    const bool touched = a.rowhead[a.E + r].x >= 0;
+    if (!touched && !a.adam) return;
+    const int cols = Dr + De * Dr, c4 = cols >> 2;
+    const float4 *g4 = reinterpret_cast<const float4 *>(a.grel + (i64)r * cols);
+    for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < c4; v += gridDim.y * blockDim.x) {
+        const int e = v * 4;
+        const bool is_rel = e < Dr;
+        const i64 off = is_rel ? (i64)r * Dr + e : (i64)r * De * Dr + (e - Dr);
+        float *x = (is_rel ? a.m.rel : a.m.rel_aux) + off;
+        const float4 g = touched ? __ldg(g4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 xv = *reinterpret_cast<float4 *>(x);
+        const float gs[4] = {g.x, g.y, g.z, g.w};
+        float *xs = reinterpret_cast<float *>(&xv);
+        if (a.adam) {
+            float *mp = (is_rel ? a.m.m_rel : a.m.m_rel_aux) + off, *vp = (is_rel ? a.m.v_rel : a.m.v_rel_aux) + off;
+            float4 mv = *reinterpret_cast<float4 *>(mp), vv = *reinterpret_cast<float4 *>(vp);
+            float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float mq = ms[q] * a.hp.beta1 + gs[q] * (1.f - a.hp.beta1);
+                const float vq = vs[q] * a.hp.beta2 + (gs[q] * gs[q]) * (1.f - a.hp.beta2);
+                ms[q] = mq; vs[q] = vq;
+                xs[q] -= a.hp.lr * mq / (sqrtf(vq) + a.hp.eps);
+            }
+            *reinterpret_cast<float4 *>(mp) = mv; *reinterpret_cast<float4 *>(vp) = vv;
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; q++) xs[q] -= a.hp.lr * gs[q];
+        }
+        *reinterpret_cast<float4 *>(x) = xv;
+    }
+}
+
+int okb_transr_check(okb_ctx *c, const okb_model *m) {
+    if (!m->rel_aux) OKB_FAIL(c, OKB_ERR_ARG, "transfer_matrix table missing");
+    if (m->ent_dim % 4 || m->rel_dim % 4 || m->ent_dim > 128 || m->rel_dim > 128)
+        OKB_FAIL(c, OKB_ERR_ARG, "TransR training needs ent_size, rel_size multiples of 4 and <= 128");
+    if ((m->ent_dim / 4) * (m->rel_dim / 4) > TR_MAXT * TR_THREADS) OKB_FAIL(c, OKB_ERR_ARG, "TransR matrix too large");
+    if (c->KR != 0) OKB_FAIL(c, OKB_ERR_ARG, "TransR training with rel_neg_rate > 0 is not supported yet");
+    if (2 + c->K > TR_ROWS) OKB_FAIL(c, OKB_ERR_ARG, "TransR training: ent_neg_rate too large for the chunk size");
+    return 0;
+}
+
+int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const i32 *batch, const i32 *skeys,
+                           const i32 *perm, const int4 *rowhead, i64 n, INT b_lo, INT b_hi, float *gent, float *grel,
+                           float *loss_terms, cudaStream_t s) {
+    int rc = okb_transr_check(c, m);
+    if (rc) return rc;
+    if (b_lo != 0 || b_hi != c->B) OKB_FAIL(c, OKB_ERR_ARG, "TransR gradients are reduced per relation: data-parallel slices are not supported yet");
+    const i64 S = c->B * (1 + c->K);
+    TrArgs a;
+    a.m = *m; a.bh = batch; a.bt = batch + S; a.br = batch + 2 * S;
+    a.skeys = skeys; a.perm = perm; a.rowhead = rowhead;
+    a.gent = gent; a.grel = grel; a.loss_terms = loss_terms;
+    a.margin = hp->margin; a.w = 1.0f / (float)(c->B * c->K);
+    a.B = (i32)c->B; a.k = (i32)c->K; a.NE = (i32)(2 + c->K); a.E = (i32)c->E; a.R = (i32)c->R; a.n = (i32)n;
+    a.nes = (i32)c->plan_ne; a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi;
+    a.CH = (i32)(TR_ROWS / (2 + c->K));
+    const int De = m->ent_dim, Dr = m->rel_dim;
+    const size_t smem = sizeof(float) * ((size_t)De * Dr + (size_t)TR_ROWS * De + 2 * (size_t)TR_ROWS * Dr + (size_t)a.CH * Dr + 2 * Dr + TR_ROWS) +
+                        sizeof(i32) * (2 * TR_ROWS + a.CH + (size_t)a.CH * a.k) + 64;
+    if (smem > 226 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "TransR dimensions too large for shared memory");
+    static size_t attr = 0;                                // static + dynamic must stay within 227 KB
+    if (smem > attr) { OKB_CUDA(c, cudaFuncSetAttribute(transr_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    {
+        ProfScope ps(c, PROF_GRAD, s);
+        transr_bucket_kernel<<<(unsigned)c->R, TR_THREADS, smem, s>>>(a);
+    }
+    OKB_LAUNCHED(1);
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+int okb_transr_launch_rel_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const int4 *rowhead, const float *grel,
+                                 cudaStream_t s) {
+    TrUpdArgs a;
+    a.m = *m; a.hp = *hp; a.rowhead = rowhead; a.grel = grel; a.E = (i32)c->E; a.R = (i32)c->R;
+    a.adam = m->optimizer == OKB_ADAM;
+    if (a.adam && (!m->m_rel_aux || !m->v_rel_aux)) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
+    const int cols = m->rel_dim + m->ent_dim * m->rel_dim;
+    const unsigned gy = (unsigned)std::max(1, std::min(8, (cols / 4 + 255) / 256));
+    transr_rel_update_kernel<<<dim3((unsigned)c->R, gy), 256, 0, s>>>(a);
+    OKB_LAUNCHED(1);
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
 }

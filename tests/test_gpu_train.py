@@ -3,8 +3,8 @@
 Stated fp32 tolerances (against the fp64 run of the restatement):
   loss .................. |dl| <= 2e-5 * |l| + 1e-6
   SGD tables ............ max|err| <= max(4 x the fp32 CPU restatement's own error, 1e-4 * max|update| + 2e-6)
-  Adam slots m, v ....... linear / quadratic in the gradient, so they carry the gradient check:
-                          |dm| <= 1e-4 * max|m| + 1e-9 ; |dv| <= 2e-4 * max|v| + 1e-12
+  Adam slots m, v ....... (after the FIRST step) linear / quadratic in the gradient, so they carry the gradient check:
+                          99.9 % of elements: |dm| <= 1e-4 * max|m| + 1e-9 ; |dv| <= 2e-4 * max|v| + 1e-12
   Adam tables ........... Adam normalises every element's step to ~lr regardless of |g|, so an element whose
                           gradient is ~0 flips between -lr and +lr on fp32 rounding noise (the fp32 CPU
                           restatement itself is up to lr away from fp64 there).  Hence: 99.5 % of elements
@@ -20,7 +20,7 @@ from conftest import make_params
 pytestmark = pytest.mark.gpu
 
 
-def _config(path, model, D, k, kr, opt, nbatches=6, alpha=0.01, margin=1.0, W=4, bern=1):
+def _config(path, model, D, k, kr, opt, nbatches=6, alpha=0.01, margin=1.0, W=4, bern=1, Dr=None):
     import openkeonspark_b200 as okb
     con = okb.Config(private_context=True)
     con.set_in_path(path)
@@ -31,6 +31,8 @@ def _config(path, model, D, k, kr, opt, nbatches=6, alpha=0.01, margin=1.0, W=4,
     con.set_alpha(alpha)
     con.set_opt_method(opt)
     con.set_dimension(D)
+    if Dr is not None:
+        con.set_rel_dimension(Dr)
     con.set_bern(bern)
     con.workThreads = W
     con.init()
@@ -39,6 +41,16 @@ def _config(path, model, D, k, kr, opt, nbatches=6, alpha=0.01, margin=1.0, W=4,
     con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), W)
     con.set_model_and_session(getattr(okb, model))
     return con
+
+
+def _check_adam_slots(con, ref64):
+    """m and v are linear / quadratic in the gradient.  A hinge term within rounding of 0 may be active in fp32
+    and inactive in fp64 (whole rows then differ), so the bound is on the 99.9 % quantile, not the maximum."""
+    for name in ref64.m:
+        m_gpu, v_gpu = con._adam["m_" + name].cpu().numpy(), con._adam["v_" + name].cpu().numpy()
+        m_ref, v_ref = ref64.m[name].numpy(), ref64.v[name].numpy()
+        assert np.quantile(np.abs(m_gpu - m_ref), 0.999) <= 1e-4 * np.abs(m_ref).max() + 1e-9, name
+        assert np.quantile(np.abs(v_gpu - v_ref), 0.999) <= 2e-4 * np.abs(v_ref).max() + 1e-12, name
 
 
 @pytest.mark.parametrize("model", ["TransE", "TransH", "TransD"])
@@ -60,6 +72,8 @@ def test_train_step_parity(built, small_ds, model, opt, D, k, kr):
         l32 = ref32.step(h, t, r, B, k, kr)
         l64 = ref64.step(h, t, r, B, k, kr)
         assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6, (it, loss, l32, l64)
+        if it == 0 and opt == "Adam":          # after ONE step m = 0.1 g and v = 0.001 g^2: the pure gradient check
+            _check_adam_slots(con, ref64)
     got = con.get_parameters()
     exp = ref64.params()
     for name in exp:
@@ -69,10 +83,6 @@ def test_train_step_parity(built, small_ds, model, opt, D, k, kr):
         if opt == "SGD":
             assert err.max() <= max(4 * err32, 1e-4 * delta + 2e-6), (name, err.max(), err32, delta)
         else:
-            m_gpu, v_gpu = con._adam["m_" + name].cpu().numpy(), con._adam["v_" + name].cpu().numpy()
-            m_ref, v_ref = ref64.m[name].numpy(), ref64.v[name].numpy()
-            assert np.abs(m_gpu - m_ref).max() <= 1e-4 * np.abs(m_ref).max() + 1e-9, name
-            assert np.abs(v_gpu - v_ref).max() <= 2e-4 * np.abs(v_ref).max() + 1e-12, name
             assert np.quantile(err, 0.995) <= 1e-5, (name, np.quantile(err, 0.995))
             assert err.max() <= 2 * 0.01 * 3 + 1e-6, (name, err.max())
 
@@ -145,3 +155,44 @@ def test_chunked_lookahead_equals_step_by_step(built, small_ds):
     for name in outs[0][1]:
         assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
         assert np.array_equal(outs[0][1][name], outs[2][1][name]), name
+
+
+@pytest.mark.parametrize("opt", ["SGD", "Adam"])
+@pytest.mark.parametrize("D,Dr,k", [(100, 100, 1), (20, 20, 2), (40, 24, 3), (64, 128, 10)])
+def test_transr_train_step_parity(built, small_ds, opt, D, Dr, k):
+    """TransR: relation-bucketed kernel (projection, dA, dM contractions) vs the TF-graph restatement."""
+    import torch
+    from oracle import models_ref
+    con = _config(small_ds, "TransR", D, k, 0, opt, Dr=Dr)
+    P = make_params("TransR", con.entTotal, con.relTotal, D, seed=7, Dr=Dr)
+    con.set_parameters(P)
+    ref32 = models_ref.Trainer("TransR", P, margin=1.0, lr=0.01, opt=opt)
+    ref64 = models_ref.Trainer("TransR", P, margin=1.0, lr=0.01, opt=opt, dtype=torch.float64)
+    B = con.batch_size
+    for it in range(3):
+        con.sampling()
+        h, t, r = con.batch_h.copy(), con.batch_t.copy(), con.batch_r.copy()
+        loss = float(con.train_step_device(0).item())
+        ref32.step(h, t, r, B, k, 0)
+        l64 = ref64.step(h, t, r, B, k, 0)
+        assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6, (it, loss, l64)
+        if it == 0 and opt == "Adam":
+            _check_adam_slots(con, ref64)
+    got, exp = con.get_parameters(), ref64.params()
+    for name in exp:
+        delta = np.abs(exp[name] - P[name]).max()
+        err = np.abs(got[name] - exp[name])
+        err32 = np.abs(ref32.params()[name] - exp[name]).max()
+        if opt == "SGD":
+            assert err.max() <= max(4 * err32, 1e-4 * delta + 2e-6), (name, err.max(), err32, delta)
+        else:
+            assert np.quantile(err, 0.995) <= 1e-5, (name, np.quantile(err, 0.995))
+            assert err.max() <= 2 * 0.01 * 3 + 1e-6, (name, err.max())
+
+
+def test_transr_unsupported_configs_fail_loudly(built, small_ds):
+    from openkeonspark_b200 import OkbError
+    con = _config(small_ds, "TransR", 20, 1, 1, "SGD")          # rel_neg_rate > 0
+    con.sampling_device()
+    with pytest.raises(OkbError):
+        con.train_step_device(0)
