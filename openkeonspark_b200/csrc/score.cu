@@ -234,8 +234,10 @@ struct QArgs {
     const i32 *th, *tt, *tr;
     const i32 *q_group;        // group index of each query (relative to chunk)
     const i32 *grp_rel;
+    const i32 *g_qlo, *g_blk;  // first query / first 8-query block of each group
     const float *rv;
-    float *qa, *qt, *ref;
+    float *qa, *qt;            // blocked: [block][d][8], blocks of a group contiguous (zero padded)
+    float *ref, *thr;          // per query: finished score of the true triple; raw-sum threshold (see below)
     i32 q_lo, nq;
 };
 // dynamic shared memory per warp: H, T input rows [32][Din+1]; a second pair (TransD: ent_transfer rows,
@@ -269,14 +271,27 @@ __global__ void __launch_bounds__(128) qvec_kernel(QArgs a) {
     float *t = a.m.model == OKB_TRANSR ? T2 + lane * s2 : T + lane * sin;
     canon_row(a.m.model, H + lane * sin, h, rv + D, H2 + lane * s2, M, Din, D);
     canon_row(a.m.model, T + lane * sin, t, rv + D, T2 + lane * s2, M, Din, D);
+    const i32 ql = q - a.g_qlo[g];
+    float *oa = a.qa + ((i64)(a.g_blk[g] + (ql >> 3)) * D) * 8 + (ql & 7), *ot = a.qt + (oa - a.qa);
     float s = 0.f;
     for (int d = 0; d < D; d++) {
         const float x = __fadd_rn(h[d], rv[d]);
-        a.qa[(i64)q * D + d] = x;
-        a.qt[(i64)q * D + d] = t[d];
+        oa[d * 8] = x;
+        ot[d * 8] = t[d];
         s = __fadd_rn(s, fabsf(__fsub_rn(x, t[d])));
     }
-    a.ref[q] = c_finish(a.m.model, s, D);
+    const float ref = c_finish(a.m.model, s, D);
+    a.ref[q] = ref;
+    // The reference compares FINISHED scores (TransE: sum / D).  fl(x / D) is monotone in x, so
+    // "fl(x / D) < ref" is "x < T" with T = min{x : fl(x / D) >= ref}: the ranking kernel compares raw sums
+    // against T and divides only for the candidates that count.
+    float thr = ref;
+    if (a.m.model == OKB_TRANSE && ref > 0.f) {
+        thr = __fmul_rn(ref, (float)D);
+        while (thr > 0.f && __fdiv_rn(thr, (float)D) >= ref) thr = __uint_as_float(__float_as_uint(thr) - 1u);
+        while (__fdiv_rn(thr, (float)D) < ref) thr = __uint_as_float(__float_as_uint(thr) + 1u);
+    }
+    a.thr[q] = thr;
 }
 
 // type flags per (group, candidate): bit 0 = in head_type[r], bit 1 = in tail_type[r]
@@ -326,7 +341,9 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
 struct RankArgs {
     const float *cand;         // [ntab][D][ncol]
     const float *rv;           // [G][2][D]
-    const float *qa, *qt, *ref;   // per query of the chunk
+    const float *qa, *qt;      // blocked query vectors [block][D][8]
+    const float *thr;          // raw-sum thresholds per query of the chunk
+    const i32 *g_blk;          // first block of each group
     const unsigned char *tflag;   // [G][ncol]
     const i32 *th, *tt;        // test heads / tails (global test index)
     const int4 *trun;          // known-list runs per test triple
@@ -336,115 +353,131 @@ struct RankArgs {
     i32 D, ncol, j0, cand_lo, cand_hi, q_lo, model, tab_per_group;
 };
 
-template <bool HEADS>
-__global__ void __launch_bounds__(CT) rank_kernel(RankArgs a) {
+// QG thread groups of CT threads share ONE staged candidate tile; group g owns queries g*QB .. g*QB+QB-1
+// of every pass, so a CTA ranks QG*QB queries per pass against 128 candidates.  (One candidate column
+// costs D*4 bytes of shared memory: sharing it between QG threads is what lifts residency from 12 to
+// 24-32 warps per SM.)
+template <bool HEADS, int QG>
+__global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int D = a.D, tid = threadIdx.x;
+    constexpr int NQ = QG * QB;                            // queries per pass
+    const int D = a.D, tid = threadIdx.x, jl = tid % CT, qg = tid / CT;
     float *tile = (float *)smraw;                          // [D][CT]
     float *rhat = tile + (size_t)D * CT;                   // [D]
-    float *qa = rhat + ((D + 3) & ~3);                     // [D][QB]
-    float *qt = qa + (size_t)D * QB;                       // [D][QB]
-    float *refs = qt + (size_t)D * QB;                     // [QB]
-    i32 *tgt = (i32 *)(refs + QB);                         // [QB][2]
-    int4 *runs = (int4 *)(tgt + 2 * QB);                   // [QB]
-    unsigned *cnt = (unsigned *)(runs + QB);               // [QB][2][4]
-    unsigned long long *bst = (unsigned long long *)(cnt + QB * 8);   // [QB][2][4]
-    unsigned long long *bar = bst + QB * 8;
+    float *qa = rhat + ((D + 3) & ~3);                     // [QG][D][8]  (the global blocked layout)
+    float *qt = qa + (size_t)D * NQ;                       // [QG][D][8]
+    float *refs = qt + (size_t)D * NQ;                     // [NQ] raw-sum thresholds
+    i32 *tgt = (i32 *)(refs + NQ);                         // [NQ][2]
+    int4 *runs = (int4 *)(tgt + 2 * NQ);                   // [NQ]
+    unsigned *cnt = (unsigned *)(runs + NQ);               // [NQ][2][4]
+    unsigned long long *bst = (unsigned long long *)(cnt + NQ * 8);   // [NQ][2][4]
+    unsigned long long *bar = bst + NQ * 8;
 
     const i32 g = blockIdx.y;
     const i32 col0 = blockIdx.x * CT;
     const i32 tab = a.tab_per_group ? g : 0;
+    const i32 qlo = a.g_qlo[g], qhi = a.g_qhi[g];
+    const i32 nblk = (qhi - qlo + QB - 1) / QB, blk0 = a.g_blk[g];
+    unsigned phase = 0;
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_expect_tx(bar, (unsigned)(D * CT * sizeof(float)));
         const float *src = a.cand + (i64)tab * D * a.ncol + col0;
         for (int d = 0; d < D; d++) tma_load_1d(tile + (size_t)d * CT, src + (i64)d * a.ncol, CT * sizeof(float), bar);
     }
-    for (int d = tid; d < D; d += CT) rhat[d] = a.rv[(i64)g * 2 * D + d];
-    const i32 j = a.j0 + col0 + tid;
+    for (int d = tid; d < D; d += CT * QG) rhat[d] = a.rv[(i64)g * 2 * D + d];
+    const i32 j = a.j0 + col0 + jl;
     const bool valid = j >= a.cand_lo && j < a.cand_hi;
-    const unsigned tf = valid ? a.tflag[(i64)g * a.ncol + col0 + tid] : 0u;
+    const unsigned tf = valid ? a.tflag[(i64)g * a.ncol + col0 + jl] : 0u;
     __syncthreads();                                       // barrier init visible to all waiters
-    mbar_wait(bar, 0);
+    mbar_wait(bar, phase); phase ^= 1;
 
-    const i32 qlo = a.g_qlo[g], qhi = a.g_qhi[g];
-    for (i32 qb = qlo; qb < qhi; qb += QB) {
-        __syncthreads();
-        for (int idx = tid; idx < D * QB; idx += CT) {
-            const int q = idx / D, d = idx - q * D;
-            const bool ok = qb + q < qhi;
-            qa[d * QB + q] = ok ? a.qa[(i64)(qb + q) * D + d] : 0.f;
-            if (HEADS) qt[d * QB + q] = ok ? a.qt[(i64)(qb + q) * D + d] : 0.f;
+    for (i32 pb = 0; pb < nblk; pb += QG) {                // a pass = QG consecutive 8-query blocks of the group
+        const i32 nb = min(QG, nblk - pb), qb = qlo + pb * QB;
+        __syncthreads();                                   // previous pass fully consumed
+        if (tid == 0) {                                    // the pass's query vectors are contiguous: two bulk copies
+            const unsigned bytes = (unsigned)(nb * D * QB * sizeof(float));
+            mbar_expect_tx(bar, HEADS ? 2 * bytes : bytes);
+            tma_load_1d(qa, a.qa + (i64)(blk0 + pb) * D * QB, bytes, bar);
+            if (HEADS) tma_load_1d(qt, a.qt + (i64)(blk0 + pb) * D * QB, bytes, bar);
         }
-        if (tid < QB) {
+        if (tid < NQ) {
             const bool ok = qb + tid < qhi;
             const i32 ti = a.q_lo + qb + tid;
-            refs[tid] = ok ? a.ref[qb + tid] : 0.f;
+            refs[tid] = ok ? a.thr[qb + tid] : 0.f;
             tgt[2 * tid] = ok ? a.th[ti] : -1;
             tgt[2 * tid + 1] = ok ? a.tt[ti] : -1;
             runs[tid] = ok ? a.trun[ti] : make_int4(0, 0, 0, 0);
         }
-        if (tid < QB * 8) { cnt[tid] = 0u; bst[tid] = ~0ull; }
+        for (int idx = tid; idx < NQ * 8; idx += CT * QG) { cnt[idx] = 0u; bst[idx] = ~0ull; }
         __syncthreads();
+        mbar_wait(bar, phase); phase ^= 1;
 
-        float accT[QB], accH[QB];
+        if (qg < nb) {
+            const i32 q0 = qg * QB;                        // this thread group's queries within the pass
+            const float *qas = qa + (size_t)qg * D * QB, *qts = qt + (size_t)qg * D * QB;
+            float accT[QB], accH[QB];
 #pragma unroll
-        for (int q = 0; q < QB; q++) { accT[q] = 0.f; accH[q] = 0.f; }
-        for (int d = 0; d < D; d++) {
-            const float c = tile[d * CT + tid];
-            const float cr = __fadd_rn(c, rhat[d]);
-            const float4 *pa = (const float4 *)(qa + d * QB), *pt = (const float4 *)(qt + d * QB);
+            for (int q = 0; q < QB; q++) { accT[q] = 0.f; accH[q] = 0.f; }
+#pragma unroll 4
+            for (int d = 0; d < D; d++) {
+                const float c = tile[d * CT + jl];
+                const float cr = __fadd_rn(c, rhat[d]);
+                const float4 *pa = (const float4 *)(qas + d * QB), *pt = (const float4 *)(qts + d * QB);
 #pragma unroll
-            for (int v = 0; v < QB / 4; v++) {
-                const float4 x = pa[v];
-                accT[4 * v + 0] = __fadd_rn(accT[4 * v + 0], fabsf(__fsub_rn(x.x, c)));
-                accT[4 * v + 1] = __fadd_rn(accT[4 * v + 1], fabsf(__fsub_rn(x.y, c)));
-                accT[4 * v + 2] = __fadd_rn(accT[4 * v + 2], fabsf(__fsub_rn(x.z, c)));
-                accT[4 * v + 3] = __fadd_rn(accT[4 * v + 3], fabsf(__fsub_rn(x.w, c)));
-                if (HEADS) {
-                    const float4 y = pt[v];
-                    accH[4 * v + 0] = __fadd_rn(accH[4 * v + 0], fabsf(__fsub_rn(cr, y.x)));
-                    accH[4 * v + 1] = __fadd_rn(accH[4 * v + 1], fabsf(__fsub_rn(cr, y.y)));
-                    accH[4 * v + 2] = __fadd_rn(accH[4 * v + 2], fabsf(__fsub_rn(cr, y.z)));
-                    accH[4 * v + 3] = __fadd_rn(accH[4 * v + 3], fabsf(__fsub_rn(cr, y.w)));
+                for (int v = 0; v < QB / 4; v++) {
+                    const float4 x = pa[v];
+                    accT[4 * v + 0] = __fadd_rn(accT[4 * v + 0], fabsf(__fsub_rn(x.x, c)));
+                    accT[4 * v + 1] = __fadd_rn(accT[4 * v + 1], fabsf(__fsub_rn(x.y, c)));
+                    accT[4 * v + 2] = __fadd_rn(accT[4 * v + 2], fabsf(__fsub_rn(x.z, c)));
+                    accT[4 * v + 3] = __fadd_rn(accT[4 * v + 3], fabsf(__fsub_rn(x.w, c)));
+                    if (HEADS) {
+                        const float4 y = pt[v];
+                        accH[4 * v + 0] = __fadd_rn(accH[4 * v + 0], fabsf(__fsub_rn(cr, y.x)));
+                        accH[4 * v + 1] = __fadd_rn(accH[4 * v + 1], fabsf(__fsub_rn(cr, y.y)));
+                        accH[4 * v + 2] = __fadd_rn(accH[4 * v + 2], fabsf(__fsub_rn(cr, y.z)));
+                        accH[4 * v + 3] = __fadd_rn(accH[4 * v + 3], fabsf(__fsub_rn(cr, y.w)));
+                    }
                 }
             }
-        }
 #pragma unroll
-        for (int q = 0; q < QB; q++) {
-            const bool qok = valid && qb + q < qhi;
-            const float ref = refs[q];
+            for (int q = 0; q < QB; q++) {
+                const int ql = q0 + q;
+                const bool qok = valid && qb + ql < qhi;
+                const float thr = refs[ql];
 #pragma unroll
-            for (int side = HEADS ? 0 : 1; side < 2; side++) {
-                const float s = c_finish(a.model, side ? accT[q] : accH[q], D);
-                if (qok && j != tgt[2 * q + side] && s < ref) {              // Test.h:59,62 / 168,171
-                    // known-true filter: is (j, t, r) / (h, j, r) in train+valid+test?  (Corrupt.h:104-115)
-                    const int4 rn = runs[q];
-                    const i32 *lst = side ? a.known_t : a.known_h;
-                    const i32 end = side ? rn.y : rn.w;
-                    i32 lo = side ? rn.x : rn.z, hi = end;
-                    while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (__ldg(lst + mid) < j) lo = mid + 1; else hi = mid; }
-                    const bool known = lo < end && __ldg(lst + lo) == j;
-                    const bool typed = (tf >> side) & 1u;
-                    const unsigned long long pk = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned)j;
-                    unsigned *cq = cnt + (q * 2 + side) * 4;
-                    unsigned long long *bq = bst + (q * 2 + side) * 4;
-                    atomicAdd(cq + 0, 1u); atomicMin(bq + 0, pk);
-                    if (!known) { atomicAdd(cq + 1, 1u); atomicMin(bq + 1, pk); }
-                    if (typed) {
-                        atomicAdd(cq + 2, 1u); atomicMin(bq + 2, pk);
-                        if (!known) { atomicAdd(cq + 3, 1u); atomicMin(bq + 3, pk); }
+                for (int side = HEADS ? 0 : 1; side < 2; side++) {
+                    const float raw = side ? accT[q] : accH[q];
+                    if (qok && j != tgt[2 * ql + side] && raw < thr) {           // Test.h:59,62 / 168,171
+                        const float s = c_finish(a.model, raw, D);
+                        // known-true filter: is (j, t, r) / (h, j, r) in train+valid+test?  (Corrupt.h:104-115)
+                        const int4 rn = runs[ql];
+                        const i32 *lst = side ? a.known_t : a.known_h;
+                        const i32 end = side ? rn.y : rn.w;
+                        i32 lo = side ? rn.x : rn.z, hi = end;
+                        while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (__ldg(lst + mid) < j) lo = mid + 1; else hi = mid; }
+                        const bool known = lo < end && __ldg(lst + lo) == j;
+                        const bool typed = (tf >> side) & 1u;
+                        const unsigned long long pk = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned)j;
+                        unsigned *cq = cnt + (ql * 2 + side) * 4;
+                        unsigned long long *bq = bst + (ql * 2 + side) * 4;
+                        atomicAdd(cq + 0, 1u); atomicMin(bq + 0, pk);
+                        if (!known) { atomicAdd(cq + 1, 1u); atomicMin(bq + 1, pk); }
+                        if (typed) {
+                            atomicAdd(cq + 2, 1u); atomicMin(bq + 2, pk);
+                            if (!known) { atomicAdd(cq + 3, 1u); atomicMin(bq + 3, pk); }
+                        }
                     }
                 }
             }
         }
         __syncthreads();
-        if (tid < QB * 8) {
-            const int q = tid >> 3;
+        for (int idx = tid; idx < NQ * 8; idx += CT * QG) {
+            const int q = idx >> 3;
             if (qb + q < qhi) {
-                const i64 o = (i64)(qb + q) * 8 + (tid & 7);
-                if (cnt[tid]) atomicAdd(a.counts + o, (unsigned long long)cnt[tid]);
-                if (bst[tid] != ~0ull) atomicMin(a.best + o, bst[tid]);
+                const i64 o = (i64)(qb + q) * 8 + (idx & 7);
+                if (cnt[idx]) atomicAdd(a.counts + o, (unsigned long long)cnt[idx]);
+                if (bst[idx] != ~0ull) atomicMin(a.best + o, bst[idx]);
             }
         }
     }
@@ -585,13 +618,19 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
     const size_t budget = (size_t)4 << 30;
     i64 gmax = per_group ? std::max<i64>(1, (i64)(budget / tab_bytes)) : (i64)grel.size();
     gmax = std::min<i64>(gmax, 8192);
-    const size_t smem_rank = sizeof(float) * ((size_t)D * CT + ((D + 3) & ~3) + 2 * (size_t)D * QB + QB) + sizeof(i32) * 2 * QB +
-                             sizeof(int4) * QB + sizeof(unsigned) * QB * 8 + sizeof(unsigned long long) * (QB * 8 + 1) + 128;
+    // thread groups per CTA: more groups = more warps per staged tile; 4 when groups are large enough to fill 32 queries
+    const i64 avg_q = grel.empty() ? 1 : (q_hi - q_lo) / (i64)grel.size();
+    const int QGsel = avg_q >= 20 ? 4 : 2;
+    const size_t NQ = (size_t)QGsel * QB;
+    const size_t smem_rank = sizeof(float) * ((size_t)D * CT + ((D + 3) & ~3) + 2 * (size_t)D * NQ + NQ) + sizeof(i32) * 2 * NQ +
+                             sizeof(int4) * NQ + sizeof(unsigned) * NQ * 8 + sizeof(unsigned long long) * (NQ * 8 + 1) + 128;
     if (smem_rank > 227 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension too large for the ranking tile");
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(rank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(rank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(rank_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(rank_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(rank_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(rank_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(qvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
@@ -614,10 +653,13 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         // workspace layout
         size_t off = 0;
         auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-        const size_t o_cand = take(tab_bytes * ntab), o_rv = take(sizeof(float) * G * 2 * D), o_qa = take(sizeof(float) * nq * D),
-                     o_qt = take(sizeof(float) * nq * D), o_ref = take(sizeof(float) * nq), o_tf = take((size_t)G * ncol),
-                     o_grel = take(sizeof(i32) * G), o_gqlo = take(sizeof(i32) * G), o_gqhi = take(sizeof(i32) * G),
-                     o_qg = take(sizeof(i32) * nq);
+        std::vector<i32> gblk(G);
+        i64 NBq = 0;                                       // 8-query blocks, per group padded
+        for (i64 g = 0; g < G; g++) { gblk[g] = (i32)NBq; NBq += (gqhi[g0 + g] - gqlo[g0 + g] + QB - 1) / QB; }
+        const size_t o_cand = take(tab_bytes * ntab), o_rv = take(sizeof(float) * G * 2 * D), o_qa = take(sizeof(float) * NBq * QB * D),
+                     o_qt = take(sizeof(float) * NBq * QB * D), o_ref = take(sizeof(float) * nq), o_thr = take(sizeof(float) * nq),
+                     o_tf = take((size_t)G * ncol), o_grel = take(sizeof(i32) * G), o_gqlo = take(sizeof(i32) * G),
+                     o_gqhi = take(sizeof(i32) * G), o_gblk = take(sizeof(i32) * G), o_qg = take(sizeof(i32) * nq);
         if (c->rank_ws.ensure(off)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (ranking workspace)");
         char *ws = c->rank_ws.as<char>();
         std::vector<i32> rel_lo(G), rel_hi(G), qg(nq);
@@ -629,9 +671,13 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         OKB_CUDA(c, cudaMemcpyAsync(ws + o_gqlo, rel_lo.data(), sizeof(i32) * G, cudaMemcpyHostToDevice, s));
         OKB_CUDA(c, cudaMemcpyAsync(ws + o_gqhi, rel_hi.data(), sizeof(i32) * G, cudaMemcpyHostToDevice, s));
         OKB_CUDA(c, cudaMemcpyAsync(ws + o_qg, qg.data(), sizeof(i32) * nq, cudaMemcpyHostToDevice, s));
+        OKB_CUDA(c, cudaMemcpyAsync(ws + o_gblk, gblk.data(), sizeof(i32) * G, cudaMemcpyHostToDevice, s));
         OKB_CUDA(c, cudaStreamSynchronize(s));            // host vectors above go out of scope
         OKB_CUDA(c, cudaMemsetAsync(ws + o_tf, 0, (size_t)G * ncol, s));
+        OKB_CUDA(c, cudaMemsetAsync(ws + o_qa, 0, sizeof(float) * NBq * QB * D, s));      // padded query slots stay finite
+        OKB_CUDA(c, cudaMemsetAsync(ws + o_qt, 0, sizeof(float) * NBq * QB * D, s));
 
+        prof_mark(c, PROF_RANK_PREP, s);
         relvec_kernel<<<(unsigned)((G + 63) / 64), 64, 0, s>>>(*m, (const i32 *)(ws + o_grel), (float *)(ws + o_rv), (i32)G);
         CandArgs ca;
         ca.m = *m; ca.rv = (const float *)(ws + o_rv); ca.out = (float *)(ws + o_cand); ca.grp_rel = (const i32 *)(ws + o_grel);
@@ -641,14 +687,17 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         qa.m = *m; qa.th = c->d_test_h; qa.tt = c->d_test_t; qa.tr = c->d_test_r; qa.q_group = (const i32 *)(ws + o_qg);
         qa.grp_rel = (const i32 *)(ws + o_grel);
         qa.rv = (const float *)(ws + o_rv); qa.qa = (float *)(ws + o_qa); qa.qt = (float *)(ws + o_qt); qa.ref = (float *)(ws + o_ref);
+        qa.thr = (float *)(ws + o_thr); qa.g_qlo = (const i32 *)(ws + o_gqlo); qa.g_blk = (const i32 *)(ws + o_gblk);
         qa.q_lo = (i32)cq_lo; qa.nq = (i32)nq;
         qvec_kernel<<<(unsigned)((nq + 32 * wpb_q - 1) / (32 * wpb_q)), 32 * wpb_q, smem_q, s>>>(qa);
         typeflag_kernel<<<dim3(8, (unsigned)G), 128, 0, s>>>((const i32 *)(ws + o_grel), c->head_type.d_lef, c->head_type.d_rig,
                                                             c->head_type.d_ids, c->tail_type.d_lef, c->tail_type.d_rig,
                                                             c->tail_type.d_ids, (unsigned char *)(ws + o_tf), (i32)j0, (i32)ncol);
+        prof_mark(c, PROF_RANK_PREP, s);
         RankArgs ra;
         ra.cand = (const float *)(ws + o_cand); ra.rv = (const float *)(ws + o_rv);
-        ra.qa = (const float *)(ws + o_qa); ra.qt = (const float *)(ws + o_qt); ra.ref = (const float *)(ws + o_ref);
+        ra.qa = (const float *)(ws + o_qa); ra.qt = (const float *)(ws + o_qt); ra.thr = (const float *)(ws + o_thr);
+        ra.g_blk = (const i32 *)(ws + o_gblk);
         ra.tflag = (const unsigned char *)(ws + o_tf);
         ra.th = c->d_test_h; ra.tt = c->d_test_t; ra.trun = c->d_test_run; ra.known_t = c->d_known_t; ra.known_h = c->d_known_h;
         ra.g_qlo = (const i32 *)(ws + o_gqlo); ra.g_qhi = (const i32 *)(ws + o_gqhi);
@@ -658,8 +707,8 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         ra.q_lo = (i32)cq_lo; ra.model = m->model; ra.tab_per_group = per_group ? 1 : 0;
         const dim3 grid((unsigned)(ncol / CT), (unsigned)G);
         { ProfScope ps(c, PROF_RANK, s);
-        if (heads) rank_kernel<true><<<grid, CT, smem_rank, s>>>(ra);
-        else rank_kernel<false><<<grid, CT, smem_rank, s>>>(ra); }
+        if (QGsel == 4) { if (heads) rank_kernel<true, 4><<<grid, CT * 4, smem_rank, s>>>(ra); else rank_kernel<false, 4><<<grid, CT * 4, smem_rank, s>>>(ra); }
+        else { if (heads) rank_kernel<true, 2><<<grid, CT * 2, smem_rank, s>>>(ra); else rank_kernel<false, 2><<<grid, CT * 2, smem_rank, s>>>(ra); } }
         OKB_LAUNCHED(5);
         OKB_CUDA(c, cudaGetLastError());
     }
