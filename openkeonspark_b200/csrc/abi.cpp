@@ -43,7 +43,7 @@ int okb_destroy(okb_ctx *c) {
         if (L->d_ids) cudaFree(L->d_ids);
     }
     for (DevBuf *b : {&c->batch, &c->keys_ent, &c->keys_rel, &c->perm_ent, &c->perm_rel, &c->sort_tmp, &c->hist, &c->gent, &c->grel,
-                      &c->flags, &c->lossterms, &c->rowseg_e, &c->rowseg_r, &c->rank_ws, &c->host_io})
+                      &c->flags, &c->lossterms, &c->rowseg_e, &c->rowseg_r, &c->rank_ws, &c->host_io, &c->partial})
         b->release();
     if (c == g_ctx) g_ctx = nullptr;
     delete c;

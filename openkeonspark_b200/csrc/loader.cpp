@@ -170,6 +170,15 @@ static int build_train(okb_ctx *c, const i64 *h, const i64 *t, const i64 *r, i64
         c->tph[r_] = (float)freq[r_] / c->tph[r_];
         c->hpt[r_] = (float)freq[r_] / c->hpt[r_];
     }
+    {   // hub statistics: how long can a gradient-row segment get?  (picks the pre-reduction path of the update)
+        i64 mr = 0, me_ = 0;
+        for (i64 r_ = 0; r_ < R; r_++) mr = std::max(mr, freq[r_]);
+        std::vector<i32> deg(E, 0);
+        for (i64 i = 0; i < n; i++) { deg[(i64)(k_hrt[i] >> (pk.br + pk.be))]++; deg[c->byh_t[i]]++; }
+        for (i64 e = 0; e < E; e++) me_ = std::max<i64>(me_, deg[e]);
+        c->max_rel_share = (double)mr / (double)n;
+        c->max_ent_share = (double)me_ / (double)(2 * n);
+    }
     return okb_upload_train(c);
 }
 

@@ -37,6 +37,7 @@ struct okb_ctx {
     std::vector<i32> byh_r, byh_t, byt_r, byt_h, byht_t, byht_r;   // secondary key / value of the 3 sorted copies
     std::vector<i32> lef_h, rig_h, lef_t, rig_t, lef_ht, rig_ht;
     std::vector<float> tph, hpt;                       // left_mean / right_mean
+    double max_rel_share = 0, max_ent_share = 0;       // largest fraction of train rows touching one relation / entity
     std::vector<i32> test_h, test_t, test_r, valid_h, valid_t, valid_r;   // sorted (r,h,t)
     std::vector<i32> test_lef, test_rig, valid_lef, valid_rig;
     std::vector<u64> all_hrt;                          // packed keys of train+valid+test sorted (h,r,t), dups kept
@@ -63,8 +64,9 @@ struct okb_ctx {
     DevBuf batch;                     // int32 [steps][3][S]
     // ---------------- plan / workspace
     DevBuf keys_ent, keys_rel, perm_ent, perm_rel, sort_tmp, hist, gent, grel, flags, lossterms, rowseg_e, rowseg_r;
-    DevBuf rank_ws, host_io;
+    DevBuf rank_ws, host_io, partial;
     i64 plan_ne = 0, plan_nr = 0, plan_lo = 0, plan_hi = 0;   // steps [plan_lo, plan_hi) of the sampled batches are planned
+    bool loss_ctr_ready = false;
     bool rowhead_ready = false;       // Adam: per-step row -> first sorted position map built for the planned chunk
     int ent_bits = 0, rel_bits = 0;
     // ---------------- optional per-kernel timing (CUDA events on the launching stream; bench.py)

@@ -21,6 +21,7 @@
 
 #define FULL 0xffffffffu
 #define WARPS_PER_BLOCK 4
+#define PCH 8                  // long segments (> PCH rows) are pre-reduced in fixed chunks of PCH sorted positions
 // grad kernel: one warp per block so that residency is quantised in single warps: <= 120 registers
 // -> 17 warps per SM -> B = 4831 positives fit in 2 waves instead of 2.04 (= 3)
 #ifndef GRAD_WARPS
@@ -425,64 +426,155 @@ struct UpdArgs {
     const int4 *rowhead;       // Adam: {first, end, slot0, slot1}: sorted-position range of each table row in this step's
                                // plan (first = -1 if untouched) with its first two gradient slots inlined
     DenseTab tab[4];
+    const float *partial;      // hub path: chunk sums of long segments, row i = sum of sorted positions [i, i + PCH)
+    i32 pcols, hub, by_row, loss_blocks;
+    float *loss_part;
+    unsigned *loss_ctr;
     i32 n, n_ent_slots, E, R, ce, cr, B, key_limit, ntab, work_blocks;
     float w;
 };
 
-// mean hinge over B*(k+kr) pairs in a fixed order, by the extra last block of the update launch
+// mean hinge over B*(k+kr) pairs in a fixed order, by `loss_blocks` extra blocks of the update launch: each
+// sums a fixed contiguous range of the per-positive terms; the block that finishes last adds the partial
+// sums in index order (so the result does not depend on which block that is).
 __device__ __forceinline__ void loss_block(const UpdArgs &a) {
     __shared__ float sh[32];
+    __shared__ unsigned ticket;
     if (!a.loss_out) return;
-    float s = 0.f;
-    for (i32 i = threadIdx.x; i < a.B; i += blockDim.x) s += a.loss_terms[i];
-    s = wsum(s);
+    const i32 lb = (i32)blockIdx.x - a.work_blocks;
+    const i32 per = (a.B + a.loss_blocks - 1) / a.loss_blocks;
+    const i32 lo = lb * per, hi = min(a.B, lo + per);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const i32 T = blockDim.x;
+    for (i32 i = lo + threadIdx.x; i < hi; i += 4 * T) {
+        s0 += a.loss_terms[i];
+        if (i + T < hi) s1 += a.loss_terms[i + T];
+        if (i + 2 * T < hi) s2 += a.loss_terms[i + 2 * T];
+        if (i + 3 * T < hi) s3 += a.loss_terms[i + 3 * T];
+    }
+    float s = wsum((s0 + s1) + (s2 + s3));
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x < 32) {
         s = wsum(threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f);
-        if (threadIdx.x == 0) a.loss_out[0] = s * a.w;
+        if (threadIdx.x == 0) {
+            a.loss_part[lb] = s;
+            __threadfence();
+            ticket = atomicAdd(a.loss_ctr, 1u);
+        }
+    }
+    __syncthreads();
+    if (ticket == (unsigned)a.loss_blocks - 1 && threadIdx.x == 0) {
+        __threadfence();
+        float tot = 0.f;
+        for (i32 q = 0; q < a.loss_blocks; q++) tot += ((volatile float *)a.loss_part)[q];
+        a.loss_out[0] = tot * a.w;
+        *a.loss_ctr = 0u;
     }
 }
 
-// Sum the gradient rows of the segment starting at sorted position `pos` (fixed slot order).
+// Gradient row of sorted position j, part `part` (D floats)
+__device__ __forceinline__ const float *grad_row(const UpdArgs &a, i32 j, bool is_ent, int D, int part) {
+    const i32 slot = __ldg(a.perm + j);
+    return (is_ent ? a.gent + (i64)slot * a.ce : a.grel + (i64)(slot - a.n_ent_slots) * a.cr) + part * D;
+}
+
+// Sum `cnt` rows starting at index lo with stride `step` (raw gradient rows via perm[], or pre-reduced
+// block sums); loads are issued four at a time, additions stay in ascending order.
 template <int VW, int NV>
-__device__ __forceinline__ void seg_sum(const UpdArgs &a, i32 pos, i32 key, bool is_ent, int D, int part, int lane, float *acc) {
+__device__ __forceinline__ void sum_rows(const UpdArgs &a, i32 lo, i32 hi, bool is_ent, int D, int part, int lane, float *acc,
+                                         bool from_partial) {
     constexpr int N = VW * NV;
+    for (i32 j = lo; j < hi; j += 4) {
+        Frag<VW, NV> f[4];
 #pragma unroll
-    for (int q = 0; q < N; q++) acc[q] = 0.f;
-    const i32 cols = is_ent ? a.ce : a.cr;
-    for (i32 j = pos; j < a.n && a.skeys[j] == key; j++) {
-        const i32 slot = a.perm[j];
-        const float *row = is_ent ? a.gent + (i64)slot * cols : a.grel + (i64)(slot - a.n_ent_slots) * cols;
-        Frag<VW, NV> f;
-        f.load(row + part * D, D, lane);
+        for (int u = 0; u < 4; u++) {
+            const i32 jj = j + u;
+            if (jj < hi) f[u].load(from_partial ? a.partial + (i64)jj * a.pcols + part * D : grad_row(a, jj, is_ent, D, part), D, lane);
+            else f[u].zero();
+        }
 #pragma unroll
-        for (int q = 0; q < N; q++) acc[q] += f.v[q];
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int q = 0; q < N; q++) acc[q] += f[u].v[q];
+    }
+}
+// Whole segment [s, e).  Long segments (hub rows) use the block sums of prereduce_kernel for the PCH-aligned
+// blocks that lie inside the segment and raw rows for the two fringes — always in ascending position order.
+template <int VW, int NV>
+__device__ __forceinline__ void seg_sum(const UpdArgs &a, i32 s, i32 e, bool is_ent, int D, int part, int lane, float *acc) {
+    const i32 b0 = (s + PCH - 1) / PCH, b1 = e / PCH;     // blocks [b0, b1) are interior
+    if (a.hub && e - s > PCH && b0 < b1) {
+        sum_rows<VW, NV>(a, s, b0 * PCH, is_ent, D, part, lane, acc, false);
+        sum_rows<VW, NV>(a, b0, b1, is_ent, D, part, lane, acc, true);
+        sum_rows<VW, NV>(a, b1 * PCH, e, is_ent, D, part, lane, acc, false);
+    } else {
+        sum_rows<VW, NV>(a, s, e, is_ent, D, part, lane, acc, false);
     }
 }
 
-// SGD: one warp per sorted position; only segment heads work.  row -= lr * sum of its gradient rows
-// (GradientDescentOptimizer's sparse apply: duplicates accumulate).
+// Hub path, level 1: one warp per PCH-aligned block of sorted positions; a block that lies inside ONE
+// segment is summed into partial[block].  Block boundaries depend only on positions: fixed order.
+template <int VW, int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) prereduce_kernel(UpdArgs a, float *partial) {
+    constexpr int N = VW * NV;
+    const int lane = threadIdx.x & 31;
+    const i32 w = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    const i32 lo = w * PCH;
+    if (lo + PCH > a.n) return;
+    const i32 key = a.skeys[lo];
+    if (key >= a.key_limit || a.skeys[lo + PCH - 1] != key) return;
+    const bool is_ent = key < a.E;
+    const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
+    const int parts = (is_ent ? a.ce : a.cr) / D;
+    for (int p = 0; p < parts; p++) {
+        float acc[N];
+#pragma unroll
+        for (int q = 0; q < N; q++) acc[q] = 0.f;
+        sum_rows<VW, NV>(a, lo, lo + PCH, is_ent, D, p, lane, acc, false);
+        Frag<VW, NV> f;
+#pragma unroll
+        for (int q = 0; q < N; q++) f.v[q] = acc[q];
+        f.store(partial + (i64)w * a.pcols + p * D, D, lane);
+    }
+}
+
+// SGD: row -= lr * sum of its gradient rows (GradientDescentOptimizer's sparse apply: duplicates accumulate).
+// One warp per sorted position (only segment heads work), or — when the batch has more gradient rows than the
+// tables have rows — one warp per table row.
 template <int VW, int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
     constexpr int N = VW * NV;
-    if ((i32)blockIdx.x == a.work_blocks) { loss_block(a); return; }
+    if ((i32)blockIdx.x >= a.work_blocks) { loss_block(a); return; }
     const int lane = threadIdx.x & 31;
-    const i32 i = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
-    if (i >= a.n) return;
-    const i32 key = a.skeys[i];
-    if (key >= a.key_limit || (i > 0 && a.skeys[i - 1] == key)) return;
+    const i32 w = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    i32 key, i, end;
+    if (a.by_row) {
+        key = w;
+        if (key >= a.key_limit) return;
+        const int4 seg = __ldg(a.rowhead + key);
+        if (seg.x < 0) return;
+        i = seg.x; end = seg.y;
+    } else {
+        i = w;
+        if (i >= a.n) return;
+        key = a.skeys[i];
+        if (key >= a.key_limit || (i > 0 && a.skeys[i - 1] == key)) return;
+        end = __ldg(a.rowhead + key).y;
+    }
     const bool is_ent = key < a.E;
     const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
     const i32 row = is_ent ? key : key - a.E;
     const int parts = (is_ent ? a.ce : a.cr) / D;
     for (int p = 0; p < parts; p++) {
-        float g[N];
-        seg_sum<VW, NV>(a, i, key, is_ent, D, p, lane, g);
         float *tab = is_ent ? (p ? a.m.ent_aux : a.m.ent) : (p ? a.m.rel_aux : a.m.rel);
         const i64 off = (i64)row * D;
         Frag<VW, NV> x;
-        x.load(tab + off, D, lane);
+        x.load(tab + off, D, lane);                       // independent of the gradient rows: in flight first
+        float g[N];
+#pragma unroll
+        for (int q = 0; q < N; q++) g[q] = 0.f;
+        seg_sum<VW, NV>(a, i, end, is_ent, D, p, lane, g);
 #pragma unroll
         for (int q = 0; q < N; q++) x.v[q] -= a.hp.lr * g[q];
         x.store(tab + off, D, lane);
@@ -497,7 +589,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
 //   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; x <- x - lr_t m / (sqrt(v) + eps)
 template <int VW>
 __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
-    if ((i32)blockIdx.x == a.work_blocks) { loss_block(a); return; }
+    if ((i32)blockIdx.x >= a.work_blocks) { loss_block(a); return; }
     typedef typename VecT<VW>::T V;
     const i64 total = a.tab[a.ntab - 1].vec_end;
     const i64 stride = (i64)a.work_blocks * blockDim.x;
@@ -516,7 +608,8 @@ __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
         float g[VW];
 #pragma unroll
         for (int q = 0; q < VW; q++) g[q] = 0.f;
-        if (seg.x >= 0) {
+        const bool long_seg = seg.x >= 0 && a.hub && seg.y - seg.x > PCH && (seg.x + PCH - 1) / PCH < seg.y / PCH;
+        if (seg.x >= 0 && !long_seg) {
             const float *gbase = T.grad + T.part * T.D + col;
             const i32 cnt = seg.y - seg.x;
             // the first two contributions come straight from the row map: no perm[] hop for the common case
@@ -532,6 +625,26 @@ __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
 #pragma unroll
                 for (int q = 0; q < VW; q++) g[q] += pj[q];
             }
+        }
+        if (long_seg) {                                    // hub row: fringe rows + pre-reduced interior blocks, ascending order
+            const float *gbase = T.grad + T.part * T.D + col, *pbase = a.partial + T.part * T.D + col;
+            const i32 b0 = (seg.x + PCH - 1) / PCH, b1 = seg.y / PCH;
+            auto add_raw = [&](i32 lo, i32 hi) {
+                for (i32 j = lo; j < hi; j++) {
+                    const V gj = __ldg(reinterpret_cast<const V *>(gbase + (i64)(__ldg(a.perm + j) - T.slot_off) * T.cols));
+                    const float *pj = reinterpret_cast<const float *>(&gj);
+#pragma unroll
+                    for (int q = 0; q < VW; q++) g[q] += pj[q];
+                }
+            };
+            add_raw(seg.x, b0 * PCH);
+            for (i32 b = b0; b < b1; b++) {
+                const V gj = __ldg(reinterpret_cast<const V *>(pbase + (i64)b * a.pcols));
+                const float *pj = reinterpret_cast<const float *>(&gj);
+#pragma unroll
+                for (int q = 0; q < VW; q++) g[q] += pj[q];
+            }
+            add_raw(b1 * PCH, seg.y);
         }
         float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
 #pragma unroll
@@ -717,14 +830,30 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
     a.n = (i32)n; a.n_ent_slots = (i32)c->plan_ne; a.E = (i32)c->E; a.R = (i32)c->R; a.B = (i32)c->B;
     a.w = 1.0f / (float)(c->B * (c->K + c->KR));
     group_cols(m, a.ce, a.cr);
-    a.rowhead = nullptr; a.ntab = 0;
+    a.ntab = 0;
     a.key_limit = is_tr ? (i32)c->E : (i32)(c->E + c->R);
+    if ((rc = ensure_rowhead(c, s))) return rc;
+    a.rowhead = c->rowseg_e.as<int4>() + (step - c->plan_lo) * (c->E + c->R);
+    // hub heuristic from load-time statistics: expected longest segment of this batch
+    a.pcols = std::max(a.ce, is_tr ? 0 : a.cr);
+    a.hub = (double)c->plan_ne * c->max_ent_share > PCH || (!is_tr && (double)c->plan_nr * c->max_rel_share > PCH);
+    a.partial = nullptr; a.by_row = 0;
+    a.loss_blocks = (i32)std::max<i64>(1, std::min<i64>(64, c->B / 8192));
+    if (c->flags.ensure(sizeof(float) * 64 + 16)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+    if (!c->loss_ctr_ready) { OKB_CUDA(c, cudaMemsetAsync(c->flags.p, 0, sizeof(float) * 64 + 16, s)); c->loss_ctr_ready = true; }
+    a.loss_part = c->flags.as<float>(); a.loss_ctr = (unsigned *)(c->flags.as<float>() + 64);
+    if (a.hub) {
+        const i64 nblocks = n / PCH;
+        if (c->partial.ensure(sizeof(float) * (size_t)(nblocks + 1) * a.pcols)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (partial sums)");
+        a.partial = c->partial.as<float>();
+        const unsigned pg = (unsigned)((nblocks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK + 1);
+#define CALL_PRE(VW, NV) prereduce_kernel<VW, NV><<<pg, WARPS_PER_BLOCK * 32, 0, s>>>(a, c->partial.as<float>())
+        DISPATCH_LAYOUT(vw, nv, CALL_PRE);
+        OKB_LAUNCHED(1);
+    }
     a.work_blocks = (i32)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
     if (m->optimizer == OKB_ADAM) {
         if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
-        const i64 rows = c->E + c->R;
-        if ((rc = ensure_rowhead(c, s))) return rc;
-        a.rowhead = c->rowseg_e.as<int4>() + (step - c->plan_lo) * rows;
         i64 acc = 0;
         auto add = [&](float *x, float *mm, float *vv, i64 nrows, int D, bool is_ent, int part) {
             if (!x) return;
@@ -741,13 +870,15 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         if (!is_tr && m->model != OKB_TRANSE) add(m->rel_aux, m->m_rel_aux, m->v_rel_aux, c->R, m->rel_dim, false, 1);
         a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)148 * 16);
         ProfScope ps(c, PROF_UPDATE, s);
-        if (vw == 4) adam_kernel<4><<<a.work_blocks + 1, 256, 0, s>>>(a);
-        else if (vw == 2) adam_kernel<2><<<a.work_blocks + 1, 256, 0, s>>>(a);
-        else adam_kernel<1><<<a.work_blocks + 1, 256, 0, s>>>(a);
+        if (vw == 4) adam_kernel<4><<<a.work_blocks + a.loss_blocks, 256, 0, s>>>(a);
+        else if (vw == 2) adam_kernel<2><<<a.work_blocks + a.loss_blocks, 256, 0, s>>>(a);
+        else adam_kernel<1><<<a.work_blocks + a.loss_blocks, 256, 0, s>>>(a);
         OKB_LAUNCHED(1);
     } else {
+        a.by_row = a.key_limit < n;                       // fewer table rows than gradient rows: one warp per table row
+        a.work_blocks = (i32)(((a.by_row ? (i64)a.key_limit : n) + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         ProfScope ps(c, PROF_UPDATE, s);
-#define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<a.work_blocks + 1, WARPS_PER_BLOCK * 32, 0, s>>>(a)
+#define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<a.work_blocks + a.loss_blocks, WARPS_PER_BLOCK * 32, 0, s>>>(a)
         DISPATCH_LAYOUT(vw, nv, CALL_SGD);
         OKB_LAUNCHED(1);
     }

@@ -30,6 +30,8 @@ SHAPES = {
     # small shapes for CPU-side tests (oracle finishes in well under a second)
     "tiny": dict(E=60, R=7, n_train=400, n_valid=40, n_test=50),
     "small": dict(E=500, R=23, n_train=6000, n_valid=300, n_test=400),
+    # many relations / entities relative to the batch: gradient-row segments stay short (no hub pre-reduction)
+    "wide": dict(E=4000, R=800, n_train=8000, n_valid=200, n_test=200),
 }
 
 

@@ -61,3 +61,8 @@ def make_params(model, E, R, D, seed=0, Dr=None):
         P["ent_transfer"] = datagen.xavier_normal(rng, E, D)
         P["rel_transfer"] = datagen.xavier_normal(rng, R, Dr)
     return P
+
+
+@pytest.fixture(scope="session")
+def wide_ds(tmp_path_factory):
+    return _dataset(tmp_path_factory, "wide", seed=4)

@@ -71,7 +71,10 @@ def test_train_step_parity(built, small_ds, model, opt, D, k, kr):
         loss = float(con.train_step_device(0).item())
         l32 = ref32.step(h, t, r, B, k, kr)
         l64 = ref64.step(h, t, r, B, k, kr)
-        assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6, (it, loss, l32, l64)
+        # Adam: from the second step on the fp32/fp64 tables differ by up to lr in near-zero-gradient elements (see
+        # the module docstring), which feeds back into the loss; only the first step isolates the forward pass
+        tol = 2e-5 if (opt == "SGD" or it == 0) else 1e-3
+        assert abs(loss - l64) <= tol * abs(l64) + 1e-6, (it, loss, l32, l64)
         if it == 0 and opt == "Adam":          # after ONE step m = 0.1 g and v = 0.001 g^2: the pure gradient check
             _check_adam_slots(con, ref64)
     got = con.get_parameters()
@@ -175,7 +178,8 @@ def test_transr_train_step_parity(built, small_ds, opt, D, Dr, k):
         loss = float(con.train_step_device(0).item())
         ref32.step(h, t, r, B, k, 0)
         l64 = ref64.step(h, t, r, B, k, 0)
-        assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6, (it, loss, l64)
+        tol = 2e-5 if (opt == "SGD" or it == 0) else 1e-3
+        assert abs(loss - l64) <= tol * abs(l64) + 1e-6, (it, loss, l64)
         if it == 0 and opt == "Adam":
             _check_adam_slots(con, ref64)
     got, exp = con.get_parameters(), ref64.params()
@@ -196,3 +200,26 @@ def test_transr_unsupported_configs_fail_loudly(built, small_ds):
     con.sampling_device()
     with pytest.raises(OkbError):
         con.train_step_device(0)
+
+
+@pytest.mark.parametrize("model,opt", [("TransE", "SGD"), ("TransH", "Adam"), ("TransD", "SGD"), ("TransR", "Adam")])
+def test_short_segment_path_parity(built, wide_ds, model, opt):
+    """Graph with many relations/entities relative to the batch: the update runs WITHOUT the hub pre-reduction
+    (small_ds, with 23 Zipf relations, always takes the pre-reduced path)."""
+    import torch
+    from oracle import models_ref
+    con = _config(wide_ds, model, 20, 1, 0, opt, nbatches=80)
+    P = make_params(model, con.entTotal, con.relTotal, 20, seed=7)
+    con.set_parameters(P)
+    ref64 = models_ref.Trainer(model, P, margin=1.0, lr=0.01, opt=opt, dtype=torch.float64)
+    con.sampling()
+    h, t, r = con.batch_h.copy(), con.batch_t.copy(), con.batch_r.copy()
+    loss = float(con.train_step_device(0).item())
+    l64 = ref64.step(h, t, r, con.batch_size, 1, 0)
+    assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6
+    got, exp = con.get_parameters(), ref64.params()
+    for name in exp:
+        if opt == "SGD":
+            assert np.abs(got[name] - exp[name]).max() <= 1e-4 * np.abs(exp[name] - P[name]).max() + 2e-6, name
+        else:
+            _check_adam_slots(con, ref64)
