@@ -208,6 +208,12 @@ INT okb_n_interval(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_n
 INT *okb_tpfp(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg, const REAL *score_pos_test,
               const REAL *score_neg_test);                                                        /* Test.h:410-444 */
 
+/* Flags.  OKB_FLAG_TRANSR_TC = 1: okb_rank projects TransR candidates (Ent . M_r per relation group) on the tcgen05
+ * tensor cores with 3xTF32 split operands instead of the canonical sequential-fp32 kernel.  Scores then agree with
+ * the canonical order to ~1e-6 relative instead of bit-for-bit, so the flag is off by default. */
+enum { OKB_FLAG_TRANSR_TC = 1 };
+int okb_set_flag(okb_ctx *c, int flag, INT value);
+
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:
  * id 0 sampler, 1 plan (keys + radix sort), 2 grad kernel, 3 update kernel (SGD / Adam), 4 rank kernel,
  * 5 rank preparation.  okb_prof_read synchronises, returns the summed milliseconds and the number of

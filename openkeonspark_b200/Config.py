@@ -74,6 +74,7 @@ class Config(object):
         self._step = 0
         self._adam = None
         self._world = None            # parallel.DataParallel when running under torch.distributed
+        self.transr_tensor_cores = False   # TransR ranking: project candidates with tcgen05 (3xTF32) instead of canonical fp32
         self.plan_ahead = 64          # steps sampled + planned per launch chunk (integer work, parameter-independent)
         self._chunk_pos = self._chunk_len = 0
 
@@ -493,6 +494,7 @@ class Config(object):
         counts = torch.zeros(n * 8, dtype=torch.int64, device=dev)
         best = torch.full((n * 8,), -1, dtype=torch.int64, device=dev)       # all ones = "no candidate"
         m = self._cmodel()
+        self.ctx.call("okb_set_flag", 1, int(bool(self.transr_tensor_cores)))
         self.ctx.call("okb_rank", ctypes.byref(m), q_lo, q_hi, int(bool(self.test_head)), cand_lo, cand_hi,
                       _vp(counts.data_ptr()), _vp(best.data_ptr()), _stream())
         if reduce_fn is not None:

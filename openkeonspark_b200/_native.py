@@ -74,6 +74,7 @@ _SIGS = {
     "okb_test_list": (_int, [_vp, _int, _vp, _vp, _vp]),
     "okb_n_interval": (_i64, [_vp, _i64, _vp, _vp]),
     "okb_tpfp": (_vp, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "okb_set_flag": (_int, [_vp, _int, _i64]),
     "okb_prof_enable": (_int, [_vp, _int]),
     "okb_prof_read": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "okb_debug_cuda_error": (C.c_char_p, []),

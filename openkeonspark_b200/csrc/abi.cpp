@@ -51,6 +51,10 @@ int okb_destroy(okb_ctx *c) {
 }
 const char *okb_last_error(okb_ctx *c) { return c ? c->err.c_str() : "null context"; }
 int okb_set_device(okb_ctx *c, int device) { OKB_CUDA(c, cudaSetDevice(device)); return 0; }
+int okb_set_flag(okb_ctx *c, int flag, INT value) {
+    if (flag == OKB_FLAG_TRANSR_TC) { c->transr_tc = value != 0; return 0; }
+    OKB_FAIL(c, OKB_ERR_ARG, "unknown flag");
+}
 int okb_prof_enable(okb_ctx *c, int on) { c->prof_on = on != 0; return 0; }
 int okb_prof_read(okb_ctx *c, int id, double *total_ms, INT *count) {
     if (id < 0 || id >= 8) OKB_FAIL(c, OKB_ERR_ARG, "bad kernel id");

@@ -66,6 +66,7 @@ struct okb_ctx {
     DevBuf keys_ent, keys_rel, perm_ent, perm_rel, sort_tmp, hist, gent, grel, flags, lossterms, rowseg_e, rowseg_r;
     DevBuf rank_ws, host_io, partial;
     i64 plan_ne = 0, plan_nr = 0, plan_lo = 0, plan_hi = 0;   // steps [plan_lo, plan_hi) of the sampled batches are planned
+    bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
     bool rowhead_ready = false;       // Adam: per-step row -> first sorted position map built for the planned chunk
     int ent_bits = 0, rel_bits = 0;

@@ -568,6 +568,8 @@ __global__ void fill_u64_kernel(unsigned long long *p, unsigned long long v, i64
 
 // ------------------------------------------------------------------------------------------ host side
 extern bool okb_pick_layout(int D, int &vw, int &nv);
+int okb_transr_tc_supported(const okb_model *m);
+int okb_transr_project_tc(okb_ctx *c, const okb_model *m, const i32 *d_grp_rel, i64 G, float *out, i64 j0, i64 ncol, cudaStream_t s);
 
 static int check_score_model(okb_ctx *c, const okb_model *m) {
     if (!m || !m->ent || !m->rel) OKB_FAIL(c, OKB_ERR_ARG, "model tables missing");
@@ -682,7 +684,11 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         CandArgs ca;
         ca.m = *m; ca.rv = (const float *)(ws + o_rv); ca.out = (float *)(ws + o_cand); ca.grp_rel = (const i32 *)(ws + o_grel);
         ca.j0 = (i32)j0; ca.ncol = (i32)ncol; ca.E = (i32)c->E; ca.ntab = (i32)ntab;
-        cand_kernel<<<dim3((unsigned)(ncol / (32 * wpb_c)), (unsigned)ntab), 32 * wpb_c, smem_cand, s>>>(ca);
+        if (m->model == OKB_TRANSR && c->transr_tc && okb_transr_tc_supported(m)) {
+            int rc2 = okb_transr_project_tc(c, m, (const i32 *)(ws + o_grel), G, (float *)(ws + o_cand), j0, ncol, s);
+            if (rc2) return rc2;
+        } else
+            cand_kernel<<<dim3((unsigned)(ncol / (32 * wpb_c)), (unsigned)ntab), 32 * wpb_c, smem_cand, s>>>(ca);
         QArgs qa;
         qa.m = *m; qa.th = c->d_test_h; qa.tt = c->d_test_t; qa.tr = c->d_test_r; qa.q_group = (const i32 *)(ws + o_qg);
         qa.grp_rel = (const i32 *)(ws + o_grel);

@@ -154,3 +154,19 @@ def test_transr_rectangular_matrix(built, small_ds):
         assert np.array_equal(rec[i, 1], orc.rank(1, i, s)), i
         s = orc.predict("TransR", P, ents, np.full(orc.E, tt[i]), np.full(orc.E, tr[i]))
         assert np.array_equal(rec[i, 0], orc.rank(0, i, s)), i
+
+
+@pytest.mark.parametrize("D,Dr", [(100, 100), (40, 24), (64, 112)])
+def test_transr_tensor_core_projection(built, small_ds, D, Dr):
+    """TransR ranking with candidates projected on tcgen05 (3xTF32): the 8-int records must agree with the
+    bit-exact canonical path except where two scores are within fp32 rounding of each other.
+    Tolerance: counts may differ by at most 2 per record and at least 97 % of the records are identical."""
+    con = _config(small_ds, "TransR", D, 1, Dr=Dr)
+    P = make_params("TransR", con.entTotal, con.relTotal, D, seed=5, Dr=Dr)
+    con.set_parameters(P)
+    exact = con.link_prediction_records().cpu().numpy()
+    con.transr_tensor_cores = True
+    tc = con.link_prediction_records().cpu().numpy()
+    assert np.abs(exact[..., :4] - tc[..., :4]).max() <= 2
+    same = (exact == tc).all(axis=-1).mean()
+    assert same >= 0.97, same
