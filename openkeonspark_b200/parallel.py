@@ -59,6 +59,7 @@ class DataParallel:
         self.rank = dist.get_rank(group)
         self.chunk, self.ranges = partition(con.batch_size, con.workThreads, self.world)
         self._bufs = None
+        self._coalesce = dist.get_backend(group) == "nccl"
 
     def _buffers(self, con, m):
         if self._bufs is not None:
@@ -84,10 +85,23 @@ class DataParallel:
         con.ctx.call("okb_grad", ctypes.byref(m), ctypes.byref(hp), step, lo, hi, _vp(b["gent"].data_ptr()),
                      _vp(b["grel"].data_ptr()), _vp(b["loss"].data_ptr()), s)
         c, g = self.chunk, self.rank
-        # in-place all-gather: each rank's slot of the full buffer is its own contribution
-        dist.all_gather_into_tensor(b["gent"], b["gent"][g * c * b["ne"]:(g + 1) * c * b["ne"]], group=self.group)
-        dist.all_gather_into_tensor(b["grel"], b["grel"][g * c * b["nr"]:(g + 1) * c * b["nr"]], group=self.group)
-        dist.all_gather_into_tensor(b["loss"], b["loss"][g * c:(g + 1) * c], group=self.group)
+        # in-place all-gather: each rank's slot of the full buffer is its own contribution; the three gathers are
+        # issued as ONE NCCL group (one launch, one synchronisation over NVLink) when the backend supports it
+        parts = [(b["gent"], b["gent"][g * c * b["ne"]:(g + 1) * c * b["ne"]]),
+                 (b["grel"], b["grel"][g * c * b["nr"]:(g + 1) * c * b["nr"]]),
+                 (b["loss"], b["loss"][g * c:(g + 1) * c])]
+        if self._coalesce:
+            try:
+                with dist._coalescing_manager(group=self.group, device=b["gent"].device, async_ops=False):
+                    for full, mine in parts:
+                        dist.all_gather_into_tensor(full, mine, group=self.group)
+            except Exception:                      # backend without coalesced all-gather (gloo): plain calls
+                self._coalesce = False
+                for full, mine in parts:
+                    dist.all_gather_into_tensor(full, mine, group=self.group)
+        else:
+            for full, mine in parts:
+                dist.all_gather_into_tensor(full, mine, group=self.group)
         con.ctx.call("okb_update", ctypes.byref(m), ctypes.byref(hp), step, _vp(b["gent"].data_ptr()),
                      _vp(b["grel"].data_ptr()), _vp(b["loss"].data_ptr()), _vp(con._loss_dev.data_ptr()), s)
 
