@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libokb200.so")
+LIB_PATH = os.environ.get("OKB200_LIB") or os.path.join(HERE, "libokb200.so")    # OKB200_LIB: A/B builds (tools/)
 
 _vp, _i64, _int = C.c_void_p, C.c_int64, C.c_int
 

@@ -68,6 +68,9 @@ struct okb_ctx {
     i64 plan_ne = 0, plan_nr = 0, plan_lo = 0, plan_hi = 0;   // steps [plan_lo, plan_hi) of the sampled batches are planned
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
+    bool adam_tma = false;            // OKB_FLAG_ADAM_TMA: TMA-staged single-wave Adam pass instead of the register-only one
+    bool l2_prefetch = false;         // OKB_FLAG_L2_PREFETCH: grad kernel prefetches the Adam state into L2
+    bool pdl = true;                  // programmatic dependent launch between the grad and update kernels
     bool rowhead_ready = false;       // Adam: per-step row -> first sorted position map built for the planned chunk
     int ent_bits = 0, rel_bits = 0;
     // ---------------- optional per-kernel timing (CUDA events on the launching stream; bench.py)
@@ -109,5 +112,6 @@ i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(
 
 // radix.cu
 int okb_sort_pairs(okb_ctx *c, const i32 *keys, i32 *keys_out, i32 *perm_out, i64 n, int bits, cudaStream_t s);
+int okb_sort_pairs_seg(okb_ctx *c, const i32 *keys, i32 *keys_out, i32 *perm_out, i64 seg, i64 nseg, int bits, cudaStream_t s);
 
 static inline int bits_for(i64 n) { int b = 1; while ((1ll << b) < n) b++; return b; }
