@@ -259,7 +259,7 @@ def main():
 
     # ---------------- region C: the real training loop — one library call per chunk of steps, no L2 flush
     chunk = None
-    if world == 1:
+    if world == 1 or con._world.mode == "owner":
         n_chunks = max(1, args.steps // con.plan_ahead)
         con.train_chunk_device()
         barrier()
@@ -270,11 +270,14 @@ def main():
             con.train_chunk_device()
         b.record()
         barrier()
-        ms_c = a.elapsed_time(b)
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_c = float(t.item())
         chunk = {"value": con.batch_size * n_chunks * con.plan_ahead / (ms_c * 1e-3), "unit": "triples/s",
                  "ms_per_step": ms_c / (n_chunks * con.plan_ahead), "steps": n_chunks * con.plan_ahead,
                  "wall_ms_per_step": (time.perf_counter() - w0) * 1e3 / (n_chunks * con.plan_ahead),
-                 "what": "Config.train_chunk_device(): %d steps per okb_train_steps call, tables L2-resident (no flush)" % con.plan_ahead}
+                 "what": "Config.train_chunk_device(): %d steps per library call, tables L2-resident (no flush)" % con.plan_ahead}
     clk = clocks.stop() if clocks else None
 
     # ---------------- e2e: the reference-shaped loop through the public API with HOST buffers
@@ -358,7 +361,7 @@ def main():
                 "config": {"workload": "TransH dim=100 Adam k=1 margin=1, FB15K-shaped 14951/1345/483142, B=%d per GPU (nbatches=100), global batch %d, workThreads=%d"
                            % (B_local, con.batch_size, con.workThreads),
                            "l2": "not flushed" if flush is None else "flushed between timed steps (256 MiB fill, outside the per-step events)",
-                           "timing": "per-step CUDA events summed; max over ranks", "parallelism": "dp%d" % world},
+                           "timing": "per-step CUDA events summed; max over ranks", "parallelism": "dp%d%s" % (world, "" if world == 1 else " (%s)" % con._world.mode)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "link_prediction": lp, "training_loop_chunked": chunk, "wall_s_timed_region_incl_flush": t_wall}
         print(json.dumps(line))

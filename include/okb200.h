@@ -179,6 +179,37 @@ int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
 int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out,
                     void *cuda_stream);
 
+/* ---- synchronous data-parallel training inside one box, one process per GPU (replaces the asynchronous
+ *      parameter-server path of distribute_training.py:161-364).  Owner-sharded: every rank keeps the full tables in a
+ *      PEER ARENA (device memory the other ranks map over NVLink with CUDA IPC), computes the gradient rows of its own
+ *      positives, pushes per-row partial sums into the row owner's staging slab with peer stores, and the owner applies
+ *      SGD / TF1-Adam to its rows and stores the new rows into every rank's table.  No NCCL call on the data path.
+ *   okb_peer_alloc / okb_peer_open : cudaMalloc + cudaIpcGetMemHandle / cudaIpcOpenMemHandle (handle = 64 bytes, exchanged
+ *                                    by the host, e.g. torch.distributed.all_gather_object)
+ *   okb_dp_layout  : arena size and part offsets for a model at a world size
+ *   okb_dp_attach  : this rank's geometry + every rank's arena as mapped in this process
+ *   okb_dp_train_steps : n steps of the last okb_sample (which must cover this rank's streams): plan + grad of positives
+ *                        [b_lo, b_hi) + fused reduce/push + owner update; loss_out[i] = mean hinge of the GLOBAL batch. */
+#define OKB_DP_MAX 16
+typedef struct {
+    int32_t rank, world;
+    INT b_lo, b_hi;                 /* this rank's positives of the global batch (its sampler streams' slots) */
+    void *arena[OKB_DP_MAX];        /* arena base of every rank as mapped HERE (arena[rank] is the local allocation) */
+    INT off_ent, off_ent_aux, off_rel, off_rel_aux;   /* tables inside an arena (bytes; -1 = absent) */
+    INT off_stage_ent, off_stage_rel;                 /* staging slabs [world][ceil(rows/world)][cols] */
+    INT off_flags;                                    /* 512-byte flag block */
+    INT arena_bytes;
+} okb_dp;
+int okb_peer_alloc(okb_ctx *c, INT bytes, void **dev_ptr, unsigned char *handle64);
+int okb_peer_open(okb_ctx *c, const unsigned char *handle64, void **dev_ptr);
+int okb_peer_close(okb_ctx *c, void *dev_ptr);
+int okb_peer_free(okb_ctx *c, void *dev_ptr);
+int okb_dp_layout(okb_ctx *c, const okb_model *m, INT world, okb_dp *out);
+int okb_dp_attach(okb_ctx *c, const okb_dp *cfg);
+int okb_dp_detach(okb_ctx *c);
+int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out,
+                       void *cuda_stream);
+
 /* ---- scoring = TransX.predict_def (TransE.py:53-58 ...).  h,t,r: device int64[n]; out: device
  *      float[n] (TransE: mean over d; others: sum).  Canonical evaluation order, see DESIGN.md. */
 int okb_predict(okb_ctx *c, const okb_model *m, const int64_t *h, const int64_t *t, const int64_t *r, INT n,
@@ -226,7 +257,7 @@ int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:
  * id 0 sampler, 1 plan (keys + radix sort), 2 grad kernel, 3 update kernel (SGD / Adam), 4 rank kernel,
- * 5 rank preparation.  okb_prof_read synchronises, returns the summed milliseconds and the number of
+ * 5 rank preparation, 6 data-parallel reduce+push kernel, 7 data-parallel owner-update kernel.  okb_prof_read synchronises, returns the summed milliseconds and the number of
  * launches since the last read, and clears the list. */
 int okb_prof_enable(okb_ctx *c, int on);
 int okb_prof_read(okb_ctx *c, int id, double *total_ms, INT *count);

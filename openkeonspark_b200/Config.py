@@ -276,6 +276,8 @@ class Config(object):
         Sampling and gradient-row planning do not depend on the parameters, so they are done for
         `plan_ahead` consecutive steps in one launch each; the batches are exactly the ones that many
         consecutive sampling() calls would have produced."""
+        if self._world is not None and self._world.mode == "owner":
+            return self._world.next_step(self)
         if self._chunk_pos >= self._chunk_len:
             n = self.batch_size * (3 + self.negative_ent + self.negative_rel)
             C = max(1, min(int(self.plan_ahead), (1 << 24) // n))
@@ -296,6 +298,8 @@ class Config(object):
         return None
 
     def get_parameters(self, mode="numpy"):
+        if self._world is not None and self._world.mode == "owner":
+            self._world.quiesce()                     # collective: peers' last row updates have landed
         res = {}
         for var_name in self.get_parameter_lists():
             v = self.get_parameters_by_name(var_name)
@@ -409,7 +413,9 @@ class Config(object):
         """loss_def + optimizer on batch `step` of the last sampling_device(); loss stays on the GPU."""
         self._ensure_model()
         m, hp = self._cmodel(), self._hyper()
-        if self._world is not None:
+        if self._world is not None and self._world.mode == "owner":
+            self.ctx.call("okb_dp_train_steps", ctypes.byref(m), ctypes.byref(hp), step, 1, _vp(self._loss_dev.data_ptr()), _stream())
+        elif self._world is not None:
             self._world.train_step(self, m, hp, step)
         else:
             self.ctx.call("okb_train_step", ctypes.byref(m), ctypes.byref(hp), step, _vp(self._loss_dev.data_ptr()), _stream())
@@ -423,6 +429,8 @@ class Config(object):
         self._ensure_model()
         cap = max(1, (1 << 24) // (self.batch_size * (3 + self.negative_ent + self.negative_rel)))
         n = max(1, min(int(self.plan_ahead if n is None else n), cap))
+        if self._world is not None and self._world.mode == "owner":
+            return self._world.train_chunk(self, n)
         if self._world is not None:
             return torch.stack([self.next_step_device().clone() for _ in range(n)]).reshape(-1)
         self.sampling_device(n)

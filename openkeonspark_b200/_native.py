@@ -29,6 +29,15 @@ class okb_hyper(C.Structure):
     _fields_ = [("margin", C.c_float), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
 
 
+OKB_DP_MAX = 16
+
+
+class okb_dp(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("b_lo", _i64), ("b_hi", _i64), ("arena", _vp * OKB_DP_MAX),
+                ("off_ent", _i64), ("off_ent_aux", _i64), ("off_rel", _i64), ("off_rel_aux", _i64),
+                ("off_stage_ent", _i64), ("off_stage_rel", _i64), ("off_flags", _i64), ("arena_bytes", _i64)]
+
+
 MODEL_ID = {"TransE": 0, "TransH": 1, "TransR": 2, "TransD": 3}
 
 # name -> (restype, argtypes); every okb_* symbol of include/okb200.h
@@ -64,6 +73,14 @@ _SIGS = {
     "okb_update": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _vp, _vp, _vp, _vp, _vp]),
     "okb_train_step": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _vp, _vp]),
     "okb_train_steps": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _vp, _vp]),
+    "okb_peer_alloc": (_int, [_vp, _i64, C.POINTER(_vp), _vp]),
+    "okb_peer_open": (_int, [_vp, _vp, C.POINTER(_vp)]),
+    "okb_peer_close": (_int, [_vp, _vp]),
+    "okb_peer_free": (_int, [_vp, _vp]),
+    "okb_dp_layout": (_int, [_vp, C.POINTER(okb_model), _i64, C.POINTER(okb_dp)]),
+    "okb_dp_attach": (_int, [_vp, C.POINTER(okb_dp)]),
+    "okb_dp_detach": (_int, [_vp]),
+    "okb_dp_train_steps": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _vp, _vp]),
     "okb_predict": (_int, [_vp, C.POINTER(okb_model), _vp, _vp, _vp, _i64, _vp, _vp]),
     "okb_rank": (_int, [_vp, C.POINTER(okb_model), _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "okb_rank_finalize": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -66,10 +66,14 @@ struct okb_ctx {
     DevBuf keys_ent, keys_rel, perm_ent, perm_rel, sort_tmp, hist, gent, grel, flags, lossterms, rowseg_e, rowseg_r;
     DevBuf rank_ws, host_io, partial;
     i64 plan_ne = 0, plan_nr = 0, plan_lo = 0, plan_hi = 0;   // steps [plan_lo, plan_hi) of the sampled batches are planned
+    i64 plan_b_lo = 0, plan_b_hi = 0;                          // ... for positives [plan_b_lo, plan_b_hi) of each step
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
     bool adam_tma = false;            // OKB_FLAG_ADAM_TMA: TMA-staged single-wave Adam pass instead of the register-only one
     bool l2_prefetch = false;         // OKB_FLAG_L2_PREFETCH: grad kernel prefetches the Adam state into L2
+    okb_dp dp = {};                   // owner-sharded data parallelism (okb_dp_attach)
+    bool dp_on = false;
+    unsigned long long dp_epoch = 0;
     bool pdl = true;                  // programmatic dependent launch between the grad and update kernels
     bool rowhead_ready = false;       // Adam: per-step row -> first sorted position map built for the planned chunk
     int ent_bits = 0, rel_bits = 0;
@@ -86,7 +90,7 @@ struct okb_ctx {
     (c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return OKB_ERR_CUDA; } } while (0)
 
 // kernel ids for okb_prof_*
-enum { PROF_SAMPLE = 0, PROF_PLAN = 1, PROF_GRAD = 2, PROF_UPDATE = 3, PROF_RANK = 4, PROF_RANK_PREP = 5 };
+enum { PROF_SAMPLE = 0, PROF_PLAN = 1, PROF_GRAD = 2, PROF_UPDATE = 3, PROF_RANK = 4, PROF_RANK_PREP = 5, PROF_DP_PUSH = 6, PROF_DP_OWNER = 7 };
 static inline void prof_mark(okb_ctx *c, int id, cudaStream_t s) {
     if (!c->prof_on) return;
     cudaEvent_t e;

@@ -16,10 +16,16 @@
 // Roofline: HBM-bound gather/scatter of fp32 rows; no dense contraction, so no tensor cores here
 // (TransR's projection lives in transr.cu).
 #include <algorithm>
+#include <cstring>
 
 #include "okb_internal.h"
 
 #define FULL 0xffffffffu
+// flag block of a data-parallel peer arena (see "data parallel, owner-sharded" below), in u64 units
+#define DP_FLAG_STAGE 0        // stage_ready[16]: rank q has finished pushing its partial rows of epoch e
+#define DP_FLAG_X 16           // x_ready[16]: rank q has finished publishing its updated rows of epoch e
+#define DP_FLAG_LOSS 32        // float loss_part[16] (byte 256)
+#define DP_FLAG_BYTES 512
 // Programmatic dependent launch (PTX griddepcontrol): a kernel launched with the stream-serialization attribute may
 // start while its predecessor drains; `wait` blocks until the predecessor grid has completed and flushed.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -40,18 +46,19 @@ struct PlanArgs {
     const i32 *batch;          // [steps][3][S] plane-major batches
     i32 *keys;                 // [C][B*NE + B*NR] composite keys
     i32 B, k, kr, NE, NR, E, R, S, step_lo, C;
+    i32 b_lo, Bl;              // positives [b_lo, b_lo + Bl) of every step are planned (a data-parallel rank plans its own)
 };
 // Combined key space of one step: entity row e -> e, relation row r -> E + r, unused slot -> E + R.
 // Several steps are planned by ONE segmented sort (one segment per step, radix.cu).
 __global__ void plan_keys_kernel(PlanArgs a) {
     const i64 tid = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (i64)a.C * a.B) return;
-    const i32 c = (i32)(tid / a.B), b = (i32)(tid % a.B);
+    if (tid >= (i64)a.C * a.Bl) return;
+    const i32 c = (i32)(tid / a.Bl), bl = (i32)(tid % a.Bl), b = a.b_lo + bl;
     const i32 *bh = a.batch + (i64)(a.step_lo + c) * 3 * a.S, *bt = bh + a.S, *br = bt + a.S;
     const i32 ph = bh[b], pt = bt[b], pr = br[b];
-    const i32 n = a.B * (a.NE + a.NR), off = 0;
-    i32 *ke = a.keys + (i64)c * n + (i64)b * a.NE;
-    i32 *kr_ = a.keys + (i64)c * n + (i64)a.B * a.NE + (i64)b * a.NR;
+    const i32 n = a.Bl * (a.NE + a.NR), off = 0;
+    i32 *ke = a.keys + (i64)c * n + (i64)bl * a.NE;
+    i32 *kr_ = a.keys + (i64)c * n + (i64)a.Bl * a.NE + (i64)bl * a.NR;
     const i32 none = off + a.E + a.R;
     ke[0] = off + ph; ke[1] = off + pt; kr_[0] = off + a.E + pr;
     for (i32 m = 0; m < a.k; m++) {
@@ -351,6 +358,12 @@ struct GradArgs {
     const char *pf_ptr[12];
     unsigned pf_bytes[12], pf_slice[12];
     i32 npf;
+    i32 slot_base;             // gradient rows of positive b go to slot b - slot_base (a data-parallel rank keeps only its own)
+    // owner-sharded data parallelism: the tables are complete once every rank has published `wait_epoch`
+    const unsigned long long *wait_flags;
+    unsigned long long *announce[OKB_DP_MAX];              // this rank's x_ready word in every rank's flag block
+    unsigned long long wait_epoch;
+    i32 wait_n;
 };
 
 // ------------------------------------------------------------------------------------------ grad
@@ -360,6 +373,16 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     const int lane = threadIdx.x & 31;
     const i32 b = a.b_lo + blockIdx.x * GRAD_WARPS + (threadIdx.x >> 5);
     if (b >= a.b_hi) return;
+    if (a.wait_flags) {                                    // peers still pushing updated rows of the previous step?
+        if (lane < a.wait_n) {
+            // this rank's previous owner-update kernel has completed (stream order): tell every peer, then wait for theirs
+            if (blockIdx.x == 0 && threadIdx.x < 32)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
+            unsigned long long v;
+            do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + lane) : "memory"); } while (v < a.wait_epoch);
+        }
+        __syncwarp();
+    }
     const int D = a.m.ent_dim;
     const int ce = MODEL == OKB_TRANSD ? 2 * D : D, cr = MODEL == OKB_TRANSE ? D : 2 * D;
     const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
@@ -393,7 +416,7 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     EntG<MODEL, N> accH, accT;
     RelG<MODEL, N> accR;
     accH.zero(); accT.zero(); accR.zero();
-    float *ge = a.gent + (i64)b * a.NE * ce, *gr = a.grel + (i64)b * a.NR * cr;
+    float *ge = a.gent + (i64)(b - a.slot_base) * a.NE * ce, *gr = a.grel + (i64)(b - a.slot_base) * a.NR * cr;
     float hinge_sum = 0.f;
     i32 active = 0;
 
@@ -454,7 +477,7 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     put_ent<MODEL, VW, NV>(ge, accH, D, lane);
     put_ent<MODEL, VW, NV>(ge + ce, accT, D, lane);
     put_rel<MODEL, VW, NV>(gr, accR, D, lane);
-    if (lane == 0) a.loss_terms[b] = hinge_sum;
+    if (lane == 0) a.loss_terms[b - a.slot_base] = hinge_sum;
 }
 
 // ------------------------------------------------------------------------------------------ update
@@ -906,10 +929,17 @@ int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT B, INT k, INT kr, INT *er
 }
 
 // Plan steps [step_lo, step_hi) of the sampled batches with ONE radix sort.
-int okb_plan_steps(okb_ctx *c, INT step_lo, INT step_hi, void *stream) {
+static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, void *stream);
+int okb_plan_steps(okb_ctx *c, INT step_lo, INT step_hi, void *stream) { return plan_steps(c, step_lo, step_hi, 0, c->B, stream); }
+}  // extern "C"
+static bool planned(const okb_ctx *c, INT lo, INT hi, INT b_lo, INT b_hi) {
+    return lo >= c->plan_lo && hi <= c->plan_hi && c->plan_b_lo == b_lo && c->plan_b_hi == b_hi;
+}
+static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, void *stream) {
     if (step_lo < 0 || step_hi > c->steps || step_lo >= step_hi) OKB_FAIL(c, OKB_ERR_ARG, "step range out of range (sample first)");
+    if (b_lo < 0 || b_hi > c->B || b_lo >= b_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad positive range");
     cudaStream_t s = (cudaStream_t)stream;
-    const i64 B = c->B, NE = 2 + c->K, NR = 1 + c->KR, n = B * (NE + NR), S = B * (1 + c->K + c->KR);
+    const i64 B = b_hi - b_lo, NE = 2 + c->K, NR = 1 + c->KR, n = B * (NE + NR), S = c->B * (1 + c->K + c->KR);
     const i64 C = step_hi - step_lo, ks = c->E + c->R + 1, total = C * n;
     if (total > 0x3fffffffLL || C > 65535) OKB_FAIL(c, OKB_ERR_ARG, "too many steps planned at once");
     if (c->keys_ent.ensure(sizeof(i32) * total * 2) || c->perm_ent.ensure(sizeof(i32) * total))
@@ -918,24 +948,28 @@ int okb_plan_steps(okb_ctx *c, INT step_lo, INT step_hi, void *stream) {
     PlanArgs a;
     a.batch = c->batch.as<i32>();
     a.keys = c->keys_ent.as<i32>();
-    a.B = (i32)B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)NE; a.NR = (i32)NR; a.E = (i32)c->E; a.R = (i32)c->R;
-    a.S = (i32)S; a.step_lo = (i32)step_lo; a.C = (i32)C;
+    a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)NE; a.NR = (i32)NR; a.E = (i32)c->E; a.R = (i32)c->R;
+    a.S = (i32)S; a.step_lo = (i32)step_lo; a.C = (i32)C; a.b_lo = (i32)b_lo; a.Bl = (i32)B;
     plan_keys_kernel<<<(unsigned)((C * B + 127) / 128), 128, 0, s>>>(a);
     OKB_LAUNCHED(1);
     c->plan_ne = B * NE; c->plan_nr = B * NR; c->plan_lo = step_lo; c->plan_hi = step_hi;
+    c->plan_b_lo = b_lo; c->plan_b_hi = b_hi;
     c->rowhead_ready = false;
     int rc = okb_sort_pairs_seg(c, a.keys, a.keys + total, c->perm_ent.as<i32>(), n, C, bits_for(ks), s);
     if (rc) return rc;
     OKB_CUDA(c, cudaGetLastError());
     return 0;
 }
+extern "C" {
 int okb_plan(okb_ctx *c, INT step, void *stream) {
-    if (step >= c->plan_lo && step < c->plan_hi) return 0;      // already planned as part of a chunk
+    if (planned(c, step, step + 1, 0, c->B)) return 0;          // already planned as part of a chunk
     return okb_plan_steps(c, step, step + 1, stream);
 }
 
-int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, float *gent, float *grel,
-             float *loss_terms, void *stream) {
+}  // extern "C"
+static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, INT slot_base, float *gent,
+                       float *grel, float *loss_terms, const unsigned long long *wait_flags, unsigned long long wait_epoch, int wait_n,
+                       void *stream) {
     int vw, nv;
     int rc = check_model(c, m, vw, nv);
     if (rc) return rc;
@@ -945,7 +979,8 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
     cudaStream_t s = (cudaStream_t)stream;
     const i64 S = c->B * (1 + c->K + c->KR);
     if (m->model == OKB_TRANSR) {                          // relation-bucketed kernel; needs the plan's relation segments
-        if (step < c->plan_lo || step >= c->plan_hi) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
+        if (slot_base || wait_flags) OKB_FAIL(c, OKB_ERR_ARG, "TransR is not supported by the owner-sharded data-parallel path");
+        if (!planned(c, step, step + 1, 0, c->B)) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
         if ((rc = ensure_rowhead(c, s))) return rc;
         const i64 n = c->plan_ne + c->plan_nr, total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
         return okb_transr_launch_grad(c, m, hp, c->batch.as<i32>() + step * 3 * S, c->keys_ent.as<i32>() + total + rel,
@@ -959,7 +994,11 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
     a.gent = gent; a.grel = grel; a.loss_terms = loss_terms;
     a.margin = hp->margin; a.w = 1.0f / (float)(c->B * (c->K + c->KR));
     a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)(2 + c->K); a.NR = (i32)(1 + c->KR);
-    a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi;
+    a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi; a.slot_base = (i32)slot_base;
+    a.wait_flags = wait_flags; a.wait_epoch = wait_epoch; a.wait_n = wait_n;
+    if (wait_flags)
+        for (int q = 0; q < wait_n; q++)
+            a.announce[q] = (unsigned long long *)((char *)c->dp.arena[q] + c->dp.off_flags) + DP_FLAG_X + c->dp.rank;
     const unsigned grid = (unsigned)((b_hi - b_lo + GRAD_WARPS - 1) / GRAD_WARPS);
     a.npf = 0;
     if (m->optimizer == OKB_ADAM && c->l2_prefetch && m->m_ent) {
@@ -992,6 +1031,11 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
     OKB_CUDA(c, cudaGetLastError());
     return 0;
 }
+extern "C" {
+int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, float *gent, float *grel,
+             float *loss_terms, void *stream) {
+    return launch_grad(c, m, hp, step, b_lo, b_hi, 0, gent, grel, loss_terms, nullptr, 0, 0, stream);
+}
 
 int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
                const float *loss_terms, float *loss_out, void *stream) {
@@ -1001,7 +1045,7 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
     const bool is_tr = m->model == OKB_TRANSR;
     cudaStream_t s = (cudaStream_t)stream;
     const i64 n = c->plan_ne + c->plan_nr;
-    if (n == 0 || step < c->plan_lo || step >= c->plan_hi) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
+    if (n == 0 || !planned(c, step, step + 1, 0, c->B)) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
     const i64 total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
     UpdArgs a;
     a.m = *m; a.hp = *hp;
@@ -1093,7 +1137,7 @@ int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
     if (c->gent.ensure(sizeof(float) * er * ec) || c->grel.ensure(sizeof(float) * rr * rcn) ||
         c->lossterms.ensure(sizeof(float) * c->B))
         OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (gradient rows)");
-    if (step < c->plan_lo || step >= c->plan_hi) { if ((rc = okb_plan(c, step, stream))) return rc; }
+    if (!planned(c, step, step + 1, 0, c->B)) { if ((rc = okb_plan(c, step, stream))) return rc; }
     if ((rc = okb_grad(c, m, hp, step, 0, c->B, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), stream))) return rc;
     return okb_update(c, m, hp, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), loss_out, stream);
 }
@@ -1105,7 +1149,7 @@ int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
 // each step's loss, or pass NULL.
 int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out, void *stream) {
     if (step_lo < 0 || n < 1 || step_lo + n > c->steps) OKB_FAIL(c, OKB_ERR_ARG, "step range out of range (sample first)");
-    if (step_lo < c->plan_lo || step_lo + n > c->plan_hi) {
+    if (!planned(c, step_lo, step_lo + n, 0, c->B)) {
         int rc = okb_plan_steps(c, step_lo, step_lo + n, stream);
         if (rc) return rc;
     }
@@ -1115,5 +1159,329 @@ int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT ste
     }
     return 0;
 }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------ data parallel, owner-sharded
+// One process per GPU inside a box.  Every rank holds the full tables (the gathers of the grad kernel stay local) but
+// OWNS the update of a contiguous range of rows: its Adam slots are only maintained for that range.  A step is
+//
+//   grad         local positives only (this rank's sampler streams)            -> local gradient rows
+//   reduce+push  one warp per table row: fixed-order segment sum of the local gradient rows of that row, stored
+//                straight into the OWNER's staging slab over NVLink (peer stores), slot [this rank][row]
+//   owner update waits for every rank's slab, sums the `world` partial rows in rank order, applies SGD / TF1-Adam to
+//                its own rows and stores the new row into EVERY rank's table (peer stores)
+//
+// i.e. the reduce-scatter and all-gather of a synchronous data-parallel step are fused into the two update kernels
+// as plain stores into peer memory; per rank and step (N-1)/N of one dense gradient leaves and (N-1)/N of one table
+// arrives, independent of N, while the dense Adam pass shrinks to 1/N of the rows.  Cross-GPU ordering: each kernel
+// ends with "last block publishes the epoch in every peer's flag word" (release, system scope) and the consumer
+// kernel's blocks spin on their local flag words (acquire) before touching peer-written data.  Sums are taken in
+// rank order, so all replicas stay bit-identical to each other (not to the single-GPU order: (a+b)+(c+d)).
+
+struct DpPush {
+    char *arena[OKB_DP_MAX];
+    i64 off_stage_ent, off_stage_rel, off_flags;
+    i32 ent_lo[OKB_DP_MAX + 1], rel_lo[OKB_DP_MAX + 1];
+    i32 own_max_ent, own_max_rel, world, rank, Bl;
+    unsigned long long epoch;
+};
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Signalling rides on kernel boundaries: all peer stores of a kernel are performed when the grid completes, so the
+// NEXT kernel in the stream announces it — block 0 publishes "my previous kernel is done" (release, system scope) in
+// every peer's flag word, then every block waits (acquire) until all ranks have announced the same epoch.  No fences
+// or tickets inside the producing kernels.
+__device__ __forceinline__ void dp_announce_and_wait(char *const *arena, i64 off_flags, int world, int rank, int which,
+                                                     unsigned long long epoch, bool announce) {
+    if ((int)threadIdx.x < world) {
+        if (announce) st_release_sys((unsigned long long *)(arena[threadIdx.x] + off_flags) + which + rank, epoch);
+        const unsigned long long *f = (const unsigned long long *)(arena[rank] + off_flags) + which + threadIdx.x;
+        while (ld_acquire_sys(f) < epoch) { }
+    }
+    __syncthreads();
+}
+
+template <int VW, int NV>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) dp_reduce_push_kernel(UpdArgs a, DpPush d) {
+    constexpr int N = VW * NV;
+    const int lane = threadIdx.x & 31;
+    if ((i32)blockIdx.x >= a.work_blocks) {                // the extra block: this rank's hinge sum, in a fixed order
+        __shared__ float sh[WARPS_PER_BLOCK];
+        float x = 0.f;
+        for (i32 i = threadIdx.x; i < d.Bl; i += WARPS_PER_BLOCK * 32) x += a.loss_terms[i];
+        x = wsum(x);
+        if (lane == 0) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if ((int)threadIdx.x < d.world) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < WARPS_PER_BLOCK; w++) t += sh[w];
+            ((float *)((unsigned long long *)(d.arena[threadIdx.x] + d.off_flags) + DP_FLAG_LOSS))[d.rank] = t;
+        }
+    } else {
+        const i32 key = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+        if (key < a.key_limit) {
+            const bool is_ent = key < a.E;
+            const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
+            const i32 row = is_ent ? key : key - a.E;
+            const i32 *lo = is_ent ? d.ent_lo : d.rel_lo;
+            int o = 0;
+            while (row >= lo[o + 1]) o++;
+            const i32 cols = is_ent ? a.ce : a.cr, own_max = is_ent ? d.own_max_ent : d.own_max_rel;
+            float *dst = (float *)(d.arena[o] + (is_ent ? d.off_stage_ent : d.off_stage_rel)) +
+                         ((i64)d.rank * own_max + (row - lo[o])) * cols;
+            const int4 seg = __ldg(a.rowhead + key);
+            const int parts = cols / D;
+            for (int p = 0; p < parts; p++) {
+                Frag<VW, NV> f;
+                f.zero();
+                if (seg.x >= 0) seg_sum<VW, NV>(a, seg.x, seg.y, is_ent, D, p, lane, f.v);
+                f.store(dst + p * D, D, lane);
+            }
+        }
+    }
+}
+
+struct DpTab {
+    float *m, *v;              // local Adam slots (full-size arrays; only the owned rows are maintained)
+    i64 x_off, stage_off;      // byte offsets in an arena: the table / this table's staging slab
+    i64 vec_end;               // cumulative vector count over the OWNED rows of the table list
+    i32 D, cols, part, row_lo, own_max;
+};
+struct DpOwn {
+    okb_hyper hp;
+    char *arena[OKB_DP_MAX];
+    DpTab tab[4];
+    i64 off_flags;
+    i32 ntab, world, rank, adam;
+    unsigned long long epoch;
+    float *loss_out;
+    float w;
+};
+template <int VW>
+__global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
+    typedef typename VecT<VW>::T V;
+    dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, blockIdx.x == 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && d.loss_out) {   // mean hinge over the GLOBAL batch, rank order
+        const volatile float *lp = (const volatile float *)((unsigned long long *)(d.arena[d.rank] + d.off_flags) + DP_FLAG_LOSS);
+        float tot = 0.f;
+        for (int q = 0; q < d.world; q++) tot += lp[q];
+        d.loss_out[0] = tot * d.w;
+    }
+    const i64 total = d.tab[d.ntab - 1].vec_end;
+    const float b1 = d.hp.beta1, b2 = d.hp.beta2, lr = d.hp.lr, eps = d.hp.eps;
+    const char *own = d.arena[d.rank];
+    for (i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (i64)gridDim.x * blockDim.x) {
+        int t = 0;
+        while (v >= d.tab[t].vec_end) t++;
+        const DpTab &T = d.tab[t];
+        const unsigned lv = (unsigned)(v - (t ? d.tab[t - 1].vec_end : 0));
+        const unsigned vpr = (unsigned)T.D / VW;
+        const unsigned rl = lv / vpr, col = (lv - rl * vpr) * VW;
+        const i64 e = ((i64)T.row_lo + rl) * T.D + col;     // element index inside the full table
+        const float *st = (const float *)(own + T.stage_off) + (i64)rl * T.cols + T.part * T.D + col;
+        V xv = *reinterpret_cast<const V *>(own + T.x_off + e * 4);
+        V mv, vv;
+        if (d.adam) { mv = *reinterpret_cast<const V *>(T.m + e); vv = *reinterpret_cast<const V *>(T.v + e); }
+        float g[VW];
+#pragma unroll
+        for (int q = 0; q < VW; q++) g[q] = 0.f;
+        bool any = false;
+        for (int p = 0; p < d.world; p++) {                // partial rows in rank order
+            const V gp = __ldcg(reinterpret_cast<const V *>(st + (i64)p * T.own_max * T.cols));
+            const float *pg = reinterpret_cast<const float *>(&gp);
+#pragma unroll
+            for (int q = 0; q < VW; q++) { g[q] += pg[q]; any |= pg[q] != 0.f; }
+        }
+        float *xs = reinterpret_cast<float *>(&xv);
+        if (d.adam) {
+            float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+            for (int q = 0; q < VW; q++) {
+                const float mq = ms[q] * b1 + g[q] * (1.f - b1);
+                const float vq = vs[q] * b2 + (g[q] * g[q]) * (1.f - b2);
+                ms[q] = mq; vs[q] = vq;
+                xs[q] -= lr * mq / (sqrtf(vq) + eps);
+            }
+            *reinterpret_cast<V *>(T.m + e) = mv; *reinterpret_cast<V *>(T.v + e) = vv;
+        } else {
+            if (!any) continue;                            // SGD leaves rows without gradient untouched: nothing to publish
+#pragma unroll
+            for (int q = 0; q < VW; q++) xs[q] -= lr * g[q];
+        }
+        for (int p = 0; p < d.world; p++) *reinterpret_cast<V *>(d.arena[p] + T.x_off + e * 4) = xv;
+    }
+}
+
+static void fill_upd_args(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
+                          const float *loss_terms, UpdArgs &a) {
+    const i64 n = c->plan_ne + c->plan_nr, total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
+    a.m = *m; a.hp = *hp;
+    a.skeys = c->keys_ent.as<i32>() + total + rel; a.perm = c->perm_ent.as<i32>() + rel;
+    a.gent = gent; a.grel = grel; a.loss_terms = loss_terms; a.loss_out = nullptr;
+    a.n = (i32)n; a.n_ent_slots = (i32)c->plan_ne; a.E = (i32)c->E; a.R = (i32)c->R; a.B = (i32)c->B;
+    a.w = 1.0f / (float)(c->B * (c->K + c->KR));
+    group_cols(m, a.ce, a.cr);
+    a.ntab = 0;
+    a.key_limit = (i32)(c->E + c->R);
+    a.rowhead = c->rowseg_e.as<int4>() + (step - c->plan_lo) * (c->E + c->R);
+    a.pcols = std::max(a.ce, a.cr);
+    a.hub = (double)c->plan_ne * c->max_ent_share > PCH || (double)c->plan_nr * c->max_rel_share > PCH;
+    a.partial = nullptr; a.by_row = 1; a.loss_blocks = 1;
+    a.loss_part = nullptr; a.loss_ctr = nullptr;
+}
+
+extern "C" {
+
+int okb_dp_attach(okb_ctx *c, const okb_dp *cfg) {
+    if (!cfg || cfg->world < 1 || cfg->world > OKB_DP_MAX || cfg->rank < 0 || cfg->rank >= cfg->world)
+        OKB_FAIL(c, OKB_ERR_ARG, "bad data-parallel geometry");
+    if (cfg->b_lo < 0 || cfg->b_hi <= cfg->b_lo) OKB_FAIL(c, OKB_ERR_ARG, "bad positive range");
+    for (int q = 0; q < cfg->world; q++) if (!cfg->arena[q]) OKB_FAIL(c, OKB_ERR_ARG, "peer arena missing");
+    c->dp = *cfg;
+    c->dp_on = true;
+    c->dp_epoch = 0;
+    return 0;
+}
+int okb_dp_detach(okb_ctx *c) { c->dp_on = false; return 0; }
+
+/* bytes a rank's arena needs, and the offsets of its parts (all 256-byte aligned) */
+int okb_dp_layout(okb_ctx *c, const okb_model *m, INT world, okb_dp *out) {
+    if (world < 1 || world > OKB_DP_MAX) OKB_FAIL(c, OKB_ERR_ARG, "world size not supported");
+    if (m->model == OKB_TRANSR) OKB_FAIL(c, OKB_ERR_ARG, "TransR is not supported by the owner-sharded data-parallel path");
+    i32 ce, cr;
+    group_cols(m, ce, cr);
+    i64 off = 0;
+    auto take = [&](i64 bytes) { i64 o = off; off += (bytes + 255) & ~(i64)255; return o; };
+    const i64 tb_e = c->E * m->ent_dim * 4, tb_r = c->R * m->rel_dim * 4;
+    out->off_ent = take(tb_e);
+    out->off_ent_aux = m->model == OKB_TRANSD ? take(tb_e) : -1;
+    out->off_rel = take(tb_r);
+    out->off_rel_aux = m->model != OKB_TRANSE ? take(tb_r) : -1;
+    const i64 own_e = (c->E + world - 1) / world, own_r = (c->R + world - 1) / world;
+    out->off_stage_ent = take(world * own_e * ce * 4);
+    out->off_stage_rel = take(world * own_r * cr * 4);
+    out->off_flags = take(DP_FLAG_BYTES);
+    out->arena_bytes = off;
+    out->world = (int32_t)world;
+    return 0;
+}
+
+int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out, void *stream) {
+    if (!c->dp_on) OKB_FAIL(c, OKB_ERR_STATE, "okb_dp_attach first");
+    int vw, nv;
+    int rc = check_model(c, m, vw, nv);
+    if (rc) return rc;
+    if (m->model == OKB_TRANSR) OKB_FAIL(c, OKB_ERR_ARG, "TransR is not supported by the owner-sharded data-parallel path");
+    const okb_dp &P = c->dp;
+    if (step_lo < 0 || n < 1 || step_lo + n > c->steps) OKB_FAIL(c, OKB_ERR_ARG, "step range out of range (sample first)");
+    if (P.b_hi > c->B) OKB_FAIL(c, OKB_ERR_ARG, "rank's positive range exceeds the sampled batch");
+    char *own = (char *)P.arena[P.rank];
+    if ((char *)m->ent != own + P.off_ent || (char *)m->rel != own + P.off_rel ||
+        (m->ent_aux && (char *)m->ent_aux != own + P.off_ent_aux) || (m->rel_aux && (char *)m->rel_aux != own + P.off_rel_aux))
+        OKB_FAIL(c, OKB_ERR_ARG, "model tables must live in this rank's peer arena at the okb_dp_layout offsets");
+    cudaStream_t s = (cudaStream_t)stream;
+    const i64 Bl = P.b_hi - P.b_lo;
+    INT er, ec, rr, rcn;
+    if ((rc = okb_grad_sizes(c, m, Bl, c->K, c->KR, &er, &ec, &rr, &rcn))) return rc;
+    if (c->gent.ensure(sizeof(float) * er * ec) || c->grel.ensure(sizeof(float) * rr * rcn) || c->lossterms.ensure(sizeof(float) * Bl))
+        OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (gradient rows)");
+    if (!planned(c, step_lo, step_lo + n, P.b_lo, P.b_hi)) {      // plan everything that is sampled from here on with one sort
+        if ((rc = plan_steps(c, step_lo, c->steps, P.b_lo, P.b_hi, stream))) return rc;
+    }
+    if ((rc = ensure_rowhead(c, s))) return rc;
+    const bool was_pdl = c->pdl;
+    c->pdl = false;                                        // kernels that spin on peer flags must not start early
+    const i64 own_e = (c->E + P.world - 1) / P.world, own_r = (c->R + P.world - 1) / P.world;
+    for (INT i = 0; i < n; i++) {
+        const INT step = step_lo + i;
+        const unsigned long long epoch = c->dp_epoch + 1;
+        const unsigned long long *xflags = (const unsigned long long *)(own + P.off_flags) + DP_FLAG_X;
+        if ((rc = launch_grad(c, m, hp + i, step, P.b_lo, P.b_hi, P.b_lo, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(),
+                              xflags, c->dp_epoch, P.world, stream))) { c->pdl = was_pdl; return rc; }
+        UpdArgs a;
+        fill_upd_args(c, m, hp + i, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), a);
+        if (a.hub) {
+            const i64 nblocks = a.n / PCH;
+            if (c->partial.ensure(sizeof(float) * (size_t)(nblocks + 1) * a.pcols)) { c->pdl = was_pdl; OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (partial sums)"); }
+            a.partial = c->partial.as<float>();
+            const unsigned pg = (unsigned)((nblocks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK + 1);
+            DISPATCH_LAYOUT(vw, nv, CALL_PRE);
+            OKB_LAUNCHED(1);
+        }
+        DpPush d;
+        for (int q = 0; q < OKB_DP_MAX; q++) d.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
+        d.off_stage_ent = P.off_stage_ent; d.off_stage_rel = P.off_stage_rel; d.off_flags = P.off_flags;
+        for (int q = 0; q <= P.world; q++) { d.ent_lo[q] = (i32)std::min<i64>(c->E, q * own_e); d.rel_lo[q] = (i32)std::min<i64>(c->R, q * own_r); }
+        d.own_max_ent = (i32)own_e; d.own_max_rel = (i32)own_r; d.world = P.world; d.rank = P.rank; d.Bl = (i32)Bl; d.epoch = epoch;
+        a.work_blocks = (i32)((a.key_limit + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+        {
+            ProfScope ps(c, PROF_UPDATE, s);
+#define CALL_PUSH(VW, NV) dp_reduce_push_kernel<VW, NV><<<a.work_blocks + 1, WARPS_PER_BLOCK * 32, 0, s>>>(a, d)
+            { ProfScope pp(c, PROF_DP_PUSH, s); DISPATCH_LAYOUT(vw, nv, CALL_PUSH); }
+            ProfScope po(c, PROF_DP_OWNER, s);
+            DpOwn o;
+            o.hp = hp[i];
+            for (int q = 0; q < OKB_DP_MAX; q++) o.arena[q] = d.arena[q];
+            o.off_flags = P.off_flags; o.world = P.world; o.rank = P.rank; o.adam = m->optimizer == OKB_ADAM; o.epoch = epoch;
+            o.loss_out = loss_out ? loss_out + i : nullptr;
+            o.w = 1.0f / (float)(c->B * (c->K + c->KR));
+            o.ntab = 0;
+            i64 acc = 0;
+            auto add = [&](i64 x_off, float *mm, float *vv, bool is_ent, int part) {
+                if (x_off < 0) return;
+                const int D = is_ent ? m->ent_dim : m->rel_dim;
+                const i64 lo = is_ent ? d.ent_lo[P.rank] : d.rel_lo[P.rank], hi = is_ent ? d.ent_lo[P.rank + 1] : d.rel_lo[P.rank + 1];
+                acc += (hi - lo) * D / vw;
+                DpTab T;
+                T.m = mm; T.v = vv; T.x_off = x_off; T.stage_off = is_ent ? P.off_stage_ent : P.off_stage_rel; T.vec_end = acc;
+                T.D = D; T.cols = is_ent ? a.ce : a.cr; T.part = part; T.row_lo = (i32)lo; T.own_max = (i32)(is_ent ? own_e : own_r);
+                o.tab[o.ntab++] = T;
+            };
+            add(P.off_ent, m->m_ent, m->v_ent, true, 0);
+            if (m->model == OKB_TRANSD) add(P.off_ent_aux, m->m_ent_aux, m->v_ent_aux, true, 1);
+            add(P.off_rel, m->m_rel, m->v_rel, false, 0);
+            if (m->model != OKB_TRANSE) add(P.off_rel_aux, m->m_rel_aux, m->v_rel_aux, false, 1);
+            const unsigned og = (unsigned)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)148 * 8));
+            if (vw == 4) dp_owner_kernel<4><<<og, 256, 0, s>>>(o);
+            else if (vw == 2) dp_owner_kernel<2><<<og, 256, 0, s>>>(o);
+            else dp_owner_kernel<1><<<og, 256, 0, s>>>(o);
+        }
+        OKB_LAUNCHED(2);
+        c->dp_epoch = epoch;
+    }
+    c->pdl = was_pdl;
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+/* ---- peer memory: allocations other processes of the box map over NVLink (CUDA IPC) */
+int okb_peer_alloc(okb_ctx *c, INT bytes, void **ptr, unsigned char *handle64) {
+    if (bytes <= 0 || !ptr || !handle64) OKB_FAIL(c, OKB_ERR_ARG, "bad peer allocation request");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    void *p = nullptr;
+    OKB_CUDA(c, cudaMalloc(&p, (size_t)bytes));
+    OKB_CUDA(c, cudaMemset(p, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    OKB_CUDA(c, cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, 64);
+    *ptr = p;
+    return 0;
+}
+int okb_peer_open(okb_ctx *c, const unsigned char *handle64, void **ptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    OKB_CUDA(c, cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int okb_peer_close(okb_ctx *c, void *ptr) { OKB_CUDA(c, cudaIpcCloseMemHandle(ptr)); return 0; }
+int okb_peer_free(okb_ctx *c, void *ptr) { OKB_CUDA(c, cudaFree(ptr)); return 0; }
 
 }  // extern "C"

@@ -9,6 +9,13 @@ process per GPU over torch.distributed (NCCL over NVLink):
          computes gradients only for the positives of ITS streams [g*W/G, (g+1)*W/G) (Base.cpp:85-92
          slice geometry).  One all-gather of the gradient rows, then every rank applies the same
          sorted, fixed-order update -> replicas stay bit-identical without a parameter broadcast.
+  train  (owner-sharded, the default on GPUs for TransE/H/D) every rank samples and plans only ITS positives, keeps
+         the full tables in a peer arena the other ranks map over NVLink (CUDA IPC), pushes per-row partial gradient
+         sums into the row owner's staging slab and receives the owner's updated rows — the reduce-scatter and
+         all-gather are plain peer stores inside the update kernels (csrc/train.cu, "data parallel, owner-sharded"),
+         no NCCL call per step.  Replicas stay bit-identical to each other; against the single-GPU order the sums
+         differ by fp32 re-association ((a+b)+(c+d)), so that mode is checked to a tolerance and `mode="exact"`
+         keeps the all-gather path below.
   eval   candidate entities are split into G contiguous ranges; tables are replicated, so every rank
          computes each query's reference score bit-identically, counts better candidates in its range,
          and the integer counts are all-reduced (sum) / the packed argmins all-reduced (min).
@@ -53,6 +60,8 @@ def allreduce_best(best, group=None):
 
 
 class DataParallel:
+    mode = "exact"
+
     def __init__(self, con, group=None):
         self.group = group
         self.world = dist.get_world_size(group)
@@ -115,7 +124,151 @@ class DataParallel:
         return con.link_prediction_records(q_lo, q_hi, lo, hi, reduce_fn)
 
 
-def attach(con, group=None):
-    """Enable data-parallel mode on a Config whose init() has run (torch.distributed initialised)."""
-    con._world = DataParallel(con, group)
+def owner_rows(n_rows, world):
+    """Row ranges owned by each rank in owner-sharded mode: blocks of ceil(n_rows / world) (csrc/train.cu okb_dp_*)."""
+    per = (n_rows + world - 1) // world
+    return [(min(n_rows, g * per), min(n_rows, (g + 1) * per)) for g in range(world)]
+
+
+class _ArenaView:
+    """__cuda_array_interface__ over raw device memory, so torch can wrap a slice of the peer arena."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+class OwnerSharded(DataParallel):
+    """Owner-sharded synchronous data parallelism over peer memory (see the module docstring)."""
+    mode = "owner"
+
+    def __init__(self, con, group=None):
+        super().__init__(con, group)
+        from ._native import okb_dp
+        from .Config import _AUX_ENT, _AUX_REL
+        con._ensure_model()
+        if con.trainModel.name == "TransR":
+            raise ValueError("owner-sharded mode does not cover TransR; use mode='exact'")
+        if self.world > 16:
+            raise ValueError("owner-sharded mode supports up to 16 ranks per box")
+        m = con._cmodel()
+        lay = okb_dp()
+        con.ctx.call("okb_dp_layout", ctypes.byref(m), self.world, ctypes.byref(lay))
+        own, handle = _vp(), (ctypes.c_ubyte * 64)()
+        con.ctx.call("okb_peer_alloc", lay.arena_bytes, ctypes.byref(own), handle)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        self._opened = []
+        for q in range(self.world):
+            if q == self.rank:
+                lay.arena[q] = own.value
+            else:
+                peer = _vp()
+                con.ctx.call("okb_peer_open", (ctypes.c_ubyte * 64).from_buffer_copy(handles[q]), ctypes.byref(peer))
+                lay.arena[q] = peer.value
+                self._opened.append(peer.value)
+        # re-home the tables into the arena (values preserved); the Adam slots stay ordinary local tensors
+        name = con.trainModel.name
+        offs = {"ent_embeddings": lay.off_ent, "rel_embeddings": lay.off_rel}
+        if _AUX_ENT.get(name):
+            offs[_AUX_ENT[name]] = lay.off_ent_aux
+        if _AUX_REL.get(name):
+            offs[_AUX_REL[name]] = lay.off_rel_aux
+        P = con.trainModel.parameter_lists
+        dev = con.trainModel.device
+        self._views = []
+        for k, off in offs.items():
+            view = _ArenaView(own.value + off, P[k].shape)
+            t = torch.as_tensor(view, device=dev)
+            t.copy_(P[k])
+            P[k] = t
+            self._views.append(view)
+        con._model_struct = None
+        lay.rank, lay.world = self.rank, self.world
+        lay.b_lo, lay.b_hi = self.ranges[self.rank]
+        self._lay, self._own = lay, own.value
+        per = con.workThreads // self.world
+        self.streams = (self.rank * per, (self.rank + 1) * per)
+        con.ctx.call("okb_dp_attach", ctypes.byref(lay))
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)                # every arena initialised before anyone pushes into it
+
+    def _sample(self, con, n):
+        from .Config import _stream
+        con.ctx.call("okb_sample", con.batch_size, con.negative_ent, con.negative_rel, n, self.streams[0], self.streams[1], _stream())
+        con._chunk_pos, con._chunk_len = 0, n
+
+    def next_step(self, con):
+        """One train step; batches are sampled (this rank's streams only) and planned plan_ahead steps at a time."""
+        from .Config import _stream
+        if con._chunk_pos >= con._chunk_len:
+            n = con.batch_size * (3 + con.negative_ent + con.negative_rel) // self.world
+            self._sample(con, max(1, min(int(con.plan_ahead), (1 << 24) // max(n, 1))))
+        m, hp = con._cmodel(), con._hyper()
+        con.ctx.call("okb_dp_train_steps", ctypes.byref(m), ctypes.byref(hp), con._chunk_pos, 1, _vp(con._loss_dev.data_ptr()), _stream())
+        con._chunk_pos += 1
+        con._step += 1
+        return con._loss_dev
+
+    def train_chunk(self, con, n):
+        """n steps in ONE library call (sample + plan + n x [grad, reduce/push, owner update])."""
+        from ._native import okb_hyper
+        from .Config import _stream
+        self._sample(con, n)
+        m = con._cmodel()
+        hps = (okb_hyper * n)(*[con._hyper() for _ in range(n)])
+        if getattr(con, "_loss_chunk", None) is None or con._loss_chunk.numel() < n:
+            con._loss_chunk = torch.zeros(n, dtype=torch.float32, device=con.trainModel.device)
+        con.ctx.call("okb_dp_train_steps", ctypes.byref(m), hps, 0, n, _vp(con._loss_chunk.data_ptr()), _stream())
+        con._step += n
+        con._chunk_pos = con._chunk_len = 0
+        return con._loss_chunk[:n]
+
+    def train_step(self, con, m, hp, step):
+        raise RuntimeError("owner-sharded mode steps through next_step()/train_chunk()")
+
+    def quiesce(self):
+        """Collective: returns when every rank's updates have landed in every table (a rank's last owner-update kernel
+        stores into its peers' arenas; nothing after it in the peers' streams waits for those stores)."""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    def link_prediction(self, con, q_lo=0, q_hi=None):
+        self.quiesce()
+        return super().link_prediction(con, q_lo, q_hi)
+
+    def sync_adam_slots(self, con):
+        """Make every rank's Adam m / v complete (each rank only maintains the rows it owns): for checkpoints."""
+        if con._adam is None:
+            return
+        for k, v in con._adam.items():
+            if not torch.is_tensor(v):
+                continue
+            rows = v.shape[0]
+            per = (rows + self.world - 1) // self.world
+            pad = torch.zeros(per * self.world, *v.shape[1:], dtype=v.dtype, device=v.device)
+            lo, hi = owner_rows(rows, self.world)[self.rank]
+            dist.all_gather_into_tensor(pad, torch.nn.functional.pad(v[lo:hi], (0, 0, 0, per - (hi - lo))), group=self.group)
+            v.copy_(pad[:rows])
+
+    def close(self, con):
+        self.quiesce()
+        con.ctx.call("okb_dp_detach")
+        for p in self._opened:
+            con.ctx.call("okb_peer_close", _vp(p))
+        self._opened = []
+
+
+def attach(con, group=None, mode="auto"):
+    """Enable data-parallel mode on a Config whose init() has run (torch.distributed initialised).
+    mode: "owner" (peer-memory owner-sharded update), "exact" (all-gather of gradient rows, bit-identical to one GPU),
+    "auto" = owner on NCCL/GPU for TransE/H/D when the batch touches a sizeable share of the rows, else exact."""
+    if mode == "auto":
+        mode = "exact"
+        if dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 16:      # peer memory needs GPUs
+            con._ensure_model()
+            dense = con.batch_size * (3 + con.negative_ent + con.negative_rel) * 4 >= con.entTotal + con.relTotal
+            if dense and con.trainModel.name != "TransR":
+                mode = "owner"
+    con._world = OwnerSharded(con, group) if mode == "owner" else DataParallel(con, group)
     return con._world

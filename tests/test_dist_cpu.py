@@ -31,6 +31,16 @@ def test_partition_geometry():
     assert los[0][0] == 0 and los[-1][1] == 14951 and all(a[1] == b[0] for a, b in zip(los[:-1], los[1:]))
 
 
+def test_owner_rows_geometry():
+    """Row ownership of the owner-sharded mode mirrors csrc/train.cu: blocks of ceil(rows / world), tail clamped."""
+    from openkeonspark_b200 import parallel
+    assert parallel.owner_rows(14951, 8)[0] == (0, 1869) and parallel.owner_rows(14951, 8)[7] == (13083, 14951)
+    assert parallel.owner_rows(18, 8) == [(0, 3), (3, 6), (6, 9), (9, 12), (12, 15), (15, 18), (18, 18), (18, 18)]
+    for rows, world in ((1345, 2), (40943, 4), (5, 16)):
+        r = parallel.owner_rows(rows, world)
+        assert r[0][0] == 0 and r[-1][1] == rows and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+
+
 class FakeCtx:
     """Stands in for _native.Ctx: fills this rank's rows exactly where okb_grad would."""
 
@@ -77,6 +87,7 @@ def _worker(rank, world, port, B, W):
     sys.modules["openkeonspark_b200.Config"]._stream = lambda: None     # no CUDA stream on the CPU box
     con = FakeCon(B, W, 4, 2, 1)
     dp = parallel.attach(con)
+    assert dp.mode == "exact"                        # gloo / CPU: the peer-memory mode is never chosen
     from openkeonspark_b200._native import okb_hyper, okb_model
     dp.train_step(con, okb_model(), okb_hyper(), 0)
     assert con.ctx.calls == ["okb_grad_sizes", "okb_plan", "okb_grad", "okb_update"]
