@@ -56,7 +56,7 @@ def params_for(g, rng):
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp"
 
     def __init__(self, index=0):
         self.p = None
@@ -66,7 +66,9 @@ class ClockSampler:
         except OSError:
             pass
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Median SM clock over the samples taken inside [t_from, t_to] (time.time() values; all samples if None)."""
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -81,6 +83,10 @@ class ClockSampler:
             if len(f) < 7:
                 continue
             try:
+                if t_from is not None and len(f) > 7:
+                    ts = datetime.datetime.strptime(f[7], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t_from - 0.11 or ts > t_to + 0.11:
+                        continue
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
@@ -92,6 +98,25 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline
+class native_stdout_to_stderr:
+    """The reference's Base.so prints with C printf; stdout must carry exactly ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        try:
+            import ctypes as _c
+            _c.CDLL(None).fflush(None)
+        except Exception:  # noqa: BLE001
+            pass
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_reference_path(g, steps, warmup, B, threads):
     """The reference's serial loop on host cores: sampling() by the reference's own Base.so
     (oracle/_ref, compiled from /root/reference/base/Base.cpp; the C restatement if absent) followed
@@ -136,7 +161,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     B = g.train.shape[0] // NBATCHES
     steps = max(1, min(args.steps, 40))          # bounded sample: each CPU step is ~0.1-1 s
-    val, desc, sec, kind = cpu_reference_path(g, steps, min(args.warmup, 3), B, cores)
+    with native_stdout_to_stderr():
+        val, desc, sec, kind = cpu_reference_path(g, steps, min(args.warmup, 3), B, cores)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "triples/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -150,8 +176,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="okb200")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -176,6 +202,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    clocks = ClockSampler(local) if rank == 0 else None      # nvidia-smi needs ~0.2 s to produce its first sample: start it early
 
     g = make_graph()
     con = okb.Config(private_context=True)
@@ -214,7 +241,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(local) if rank == 0 else None      # sampled from warm-up to the end of the timed regions
+    t_clk0 = time.time()                                     # clock samples are kept from warm-up to the end of the timed regions
     con.plan_ahead = args.plan_ahead
     for _ in range(args.warmup):
         one_step()
@@ -278,7 +305,7 @@ def main():
                  "ms_per_step": ms_c / (n_chunks * con.plan_ahead), "steps": n_chunks * con.plan_ahead,
                  "wall_ms_per_step": (time.perf_counter() - w0) * 1e3 / (n_chunks * con.plan_ahead),
                  "what": "Config.train_chunk_device(): %d steps per library call, tables L2-resident (no flush)" % con.plan_ahead}
-    clk = clocks.stop() if clocks else None
+    clk = clocks.stop(t_clk0, time.time()) if clocks else None
 
     # ---------------- e2e: the reference-shaped loop through the public API with HOST buffers
     # con.sampling() fills the numpy batch_h/t/r/y (D2H); con.train_step(...) feeds them back (H2D) and
@@ -316,10 +343,15 @@ def main():
         if cnt:
             kern[name] = {"ms": ms / cnt, "gbs": nbytes / (ms / cnt * 1e-3) / 1e9, "bytes": nbytes}
     dom = max(kern, key=lambda n: kern[n]["ms"]) if kern else None
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
+    # (profiles/r01d_ncu_full_train_kernels.txt; ncu invalidates the caches before every kernel replay, so the gradient
+    # rows the update kernel normally finds in L2 are counted as DRAM reads there; updated rows stay in L2 as dirty lines)
+    NCU_TRAFFIC = {"update": 31215104 + 212224, "grad": 5297408 + 1024}
     roofline = None
     if dom:
         roofline = {"kernel": "adam_kernel" if dom == "update" else "grad_kernel", "bound": "hbm", "achieved": kern[dom]["gbs"],
-                    "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                    "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
+                    "traffic": NCU_TRAFFIC[dom] if world == 1 else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dom]["bytes"], "avg_launch_ms": kern[dom]["ms"],
                     "measured": "CUDA-event pair around every launch of the kernel in a second pass of the same %d steps (L2 flushed between steps)" % args.steps,
                     "instrumented_ms_per_step": ms_instr / args.steps,
@@ -351,7 +383,8 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        val, desc, sec, kind = cpu_reference_path(g, 12, 2, B_local, cores)
+        with native_stdout_to_stderr():
+            val, desc, sec, kind = cpu_reference_path(g, 12, 2, B_local, cores)
         cpu = {"value": val, "unit": "triples/s", "cores": cores, "kind": kind, "sample": desc}
 
     if rank == 0:

@@ -670,7 +670,11 @@ __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
         const unsigned row = lv / vpr, col = (lv - row * vpr) * VW;
         const i64 e = (i64)lv * VW;
         // issue every independent load before the first dependent use
+#ifdef EXP_ADAM_NOGRAD
+        const int4 seg = make_int4(-1, 0, 0, 0);
+#else
         const int4 seg = __ldg(a.rowhead + T.key_off + row);
+#endif
         V xv = *reinterpret_cast<const V *>(T.x + e), mv = *reinterpret_cast<const V *>(T.m + e), vv = *reinterpret_cast<const V *>(T.v + e);
         pdl_wait();                                        // gradient rows of this step are complete from here on
         float g[VW];
@@ -1094,7 +1098,11 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         if (m->model == OKB_TRANSD) add(m->ent_aux, m->m_ent_aux, m->v_ent_aux, c->E, m->ent_dim, true, 1);
         if (!is_tr) add(m->rel, m->m_rel, m->v_rel, c->R, m->rel_dim, false, 0);
         if (!is_tr && m->model != OKB_TRANSE) add(m->rel_aux, m->m_rel_aux, m->v_rel_aux, c->R, m->rel_dim, false, 1);
+#ifdef EXP_ADAM_BLOCKS
+        a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)EXP_ADAM_BLOCKS);
+#else
         a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)148 * 16);
+#endif
         ProfScope ps(c, PROF_UPDATE, s);
         // programmatic dependent launch: the kernel may start while the grad kernel drains (see adam_kernel)
         cudaLaunchConfig_t cfg = {};
