@@ -252,7 +252,9 @@ enum { OKB_FLAG_TRANSR_TC = 1,
        /* OKB_FLAG_L2_PREFETCH = 4 (default off): with Adam, the (latency-bound) grad kernel issues bulk L2 prefetches of
         * the tables and their m / v slots, so the dense update pass that follows streams from L2.  Measured on the bench
         * workload: grad +2.1 us, update -1.5 us. */
-       OKB_FLAG_L2_PREFETCH = 4 };
+       OKB_FLAG_L2_PREFETCH = 4,
+       /* OKB_FLAG_ADAM_LEGACY = 5 (default off): the first, grid-stride form of the dense Adam pass (A/B runs). */
+       OKB_FLAG_ADAM_LEGACY = 5 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:

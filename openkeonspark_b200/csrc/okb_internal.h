@@ -69,6 +69,7 @@ struct okb_ctx {
     i64 plan_b_lo = 0, plan_b_hi = 0;                          // ... for positives [plan_b_lo, plan_b_hi) of each step
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
+    bool adam_legacy = false;         // OKB_FLAG_ADAM_LEGACY: grid-stride register kernel instead of the tile kernel
     bool adam_tma = false;            // OKB_FLAG_ADAM_TMA: TMA-staged single-wave Adam pass instead of the register-only one
     bool l2_prefetch = false;         // OKB_FLAG_L2_PREFETCH: grad kernel prefetches the Adam state into L2
     okb_dp dp = {};                   // owner-sharded data parallelism (okb_dp_attach)

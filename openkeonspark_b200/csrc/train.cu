@@ -482,7 +482,8 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
 
 // ------------------------------------------------------------------------------------------ update
 // one parameter table for the flat Adam pass; vec_end: cumulative vector count over the table list
-struct DenseTab { float *x, *m, *v; const float *grad; i64 vec_end; i32 D, key_off, cols, part, slot_off, blk_end; };
+struct DenseTab { float *x, *m, *v; const float *grad; i64 vec_end; i32 D, key_off, cols, part, slot_off, blk_end;
+                  unsigned magic, shift; };    // row = vector / (D / VW) as __umulhi(vector, magic) >> shift (magic 0: shift only)
 struct UpdArgs {
     okb_model m;
     okb_hyper hp;
@@ -730,121 +731,224 @@ __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
     }
 }
 
-// ---- TMA-staged form of the same pass (128-bit rows, D % 4 == 0).
-// A CTA owns one contiguous tile of ADAM_TILE_V vectors of ONE table.  Thread 0 requests the tile's x, m and v
-// slices with three bulk-async copies (TMA engine, completion on an mbarrier): 48 KB per CTA are in flight without
-// holding a single register, 4 CTAs per SM, the whole pass is one wave.  Meanwhile every thread resolves the row
-// map of its ADAM_TU vectors and (after griddepcontrol.wait — the only data of this kernel that depends on this
-// step's grad kernel) gathers their gradient rows.  The update runs out of shared memory and the three slices go
-// back to HBM with bulk stores.
-#define ADAM_TU 4
-#define ADAM_TILE_V (256 * ADAM_TU)
+// ---- Lean form of the register kernel: one 256-vector tile of ONE table per CTA, so the table descriptor is
+// block-uniform (uniform-datapath loads instead of a per-thread search through the kernel parameters), all index math
+// is 32-bit and the row / column split is a multiply-high by a host-computed reciprocal instead of an integer
+// division.  ncu's source page of adam_kernel attributes 65 % of its 336 instructions per warp to exactly that
+// integer / control / parameter-load overhead; the pass is issue-bound in disguise (each wave loads, then all warps
+// compete for the issue slots), so fewer instructions is what shortens it.
+#ifndef ADAM_TILE_MIN_BLOCKS
+#define ADAM_TILE_MIN_BLOCKS 4     // 62 registers, no spills: 14.7 us vs 18.8 us at 6 CTAs/SM with spilled vectors (TransH D=100 FB15K)
+#endif
+template <int VW>
+__global__ void __launch_bounds__(256, ADAM_TILE_MIN_BLOCKS) adam_tile_kernel(UpdArgs a) {
+    pdl_launch_dependents();                               // next step's grad kernel may prefetch its batch ids
+    if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a); return; }
+    typedef typename VecT<VW>::T V;
+    int t = 0;
+    while ((i32)blockIdx.x >= a.tab[t].blk_end) t++;       // block-uniform
+    const DenseTab &T = a.tab[t];
+    const unsigned nvec = (unsigned)(T.vec_end - (t ? a.tab[t - 1].vec_end : 0));
+    const unsigned lv = ((unsigned)blockIdx.x - (unsigned)(t ? a.tab[t - 1].blk_end : 0)) * 256u + threadIdx.x;
+    if (lv >= nvec) return;
+    const unsigned vpr = (unsigned)T.D / VW;
+    const unsigned row = T.magic ? (__umulhi(lv, T.magic) >> T.shift) : (lv >> T.shift);
+    const unsigned col = (lv - row * vpr) * VW;
+    const size_t e = (size_t)lv * VW;
+    float *px = T.x + e, *pm = T.m + e, *pv = T.v + e;
+    const int4 seg = __ldg(a.rowhead + T.key_off + row);
+    V xv = *reinterpret_cast<const V *>(px), mv = *reinterpret_cast<const V *>(pm), vv = *reinterpret_cast<const V *>(pv);
+    pdl_wait();                                            // gradient rows of this step are complete from here on
+    float g[VW];
+#pragma unroll
+    for (int q = 0; q < VW; q++) g[q] = 0.f;
+    if (seg.x >= 0) {
+        const float *gbase = T.grad + (T.part * T.D + (i32)col);
+        const i32 cols = T.cols, soff = T.slot_off, cnt = seg.y - seg.x;
+        auto add = [&](const V &w) {
+            const float *pw = reinterpret_cast<const float *>(&w);
+#pragma unroll
+            for (int q = 0; q < VW; q++) g[q] += pw[q];
+        };
+        auto add_raw = [&](i32 lo, i32 hi) {
+            for (i32 j = lo; j < hi; j++) add(__ldg(reinterpret_cast<const V *>(gbase + (size_t)(__ldg(a.perm + j) - soff) * cols)));
+        };
+        const bool long_seg = a.hub && cnt > PCH && (seg.x + PCH - 1) / PCH < seg.y / PCH;
+        if (!long_seg) {
+            // the first two contributions come straight from the row map: no perm[] hop for the common case
+            const V g0 = __ldg(reinterpret_cast<const V *>(gbase + (size_t)(seg.z - soff) * cols));
+            if (cnt > 1) {
+                const V g1 = __ldg(reinterpret_cast<const V *>(gbase + (size_t)(seg.w - soff) * cols));
+                add(g0); add(g1);
+                add_raw(seg.x + 2, seg.y);
+            } else add(g0);
+        } else {                                           // hub row: fringe rows + pre-reduced interior blocks, ascending order
+            const i32 b0 = (seg.x + PCH - 1) / PCH, b1 = seg.y / PCH;
+            const float *pb = a.partial + (T.part * T.D + (i32)col);
+            add_raw(seg.x, b0 * PCH);
+            for (i32 b = b0; b < b1; b++) add(__ldg(reinterpret_cast<const V *>(pb + (size_t)b * a.pcols)));
+            add_raw(b1 * PCH, seg.y);
+        }
+    }
+    const float b1 = a.hp.beta1, b2 = a.hp.beta2, lr = a.hp.lr, eps = a.hp.eps, c1 = 1.f - b1, c2 = 1.f - b2;
+    float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+    for (int q = 0; q < VW; q++) {
+        const float mq = ms[q] * b1 + g[q] * c1;
+        const float vq = vs[q] * b2 + (g[q] * g[q]) * c2;
+        ms[q] = mq; vs[q] = vq;
+        xs[q] -= lr * mq / (sqrtf(vq) + eps);
+    }
+    *reinterpret_cast<V *>(px) = xv; *reinterpret_cast<V *>(pm) = mv; *reinterpret_cast<V *>(pv) = vv;
+}
+
+// ---- Pipelined TMA form of the same pass (128-bit rows, D % 4 == 0).
+// The register kernel above runs as two lock-stepped waves: every warp of a wave loads, then every warp computes
+// (IEEE sqrt + divide per element: ~330 instructions per warp), then every warp stores — the memory pipe and the
+// issue slots take turns.  Here a PERSISTENT grid of 2 CTAs per SM walks the tiles (256 vectors of one table) through
+// a ring of AP_STAGES shared-memory stages: thread 0 keeps the x / m / v slices of the next AP_STAGES tiles in
+// flight with bulk-async (TMA) copies on per-stage mbarriers — 144 KB per SM without holding a register — while all
+// threads update the tile that has landed and hand it back to the copy engine with bulk stores.  The row-map entry
+// of tile j+2 and the first two gradient rows of tile j+1 are requested while tile j is computed, so the dependent
+// gather chain is off the critical path too.  Everything but the gradient rows is independent of this step's grad
+// kernel: under programmatic dependent launch the prologue overlaps that kernel's tail.
+#define AP_TILE 256
+#define AP_STAGES 6
+#define ADAM_TILE_V AP_TILE
+struct __align__(128) ApStage { float4 x[AP_TILE], m[AP_TILE], v[AP_TILE]; };
 __device__ __forceinline__ unsigned a_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(256, 3) adam_tma_kernel(UpdArgs a) {
+struct ApTile { int t; i64 vec0; i32 nvec; };
+__device__ __forceinline__ ApTile ap_tile(const UpdArgs &a, int tile) {
+    ApTile r;
+    r.t = 0;
+    while (tile >= a.tab[r.t].blk_end) r.t++;
+    const i64 tab_vecs = a.tab[r.t].vec_end - (r.t ? a.tab[r.t - 1].vec_end : 0);
+    r.vec0 = (i64)(tile - (r.t ? a.tab[r.t - 1].blk_end : 0)) * AP_TILE;
+    r.nvec = (i32)min((i64)AP_TILE, tab_vecs - r.vec0);
+    return r;
+}
+
+__global__ void __launch_bounds__(AP_TILE, 2) adam_pipe_kernel(UpdArgs a, int ntiles) {
     typedef float4 V;
     extern __shared__ __align__(128) unsigned char adam_sm[];
-    __shared__ __align__(8) unsigned long long bar;
-    if ((i32)blockIdx.x >= a.work_blocks) { pdl_launch_dependents(); pdl_wait(); loss_block(a); return; }
-    V *sx = reinterpret_cast<V *>(adam_sm), *smm = sx + ADAM_TILE_V, *sv = smm + ADAM_TILE_V;
-    int t = 0;
-    while ((i32)blockIdx.x >= a.tab[t].blk_end) t++;
-    const DenseTab &T = a.tab[t];
-    const i64 tab_vecs = T.vec_end - (t ? a.tab[t - 1].vec_end : 0);
-    const i64 vec0 = (i64)((i32)blockIdx.x - (t ? a.tab[t - 1].blk_end : 0)) * ADAM_TILE_V;
-    const i32 nvec = (i32)min((i64)ADAM_TILE_V, tab_vecs - vec0);
-    const unsigned bytes = (unsigned)nvec * 16u;
-    float *gx = T.x + vec0 * 4, *gm = T.m + vec0 * 4, *gv = T.v + vec0 * 4;
-    if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_smem(&bar)));
+    ApStage *st = reinterpret_cast<ApStage *>(adam_sm);
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(st + AP_STAGES);
+    const int G = a.work_blocks, tid = threadIdx.x;
+    if ((int)blockIdx.x >= G) { pdl_launch_dependents(); pdl_wait(); loss_block(a); return; }
+    const int my_n = (ntiles - (int)blockIdx.x + G - 1) / G;         // this CTA's tiles: blockIdx.x + j * G
+    if (tid == 0) {
+        for (int s = 0; s < AP_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_smem(full + s)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a_smem(&bar)), "r"(3u * bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_smem(sx)), "l"(gx), "r"(bytes), "r"(a_smem(&bar)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_smem(smm)), "l"(gm), "r"(bytes), "r"(a_smem(&bar)) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_smem(sv)), "l"(gv), "r"(bytes), "r"(a_smem(&bar)) : "memory");
     }
+    __syncthreads();
+    auto issue = [&](int j) {                              // thread 0: request tile j's slices into stage j % AP_STAGES
+        const ApTile ti = ap_tile(a, (int)blockIdx.x + j * G);
+        const DenseTab &T = a.tab[ti.t];
+        ApStage *sg = st + (j % AP_STAGES);
+        const unsigned bar = a_smem(full + (j % AP_STAGES)), bytes = (unsigned)ti.nvec * 16u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(3u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_smem(sg->x)), "l"(T.x + ti.vec0 * 4), "r"(bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_smem(sg->m)), "l"(T.m + ti.vec0 * 4), "r"(bytes), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(a_smem(sg->v)), "l"(T.v + ti.vec0 * 4), "r"(bytes), "r"(bar) : "memory");
+    };
+    if (tid == 0) for (int j = 0; j < min(AP_STAGES, my_n); j++) issue(j);
     pdl_launch_dependents();                               // next step's grad kernel may prefetch its batch ids
-    const unsigned vpr = (unsigned)T.D / 4u;               // vectors per row
-    const float *gbase = T.grad + T.part * T.D;
-    const i32 cols = T.cols, soff = T.slot_off;
-    int4 seg[ADAM_TU];
-    i32 col[ADAM_TU];
-#pragma unroll
-    for (int u = 0; u < ADAM_TU; u++) {
-        const i32 l = u * 256 + threadIdx.x;
-        seg[u] = make_int4(-1, 0, 0, 0);
-        col[u] = 0;
-        if (l < nvec) {
-            const unsigned lv = (unsigned)(vec0 + l);
-            const unsigned row = lv / vpr;
-            col[u] = (i32)((lv - row * vpr) * 4u);
-            seg[u] = __ldg(a.rowhead + T.key_off + row);
-        }
-    }
-    pdl_wait();                                            // gradient rows of this step are complete from here on
-    V g0[ADAM_TU], g1[ADAM_TU];
-#pragma unroll
-    for (int u = 0; u < ADAM_TU; u++) {                     // the first two contributions come straight from the row map
-        g0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        g1[u] = g0[u];
-        if (seg[u].x >= 0) {
-            g0[u] = __ldg(reinterpret_cast<const V *>(gbase + col[u] + (i64)(seg[u].z - soff) * cols));
-            if (seg[u].y - seg[u].x > 1) g1[u] = __ldg(reinterpret_cast<const V *>(gbase + col[u] + (i64)(seg[u].w - soff) * cols));
-        }
-    }
-    __syncthreads();                                       // barrier initialisation visible to every waiter
-    {
-        unsigned done = 0;
-        while (!done)
-            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(a_smem(&bar)), "r"(0u) : "memory");
-    }
-    const float b1 = a.hp.beta1, b2 = a.hp.beta2, lr = a.hp.lr, eps = a.hp.eps;
-#pragma unroll
-    for (int u = 0; u < ADAM_TU; u++) {
-        const i32 l = u * 256 + threadIdx.x;
-        if (l >= nvec) continue;
-        float g[4] = {0.f, 0.f, 0.f, 0.f};
-        if (seg[u].x >= 0) {
-            const i32 sx_ = seg[u].x, sy = seg[u].y, cnt = sy - sx_;
-            const float *gb = gbase + col[u];
-            const bool long_seg = a.hub && cnt > PCH && (sx_ + PCH - 1) / PCH < sy / PCH;
-            auto add = [&](const V &w) { g[0] += w.x; g[1] += w.y; g[2] += w.z; g[3] += w.w; };
-            auto add_raw = [&](i32 lo, i32 hi) {
-                for (i32 j = lo; j < hi; j++) add(__ldg(reinterpret_cast<const V *>(gb + (i64)(__ldg(a.perm + j) - soff) * cols)));
-            };
-            if (!long_seg) {
-                add(g0[u]);
-                if (cnt > 1) add(g1[u]);
-                add_raw(sx_ + 2, sy);
-            } else {                                       // hub row: fringe rows + pre-reduced interior blocks, ascending order
-                const i32 bb0 = (sx_ + PCH - 1) / PCH, bb1 = sy / PCH;
-                const float *pb = a.partial + T.part * T.D + col[u];
-                add_raw(sx_, bb0 * PCH);
-                for (i32 bb = bb0; bb < bb1; bb++) add(__ldg(reinterpret_cast<const V *>(pb + (i64)bb * a.pcols)));
-                add_raw(bb1 * PCH, sy);
+
+    // per-thread view of a tile: its vector's row-map entry, gradient base and column
+    struct View { int4 seg; const float *gb; i32 cols, soff, pcol; bool live; };
+    auto view = [&](int j) {
+        View w;
+        w.seg = make_int4(-1, 0, 0, 0); w.gb = nullptr; w.cols = 0; w.soff = 0; w.pcol = 0; w.live = false;
+        if (j < my_n) {
+            const ApTile ti = ap_tile(a, (int)blockIdx.x + j * G);
+            if (tid < ti.nvec) {
+                const DenseTab &T = a.tab[ti.t];
+                const unsigned lv = (unsigned)(ti.vec0 + tid), vpr = (unsigned)T.D / 4u, row = lv / vpr;
+                w.pcol = T.part * T.D + (i32)((lv - row * vpr) * 4u);
+                w.gb = T.grad + w.pcol; w.cols = T.cols; w.soff = T.slot_off; w.live = true;
+                w.seg = __ldg(a.rowhead + T.key_off + row);
             }
         }
-        V xv = sx[l], mv = smm[l], vv = sv[l];
-        float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const float mq = ms[q] * b1 + g[q] * (1.f - b1);
-            const float vq = vs[q] * b2 + (g[q] * g[q]) * (1.f - b2);
-            ms[q] = mq; vs[q] = vq;
-            xs[q] -= lr * mq / (sqrtf(vq) + eps);
+        return w;
+    };
+    auto first_two = [&](const View &w, V &g0, V &g1) {    // the first two contributions come straight from the row map
+        g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        g1 = g0;
+        if (w.seg.x >= 0) {
+            g0 = __ldg(reinterpret_cast<const V *>(w.gb + (i64)(w.seg.z - w.soff) * w.cols));
+            if (w.seg.y - w.seg.x > 1) g1 = __ldg(reinterpret_cast<const V *>(w.gb + (i64)(w.seg.w - w.soff) * w.cols));
         }
-        sx[l] = xv; smm[l] = mv; sv[l] = vv;
+    };
+    View cur = view(0), nxt = view(1);
+    pdl_wait();                                            // gradient rows of this step are complete from here on
+    V g0, g1;
+    first_two(cur, g0, g1);
+    const float b1 = a.hp.beta1, b2 = a.hp.beta2, lr = a.hp.lr, eps = a.hp.eps;
+    for (int j = 0; j < my_n; j++) {
+        View nn = view(j + 2);
+        V h0, h1;
+        first_two(nxt, h0, h1);
+        if (tid == 0 && j >= 1 && j + AP_STAGES - 1 < my_n) {
+            // stage (j-1) % AP_STAGES was handed to the copy engine at the end of the previous iteration: once the engine
+            // has read it, tile j + AP_STAGES - 1 can land there
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            issue(j + AP_STAGES - 1);
+        }
+        {
+            const unsigned bar = a_smem(full + (j % AP_STAGES)), parity = (unsigned)(j / AP_STAGES) & 1u;
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        }
+        ApStage *sg = st + (j % AP_STAGES);
+        if (cur.live) {
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (cur.seg.x >= 0) {
+                const i32 sx_ = cur.seg.x, sy = cur.seg.y, cnt = sy - sx_;
+                const bool long_seg = a.hub && cnt > PCH && (sx_ + PCH - 1) / PCH < sy / PCH;
+                auto add = [&](const V &w) { g[0] += w.x; g[1] += w.y; g[2] += w.z; g[3] += w.w; };
+                auto add_raw = [&](i32 lo, i32 hi) {
+                    for (i32 q = lo; q < hi; q++) add(__ldg(reinterpret_cast<const V *>(cur.gb + (i64)(__ldg(a.perm + q) - cur.soff) * cur.cols)));
+                };
+                if (!long_seg) {
+                    add(g0);
+                    if (cnt > 1) add(g1);
+                    add_raw(sx_ + 2, sy);
+                } else {                                   // hub row: fringe rows + pre-reduced interior blocks, ascending order
+                    const i32 bb0 = (sx_ + PCH - 1) / PCH, bb1 = sy / PCH;
+                    const float *pb = a.partial + cur.pcol;
+                    add_raw(sx_, bb0 * PCH);
+                    for (i32 bb = bb0; bb < bb1; bb++) add(__ldg(reinterpret_cast<const V *>(pb + (i64)bb * a.pcols)));
+                    add_raw(bb1 * PCH, sy);
+                }
+            }
+            V xv = sg->x[tid], mv = sg->m[tid], vv = sg->v[tid];
+            float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float mq = ms[q] * b1 + g[q] * (1.f - b1);
+                const float vq = vs[q] * b2 + (g[q] * g[q]) * (1.f - b2);
+                ms[q] = mq; vs[q] = vq;
+                xs[q] -= lr * mq / (sqrtf(vq) + eps);
+            }
+            sg->x[tid] = xv; sg->m[tid] = mv; sg->v[tid] = vv;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the copy engine
+        __syncthreads();
+        if (tid == 0) {
+            const ApTile ti = ap_tile(a, (int)blockIdx.x + j * G);
+            const DenseTab &T = a.tab[ti.t];
+            const unsigned bytes = (unsigned)ti.nvec * 16u;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(T.x + ti.vec0 * 4), "r"(a_smem(sg->x)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(T.m + ti.vec0 * 4), "r"(a_smem(sg->m)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(T.v + ti.vec0 * 4), "r"(a_smem(sg->v)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        cur = nxt; nxt = nn; g0 = h0; g1 = h1;
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the bulk-copy engine
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gx), "r"(a_smem(sx)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gm), "r"(a_smem(smm)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gv), "r"(a_smem(sv)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // rowhead[c][key] = {first, end, slot0, slot1}: range (within step c) of the sorted entries of table row
@@ -1084,6 +1188,7 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
         i64 acc = 0;
         i32 blk = 0;
+        bool lean = !c->adam_legacy;
         auto add = [&](float *x, float *mm, float *vv, i64 nrows, int D, bool is_ent, int part) {
             if (!x) return;
             acc += nrows * D / vw;
@@ -1092,6 +1197,14 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
             T.x = x; T.m = mm; T.v = vv; T.grad = is_ent ? gent : grel; T.vec_end = acc; T.D = D;
             T.key_off = is_ent ? 0 : (i32)c->E; T.cols = is_ent ? a.ce : a.cr; T.part = part;
             T.slot_off = is_ent ? 0 : (i32)c->plan_ne; T.blk_end = blk;
+            {   // row = vector / vpr for vector < 2^31: multiply-high by ceil(2^(32+s) / vpr), s = floor(log2 vpr)
+                const unsigned vpr = (unsigned)(D / vw);
+                unsigned sh = 0;
+                while ((2u << sh) <= vpr) sh++;
+                if ((1u << sh) == vpr) { T.magic = 0; T.shift = sh; }
+                else { T.magic = (unsigned)((((unsigned long long)1 << (32 + sh)) + vpr - 1) / vpr); T.shift = sh; }
+                if (nrows * D / vw >= 0x7fffffffLL) lean = false;
+            }
             a.tab[a.ntab++] = T;
         };
         add(m->ent, m->m_ent, m->v_ent, c->E, m->ent_dim, true, 0);
@@ -1111,13 +1224,19 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
-        if (vw == 4 && c->adam_tma) {                      // TMA-staged tiles (opt-in: measured 17.3 vs 16.8 us on the bench workload)
+        if (vw == 4 && c->adam_tma) {                      // pipelined TMA ring (see adam_pipe_kernel)
             static bool attr = false;
-            const size_t smem = (size_t)3 * ADAM_TILE_V * 16;
-            if (!attr) { OKB_CUDA(c, cudaFuncSetAttribute(adam_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            a.work_blocks = blk;
+            const size_t smem = sizeof(ApStage) * AP_STAGES + 8 * AP_STAGES;
+            if (!attr) { OKB_CUDA(c, cudaFuncSetAttribute(adam_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+            a.work_blocks = std::min<i32>(blk, 148 * 2);
             cfg.gridDim = dim3((unsigned)(a.work_blocks + a.loss_blocks)); cfg.dynamicSmemBytes = smem;
-            OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tma_kernel, a));
+            OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_pipe_kernel, a, (int)blk));
+        } else if (lean) {                                 // one tile per CTA, block-uniform table (adam_tile_kernel)
+            a.work_blocks = blk;
+            cfg.gridDim = dim3((unsigned)(a.work_blocks + a.loss_blocks));
+            if (vw == 4) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<4>, a));
+            else if (vw == 2) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<2>, a));
+            else OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<1>, a));
         } else if (vw == 4) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_kernel<4>, a));
         else if (vw == 2) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_kernel<2>, a));
         else OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_kernel<1>, a));
