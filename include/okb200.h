@@ -234,6 +234,10 @@ int okb_tc_batch(okb_ctx *c, int which /*0 test, 1 valid*/, INT *ph, INT *pt, IN
 int okb_best_threshold(okb_ctx *c, REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg);
 int okb_tc_eval(okb_ctx *c, const REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg,
                 INT *tp_tn_fp_fn, REAL *acc);
+/* accuracy of rel_thresh on the VALID triples (the early-stopping check of distribute_training.py:299-316; see the
+ * note in csrc/loader.cpp about the reference's use of the test ranges there) */
+int okb_tc_eval_valid(okb_ctx *c, const REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg,
+                      INT *tp_tn_fp_fn, REAL *acc);
 int okb_test_list(okb_ctx *c, int which, INT *h, INT *t, INT *r);
 INT okb_n_interval(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg);            /* Test.h:390-407 */
 INT *okb_tpfp(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg, const REAL *score_pos_test,

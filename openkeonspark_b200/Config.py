@@ -80,6 +80,11 @@ class Config(object):
         self._world = None            # parallel.DataParallel when running under torch.distributed
         self.transr_tensor_cores = False   # TransR ranking: project candidates with tcgen05 (3xTF32) instead of canonical fp32
         self.plan_ahead = 64          # steps sampled + planned per launch chunk (integer work, parameter-independent)
+        # early stopping (main_spark.py --early_stop_patience / --early_stop_start_step / --early_stop_stopping_step)
+        self.early_stop_patience = 0  # 0 = off
+        self.early_stop_start_step = 0        # epochs before the first check
+        self.early_stop_stopping_step = 1     # epochs between checks
+        self.early_stop = None        # after run(): {"reason", "best_step", "best_acc", "best_loss", "checks"} or None
         self._chunk_pos = self._chunk_len = 0
 
     # ------------------------------------------------------------------ init (Config.py:74-186)
@@ -259,6 +264,15 @@ class Config(object):
     def set_test_head(self, flag):
         self.test_head = int(flag)
 
+    def set_early_stopping(self, patience, start_step=0, stopping_step=1):
+        """Early stopping as in distribute_training.py:253-360: from epoch `start_step` on, every `stopping_step`
+        epochs, fit the per-relation thresholds on the valid triples, measure their accuracy and look at the last
+        batch loss; stop when either has not improved `patience` checks in a row and restore the best model
+        (main_spark.py:347-376).  Needs set_valid_triple_classification(True) before init()."""
+        self.early_stop_patience = int(patience)
+        self.early_stop_start_step = int(start_step)
+        self.early_stop_stopping_step = max(1, int(stopping_step))
+
     # ------------------------------------------------------------------ sampling (Config.py:343-347)
     def sampling(self):
         """One reference sampling() call on the GPU; results land in batch_h/t/r/y like the reference's."""
@@ -315,8 +329,13 @@ class Config(object):
     def set_parameters_by_name(self, var_name, tensor):
         if var_name in self.trainModel.parameter_lists:
             dst = self.trainModel.parameter_lists[var_name]
-            src = torch.as_tensor(np.asarray(tensor, dtype=np.float32)).reshape(dst.shape)
-            dst.copy_(src)
+            src = torch.as_tensor(np.asarray(tensor, dtype=np.float32))
+            if src.dim() == 2 and src.shape[1] == dst.shape[1] and src.shape[0] < dst.shape[0] and var_name in ("ent_embeddings", "ent_transfer"):
+                # a model trained before new entities arrived: its rows land in the leading rows, the new entities keep
+                # their fresh Xavier-normal rows (main_spark.py:71-75: scatter_update into a tensor of the final shape)
+                dst[:src.shape[0]].copy_(src)
+            else:
+                dst.copy_(src.reshape(dst.shape))
 
     def set_parameters(self, lists):
         for i in lists:
@@ -325,7 +344,7 @@ class Config(object):
     def save_tensorflow(self):
         """Reference: Saver.save (Config.py:350-356).  Here: a torch checkpoint of tables + optimizer state."""
         state = {"params": {k: v.cpu() for k, v in self.trainModel.parameter_lists.items()}, "step": self._step,
-                 "adam": None if self._adam is None else {k: v.cpu() if torch.is_tensor(v) else v for k, v in self._adam.items()}}
+                 "adam": None if self._adam is None else {k: v.cpu() if torch.is_tensor(v) else float(v) for k, v in self._adam.items()}}
         torch.save(state, self.exportName)
 
     def restore_tensorflow(self):
@@ -335,9 +354,13 @@ class Config(object):
         if state.get("adam") is not None and self._adam is not None:
             for k, v in state["adam"].items():
                 if torch.is_tensor(v):
-                    self._adam[k].copy_(v)
+                    if v.shape[0] < self._adam[k].shape[0]:       # grown entity table: new rows keep zero slots (main_spark.py:77-81)
+                        self._adam[k].zero_()
+                        self._adam[k][:v.shape[0]].copy_(v)
+                    else:
+                        self._adam[k].copy_(v)
                 else:
-                    self._adam[k] = v
+                    self._adam[k] = np.float32(v)     # beta powers are fp32 running products (tf.train.AdamOptimizer)
 
     # ------------------------------------------------------------------ model (Config.py:425-461)
     def set_model(self, model):
@@ -455,28 +478,140 @@ class Config(object):
         self._chunk_pos = self._chunk_len = 0
         return float(self.train_step_device(0).item())
 
+    def _snapshot(self):
+        """Device-side copy of everything a reference checkpoint holds: tables, Adam slots, beta powers, step."""
+        snap = {"params": {k: v.clone() for k, v in self.trainModel.parameter_lists.items()}, "step": self._step, "adam": None}
+        if self._adam is not None:
+            snap["adam"] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self._adam.items()}
+        return snap
+
+    def _restore_snapshot(self, snap):
+        for k, v in snap["params"].items():
+            self.trainModel.parameter_lists[k].copy_(v)
+        if snap["adam"] is not None:
+            for k, v in snap["adam"].items():
+                if torch.is_tensor(v):
+                    self._adam[k].copy_(v)
+                else:
+                    self._adam[k] = v
+        self._step = snap["step"]
+
+    def valid_accuracy(self):
+        """Thresholds fitted on the valid triples + their accuracy there (the early-stop check).  The valid negatives
+        are generated once per run() like the reference's single getValidBatch call (distribute_training.py:262)."""
+        if getattr(self, "_valid_batch_ready", False) is False:
+            self.ctx.call("okb_tc_batch", 1, *[_vp(getattr(self, "valid_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")])
+            self._valid_batch_ready = True
+        res_pos = self.test_step(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
+        res_neg = self.test_step(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
+        self.ctx.call("okb_best_threshold", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg))
+        self.ctx.call("okb_tc_eval_valid", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg), None, _vp(self.acc_addr))
+        return float(self.acc[0])
+
     def run(self):
-        """The train loop of distribute_training.py:267-283: train_times x nbatches x [sampling, step]."""
+        """The train loop of distribute_training.py:267-283: train_times x nbatches x [sampling, step], with the
+        early-stop checks of :286-356 when set_early_stopping() was called."""
         self._ensure_model()
         losses = []
+        es = self.early_stop_patience > 0
+        self.early_stop = None
+        if es:
+            if not hasattr(self, "valid_pos_h"):
+                raise OkbError("early stopping needs set_valid_triple_classification(True) before init()")
+            self._valid_batch_ready = False
+            best_acc, best_loss = float(np.finfo("float32").min), float(np.finfo("float32").max)
+            wait_acc = wait_loss = 0
+            best_snap_acc = best_snap_loss = None
+            step0 = self._step
+            stopping = self.early_stop_stopping_step * self.nbatches
+            to_reach = self.early_stop_start_step * self.nbatches + step0
+            checks = []
+        stop = False
         for epoch in range(self.train_times):
             t0 = time.time()
             acc = torch.zeros(1, dtype=torch.float32, device=self._loss_dev.device)
             batch = 0
-            while batch < self.nbatches:
-                losses_dev = self.train_chunk_device(min(self.plan_ahead, self.nbatches - batch))
+            while batch < self.nbatches and not stop:
+                n = min(self.plan_ahead, self.nbatches - batch)
+                if es and self._step < to_reach:
+                    n = min(n, to_reach - self._step)  # a check falls right after step `to_reach`
+                losses_dev = self.train_chunk_device(n)
                 acc += losses_dev.sum()
                 batch += losses_dev.numel()
                 if self.log_every and (self._step // self.log_every != (self._step - losses_dev.numel()) // self.log_every):
                     print("Global step: {} Epoch: {} Batch: {} loss: {}".format(self._step, epoch, batch - 1, float(losses_dev[-1].item())))
+                g = self._step
+                if es and g >= to_reach and g < step0 + self.train_times * self.nbatches:
+                    while g >= to_reach:
+                        to_reach += stopping
+                    a, l = self.valid_accuracy(), float(losses_dev[-1].item())
+                    checks.append((g, a, l))
+                    if a > best_acc:                                   # distribute_training.py:319-327
+                        best_acc, wait_acc, best_snap_acc = a, 0, self._snapshot()
+                    elif wait_acc < self.early_stop_patience:
+                        wait_acc += 1
+                    if wait_acc >= self.early_stop_patience:
+                        print("Accuracy early stop. Accuracy has not been improved enough in {} times".format(self.early_stop_patience))
+                        self.early_stop = {"reason": "accuracy", "best_step": best_snap_acc["step"]}
+                        stop = True
+                        break
+                    if l < best_loss:                                  # :343-351
+                        best_loss, wait_loss, best_snap_loss = l, 0, self._snapshot()
+                    elif wait_loss < self.early_stop_patience:
+                        wait_loss += 1
+                    if wait_loss >= self.early_stop_patience:
+                        print("Loss early stop. Losses has not been improved enough in {} times".format(self.early_stop_patience))
+                        self.early_stop = {"reason": "loss", "best_step": best_snap_loss["step"]}
+                        stop = True
+                        break
             res = float(acc.item())
             losses.append(res)
             print("Epoch: {} loss: {} ({:.3f} s)".format(epoch, res, time.time() - t0))
+            if stop:
+                break
+        if es and self.early_stop is not None:
+            # main_spark.py:347-376 keeps the checkpoint nearest to the step written to stop.txt; checks fall on checkpoint
+            # steps (both are multiples of nbatches), so that is the snapshot taken when the best value was seen
+            self._restore_snapshot(best_snap_acc if self.early_stop["reason"] == "accuracy" else best_snap_loss)
+            self.early_stop.update(best_acc=best_acc, best_loss=best_loss, checks=checks)
+            if self.out_path is not None:
+                import os as _os
+                with open(_os.path.join(_os.path.dirname(self.out_path) or ".", "stop.txt"), "w") as f:
+                    f.write(str(self.early_stop["best_step"]) + "\n")
+        elif es:
+            self.early_stop = {"reason": None, "best_step": None, "best_acc": best_acc, "best_loss": best_loss, "checks": checks}
         if self.exportName is not None:
             self.save_tensorflow()
         if self.out_path is not None:
             self.save_parameters(self.out_path)
         return losses
+
+    def grow_entities(self, n_new, seed=None):
+        """New entities arrived with an incremental batch (main_spark.py:29-96 update_entities_and_model): the entity
+        tables get `n_new` more rows drawn like a fresh Xavier-normal table of the FINAL shape, their Adam slots get
+        zero rows, everything else is kept.  Call before init() re-imports the grown dataset or right after it."""
+        self._ensure_model()
+        if n_new <= 0:
+            return self.trainModel.parameter_lists["ent_embeddings"].shape[0]
+        import math
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(int(self.seed if seed is None else seed) + 7919)
+        P = self.trainModel.parameter_lists
+        for name in ("ent_embeddings", "ent_transfer"):
+            if name not in P:
+                continue
+            old = P[name]
+            rows, cols = old.shape[0] + n_new, old.shape[1]
+            std = math.sqrt(1.3 * 2.0 / (rows + cols))
+            fresh = torch.empty(n_new, cols, dtype=torch.float32)
+            torch.nn.init.trunc_normal_(fresh, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=gen)
+            P[name] = torch.cat([old, fresh.to(old.device)], 0).contiguous()
+            if self._adam is not None:
+                for pre in ("m_", "v_"):
+                    a = self._adam[pre + name]
+                    self._adam[pre + name] = torch.cat([a, torch.zeros(n_new, cols, dtype=a.dtype, device=a.device)], 0).contiguous()
+        self._model_struct = None
+        return P["ent_embeddings"].shape[0]
 
     train = run
 

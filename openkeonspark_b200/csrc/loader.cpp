@@ -526,6 +526,24 @@ int okb_tc_eval(okb_ctx *c, const REAL *thresh, const REAL *pos, const REAL *neg
     if (acc) acc[0] = 1.0 * (TP + TN) / (TP + TN + FP + FN);
     return 0;
 }
+// Accuracy of the thresholds on the VALID triples (early stopping, distribute_training.py:299-316).  The reference calls
+// test_triple_classification with the valid scores there, i.e. it indexes arrays of validTotal scores with the TEST
+// ranges (Test.h:355-366) — an out-of-bounds read whenever testTotal > validTotal.  The evident intent, accuracy over
+// the valid set with the thresholds just fitted on it, is what this entry point computes.
+int okb_tc_eval_valid(okb_ctx *c, const REAL *thresh, const REAL *pos, const REAL *neg, INT *cnt, REAL *acc) {
+    if (c->valid_lef.empty()) OKB_FAIL(c, OKB_ERR_STATE, "import test files first");
+    i64 TP = 0, TN = 0, FP = 0, FN = 0;
+    for (i64 r = 0; r < c->R; r++) {
+        if (c->valid_lef[r] == -1) continue;
+        for (i64 i = c->valid_lef[r]; i <= c->valid_rig[r]; i++) {
+            if (pos[i] <= thresh[r]) TP++; else FN++;
+            if (neg[i] > thresh[r]) TN++; else FP++;
+        }
+    }
+    if (cnt) { cnt[0] = TP; cnt[1] = TN; cnt[2] = FP; cnt[3] = FN; }
+    if (acc) acc[0] = (TP + TN + FP + FN) ? 1.0 * (TP + TN) / (TP + TN + FP + FN) : 0.f;
+    return 0;
+}
 
 // ---------------------------------------------------------------- ROC helpers (Test.h:391-444)
 INT okb_n_interval(okb_ctx *c, INT r, const REAL *pos, const REAL *neg) {
