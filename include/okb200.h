@@ -258,7 +258,9 @@ enum { OKB_FLAG_TRANSR_TC = 1,
         * workload: grad +2.1 us, update -1.5 us. */
        OKB_FLAG_L2_PREFETCH = 4,
        /* OKB_FLAG_ADAM_LEGACY = 5 (default off): the first, grid-stride form of the dense Adam pass (A/B runs). */
-       OKB_FLAG_ADAM_LEGACY = 5 };
+       OKB_FLAG_ADAM_LEGACY = 5,
+       /* OKB_FLAG_GRAD_GENERIC = 6 (default off): use the generic grad kernel even for the k = 1, kr = 0 batch (A/B runs). */
+       OKB_FLAG_GRAD_GENERIC = 6 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:

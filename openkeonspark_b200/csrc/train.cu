@@ -480,6 +480,222 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     if (lane == 0) a.loss_terms[b - a.slot_base] = hinge_sum;
 }
 
+// ------------------------------------------------------------------------------------------ grad, k = 1 specialisation
+// The generic kernel walks 16 dependent shuffle-reduction chains per positive (norms, projections, scores, the
+// backward dots of the negative and then of the positive): with 5 warps per scheduler the issue slots idle while
+// every warp sits in a chain (ncu: issue-active 50 %, short-scoreboard + wait stalls dominate).  With one entity
+// negative and no relation negative — the reference's default batch (Config.py:58-59) — the positive and its negative
+// are independent until the hinge, so their reductions are interleaved: 7 chains of 2–6 values each.  Same
+// operations, same per-value reduction tree, same accumulation order (negative first, then the positive) as the
+// generic kernel.
+#ifndef GRAD1_MIN_BLOCKS
+#define GRAD1_MIN_BLOCKS 16
+#endif
+template <int K> __device__ __forceinline__ void wsumk(float (&v)[K]) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < K; i++) v[i] += __shfl_xor_sync(FULL, v[i], o);
+    }
+}
+template <int MODEL, int N>
+__device__ __forceinline__ void ent_select(EntS<MODEL, N> &D, bool take, const EntS<MODEL, N> &A, const EntS<MODEL, N> &B) {
+#pragma unroll
+    FOR_N { D.raw[i] = take ? A.raw[i] : B.raw[i]; D.hat[i] = take ? A.hat[i] : B.hat[i]; }
+    if (MODEL == OKB_TRANSD) {
+#pragma unroll
+        FOR_N D.aux[i] = take ? A.aux[i] : B.aux[i];
+    }
+    D.inv = take ? A.inv : B.inv; D.a = take ? A.a : B.a; D.proj = take ? A.proj : B.proj;
+}
+
+template <int MODEL, int VW, int NV>
+__global__ void __launch_bounds__(32, GRAD1_MIN_BLOCKS) grad_k1_kernel(GradArgs a) {
+    constexpr int N = VW * NV;
+    const int lane = threadIdx.x & 31;
+    const i32 b = a.b_lo + blockIdx.x;
+    if (b >= a.b_hi) return;
+    if (a.wait_flags) {                                    // owner-sharded data parallelism: see grad_kernel
+        if (lane < a.wait_n) {
+            if (blockIdx.x == 0)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
+            unsigned long long v;
+            do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + lane) : "memory"); } while (v < a.wait_epoch);
+        }
+        __syncwarp();
+    }
+    const int D = a.m.ent_dim;
+    const int ce = MODEL == OKB_TRANSD ? 2 * D : D, cr = MODEL == OKB_TRANSE ? D : 2 * D;
+    const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
+    const i32 nh = a.bh[b + a.B], nt = a.bt[b + a.B];
+    pdl_wait();
+    pdl_launch_dependents();
+    const bool head_rep = nh != ph, tail_rep = !head_rep && nt != pt;
+
+    RelS<MODEL, N> R;
+    EntS<MODEL, N> H, T, X;                                // X: the entity that replaces a side in the negative
+    rel_load<MODEL, VW, NV>(R, a.m, pr, lane);
+    ent_load<MODEL, VW, NV>(H, a.m, ph, lane);
+    ent_load<MODEL, VW, NV>(T, a.m, pt, lane);
+    ent_load<MODEL, VW, NV>(X, a.m, head_rep ? nh : nt, lane);
+
+    // ---- relation: both norms in one chain
+    {
+        float s[2] = {dot<N>(R.rhat, R.rhat), MODEL == OKB_TRANSH ? dot<N>(R.aux, R.aux) : 0.f};
+        if (MODEL == OKB_TRANSH) wsumk<2>(s); else s[0] = wsum(s[0]);
+        R.proj = s[0] > EPS_NORM;
+        R.inv = rsqrtf(fmaxf(s[0], EPS_NORM));
+#pragma unroll
+        FOR_N R.rhat[i] = R.rhat[i] * R.inv;
+        if (MODEL == OKB_TRANSH) {
+            R.proj_n = s[1] > EPS_NORM;
+            R.inv_n = rsqrtf(fmaxf(s[1], EPS_NORM));
+#pragma unroll
+            FOR_N R.aux[i] = R.aux[i] * R.inv_n;
+        }
+    }
+    // ---- entities: the three projection dots in one chain, the three norms in the next
+    float pH[N], pT[N], pX[N];
+    if (MODEL == OKB_TRANSE) {
+#pragma unroll
+        FOR_N { pH[i] = H.raw[i]; pT[i] = T.raw[i]; pX[i] = X.raw[i]; }
+        H.a = T.a = X.a = 0.f;
+    } else {
+        float av[3];
+        if (MODEL == OKB_TRANSH) { av[0] = dot<N>(H.raw, R.aux); av[1] = dot<N>(T.raw, R.aux); av[2] = dot<N>(X.raw, R.aux); }
+        else { av[0] = dot<N>(H.raw, H.aux); av[1] = dot<N>(T.raw, T.aux); av[2] = dot<N>(X.raw, X.aux); }
+        wsumk<3>(av);
+        H.a = av[0]; T.a = av[1]; X.a = av[2];
+        if (MODEL == OKB_TRANSH) {
+#pragma unroll
+            FOR_N { pH[i] = H.raw[i] - H.a * R.aux[i]; pT[i] = T.raw[i] - T.a * R.aux[i]; pX[i] = X.raw[i] - X.a * R.aux[i]; }
+        } else {
+#pragma unroll
+            FOR_N { pH[i] = H.raw[i] + H.a * R.aux[i]; pT[i] = T.raw[i] + T.a * R.aux[i]; pX[i] = X.raw[i] + X.a * R.aux[i]; }
+        }
+    }
+    {
+        float sv[3] = {dot<N>(pH, pH), dot<N>(pT, pT), dot<N>(pX, pX)};
+        wsumk<3>(sv);
+        H.proj = sv[0] > EPS_NORM; H.inv = rsqrtf(fmaxf(sv[0], EPS_NORM));
+        T.proj = sv[1] > EPS_NORM; T.inv = rsqrtf(fmaxf(sv[1], EPS_NORM));
+        X.proj = sv[2] > EPS_NORM; X.inv = rsqrtf(fmaxf(sv[2], EPS_NORM));
+#pragma unroll
+        FOR_N { H.hat[i] = pH[i] * H.inv; T.hat[i] = pT[i] * T.inv; X.hat[i] = pX[i] * X.inv; }
+    }
+    // ---- the negative triple (Hn, Tn, r): the replaced side comes from X, a degenerate negative is the positive itself
+    EntS<MODEL, N> Hn, Tn;
+    ent_select<MODEL, N>(Hn, head_rep, X, H);
+    ent_select<MODEL, N>(Tn, tail_rep, X, T);
+    float gp[N], gn[N];
+    float sc[2] = {0.f, 0.f};
+#pragma unroll
+    FOR_N {
+        const float up = (H.hat[i] + R.rhat[i]) - T.hat[i], un = (Hn.hat[i] + R.rhat[i]) - Tn.hat[i];
+        sc[0] += fabsf(up); sc[1] += fabsf(un);
+        gp[i] = up > 0.f ? 1.f : (up < 0.f ? -1.f : 0.f);
+        gn[i] = un > 0.f ? 1.f : (un < 0.f ? -1.f : 0.f);
+    }
+    wsumk<2>(sc);
+    const float x = sc[0] - sc[1] + a.margin;
+    const bool active = x >= 0.f;
+
+    EntG<MODEL, N> accH, accT, gnew;
+    RelG<MODEL, N> accR;
+    accH.zero(); accT.zero(); gnew.zero(); accR.zero();
+    if (active) {
+        const float w = a.w;
+        // through l2_normalize, negative and positive together: six dots in one chain
+        float d[6] = {dot<N>(gn, Hn.hat), dot<N>(gn, Tn.hat), dot<N>(gn, R.rhat), dot<N>(gp, H.hat), dot<N>(gp, T.hat), dot<N>(gp, R.rhat)};
+        wsumk<6>(d);
+        if (!Hn.proj) d[0] = 0.f;
+        if (!Tn.proj) d[1] = 0.f;
+        if (!H.proj) d[3] = 0.f;
+        if (!T.proj) d[4] = 0.f;
+        if (!R.proj) { d[2] = 0.f; d[5] = 0.f; }
+        float GHn[N], GTn[N], GHp[N], GTp[N];
+#pragma unroll
+        FOR_N {
+            GHn[i] = Hn.inv * (gn[i] - Hn.hat[i] * d[0]);
+            GTn[i] = -Tn.inv * (gn[i] - Tn.hat[i] * d[1]);
+            accR.d[i] += -w * (R.inv * (gn[i] - R.rhat[i] * d[2]));
+            GHp[i] = H.inv * (gp[i] - H.hat[i] * d[3]);
+            GTp[i] = -T.inv * (gp[i] - T.hat[i] * d[4]);
+            accR.d[i] += w * (R.inv * (gp[i] - R.rhat[i] * d[5]));
+        }
+        EntG<MODEL, N> dHn, dTn;                           // the negative's entity gradients, routed below
+        dHn.zero(); dTn.zero();
+        if (MODEL == OKB_TRANSE) {
+#pragma unroll
+            FOR_N { dHn.d[i] = -w * GHn[i]; dTn.d[i] = -w * GTn[i]; accH.d[i] = 0.f; }
+        } else {
+            float bb[4] = {dot<N>(GHn, R.aux), dot<N>(GTn, R.aux), dot<N>(GHp, R.aux), dot<N>(GTp, R.aux)};
+            wsumk<4>(bb);
+            if (MODEL == OKB_TRANSH) {
+                float dnn[N], dnp[N];
+#pragma unroll
+                FOR_N {
+                    dHn.d[i] = -w * (GHn[i] - R.aux[i] * bb[0]);
+                    dTn.d[i] = -w * (GTn[i] - R.aux[i] * bb[1]);
+                    dnn[i] = -(Hn.a * GHn[i] + bb[0] * Hn.raw[i] + Tn.a * GTn[i] + bb[1] * Tn.raw[i]);
+                    dnp[i] = -(H.a * GHp[i] + bb[2] * H.raw[i] + T.a * GTp[i] + bb[3] * T.raw[i]);
+                }
+                float d4[2] = {dot<N>(dnn, R.aux), dot<N>(dnp, R.aux)};
+                wsumk<2>(d4);
+                if (!R.proj_n) { d4[0] = 0.f; d4[1] = 0.f; }
+#pragma unroll
+                FOR_N {
+                    accR.da[i] += -w * (R.inv_n * (dnn[i] - R.aux[i] * d4[0]));
+                    accR.da[i] += w * (R.inv_n * (dnp[i] - R.aux[i] * d4[1]));
+                }
+            } else {
+#pragma unroll
+                FOR_N {
+                    dHn.d[i] = -w * (GHn[i] + bb[0] * Hn.aux[i]);
+                    dHn.da[i] = -w * (bb[0] * Hn.raw[i]);
+                    dTn.d[i] = -w * (GTn[i] + bb[1] * Tn.aux[i]);
+                    dTn.da[i] = -w * (bb[1] * Tn.raw[i]);
+                    accR.da[i] += -w * (Hn.a * GHn[i] + Tn.a * GTn[i]);
+                    accR.da[i] += w * (H.a * GHp[i] + T.a * GTp[i]);
+                }
+            }
+            // the positive's entity gradients use bb[2], bb[3] below
+            if (MODEL == OKB_TRANSH) {
+#pragma unroll
+                FOR_N { GHp[i] = GHp[i] - R.aux[i] * bb[2]; GTp[i] = GTp[i] - R.aux[i] * bb[3]; }
+            }
+            if (MODEL == OKB_TRANSD) {
+                // route the negative first (accumulation order of the generic kernel), then add the positive
+#pragma unroll
+                FOR_N {
+                    accH.d[i] = head_rep ? 0.f : dHn.d[i]; accH.da[i] = head_rep ? 0.f : dHn.da[i];
+                    accT.d[i] = tail_rep ? 0.f : dTn.d[i]; accT.da[i] = tail_rep ? 0.f : dTn.da[i];
+                    gnew.d[i] = head_rep ? dHn.d[i] : (tail_rep ? dTn.d[i] : 0.f);
+                    gnew.da[i] = head_rep ? dHn.da[i] : (tail_rep ? dTn.da[i] : 0.f);
+                    accH.d[i] += w * (GHp[i] + bb[2] * H.aux[i]); accH.da[i] += w * (bb[2] * H.raw[i]);
+                    accT.d[i] += w * (GTp[i] + bb[3] * T.aux[i]); accT.da[i] += w * (bb[3] * T.raw[i]);
+                }
+            }
+        }
+        if (MODEL != OKB_TRANSD) {
+#pragma unroll
+            FOR_N {
+                accH.d[i] = head_rep ? 0.f : dHn.d[i];
+                accT.d[i] = tail_rep ? 0.f : dTn.d[i];
+                gnew.d[i] = head_rep ? dHn.d[i] : (tail_rep ? dTn.d[i] : 0.f);
+                accH.d[i] += w * GHp[i];
+                accT.d[i] += w * GTp[i];
+            }
+        }
+    }
+    float *ge = a.gent + (i64)(b - a.slot_base) * a.NE * ce, *gr = a.grel + (i64)(b - a.slot_base) * a.NR * cr;
+    put_ent<MODEL, VW, NV>(ge, accH, D, lane);
+    put_ent<MODEL, VW, NV>(ge + ce, accT, D, lane);
+    put_ent<MODEL, VW, NV>(ge + 2 * (i64)ce, gnew, D, lane);
+    put_rel<MODEL, VW, NV>(gr, accR, D, lane);
+    if (lane == 0) a.loss_terms[b - a.slot_base] = active ? x : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------ update
 // one parameter table for the flat Adam pass; vec_end: cumulative vector count over the table list
 struct DenseTab { float *x, *m, *v; const float *grad; i64 vec_end; i32 D, key_off, cols, part, slot_off, blk_end;
@@ -1134,7 +1350,13 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV>, a);          \
     else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV>, a);     \
     else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV>, a)
-    { ProfScope ps(c, PROF_GRAD, s); DISPATCH_LAYOUT(vw, nv, CALL_GRAD); }
+#define CALL_GRAD1(VW, NV)                                                                             \
+    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSE, VW, NV>, a);       \
+    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSH, VW, NV>, a);  \
+    else cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSD, VW, NV>, a)
+    const bool k1 = c->K == 1 && c->KR == 0 && !c->grad_generic && a.npf == 0;
+    if (k1) { cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32); }
+    { ProfScope ps(c, PROF_GRAD, s); if (k1) { DISPATCH_LAYOUT(vw, nv, CALL_GRAD1); } else { DISPATCH_LAYOUT(vw, nv, CALL_GRAD); } }
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
     return 0;
