@@ -325,7 +325,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     S = con.batch_seq_size
     e2e = {"value": con.batch_size * e2e_steps / float(t.item()), "unit": "triples/s", "h2d_bytes_per_step": 3 * 8 * S,
-           "d2h_bytes_per_step": 3 * 8 * S + 4 * S + 4, "steps": e2e_steps}
+           "d2h_bytes_per_step": 3 * 8 * S + 4, "steps": e2e_steps}
 
     # ---------------- roofline of the dominant kernel
     # Algorithmic bytes per launch: Adam update = 6*4 B per table element (var, m, v read+write)

@@ -277,8 +277,12 @@ class Config(object):
     def sampling(self):
         """One reference sampling() call on the GPU; results land in batch_h/t/r/y like the reference's."""
         self.sampling_device()
+        # labels are the fixed pattern of Base.cpp:110,129,138 (+1 for the B positives, -1 for every negative plane):
+        # written here instead of crossing PCIe as a second copy
+        self.batch_y[:self.batch_size] = 1.0
+        self.batch_y[self.batch_size:] = -1.0
         self.ctx.call("okb_batch_to_host", 0, _vp(self.batch_h_addr), _vp(self.batch_t_addr), _vp(self.batch_r_addr),
-                      _vp(self.batch_y_addr), _stream())
+                      None, _stream())
 
     def sampling_device(self, steps=1):
         """Sample `steps` consecutive batches, leaving them resident in HBM (no host copy)."""

@@ -369,7 +369,8 @@ __global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
     float *refs = qt + (size_t)D * NQ;                     // [NQ] raw-sum thresholds
     i32 *tgt = (i32 *)(refs + NQ);                         // [NQ][2]
     int4 *runs = (int4 *)(tgt + 2 * NQ);                   // [NQ]
-    unsigned *cnt = (unsigned *)(runs + NQ);               // [NQ][2][4]
+    int2 *krange = (int2 *)(runs + NQ);                    // [NQ][2] known-true ids that fall inside this CTA's candidate tile
+    unsigned *cnt = (unsigned *)(krange + 2 * NQ);         // [NQ][2][4]
     unsigned long long *bst = (unsigned long long *)(cnt + NQ * 8);   // [NQ][2][4]
     unsigned long long *bar = bst + NQ * 8;
 
@@ -409,7 +410,30 @@ __global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
             tgt[2 * tid + 1] = ok ? a.tt[ti] : -1;
             runs[tid] = ok ? a.trun[ti] : make_int4(0, 0, 0, 0);
         }
-        for (int idx = tid; idx < NQ * 8; idx += CT * QG) { cnt[idx] = 0u; bst[idx] = ~0ull; }
+        if (tid < 2 * NQ) {
+            // known-true filter (Corrupt.h:104-115), hoisted: the sorted known list of a (query, side) is cut down ONCE
+            // per pass to the ids inside this tile [jlo, jlo + CT) — almost always 0 or 1 of them — so the per-candidate
+            // test below is a warp-uniform scan of that sub-range instead of a divergent binary search per candidate
+            const int ql = tid >> 1, side = tid & 1;
+            int2 kr = make_int2(0, 0);
+            if (qb + ql < qhi) {
+                const int4 rn = a.trun[a.q_lo + qb + ql];
+                const i32 *lst = side ? a.known_t : a.known_h;
+                const i32 beg = side ? rn.x : rn.z, end = side ? rn.y : rn.w, jlo = a.j0 + col0;
+                i32 lo = beg, hi = end;
+                while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (__ldg(lst + mid) < jlo) lo = mid + 1; else hi = mid; }
+                kr.x = lo; hi = end;
+                while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (__ldg(lst + mid) < jlo + CT) lo = mid + 1; else hi = mid; }
+                kr.y = lo;
+            }
+            krange[tid] = kr;
+        }
+        // argmins start from the best packed (score, id) any CTA has published so far: candidates that cannot beat it
+        // never enter the warp reductions below
+        for (int idx = tid; idx < NQ * 8; idx += CT * QG) {
+            cnt[idx] = 0u;
+            bst[idx] = (qb + (idx >> 3) < qhi) ? a.best[(i64)(qb + (idx >> 3)) * 8 + (idx & 7)] : ~0ull;
+        }
         __syncthreads();
         mbar_wait(bar, phase); phase ^= 1;
 
@@ -440,6 +464,7 @@ __global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
                     }
                 }
             }
+            const int lane = tid & 31;
 #pragma unroll
             for (int q = 0; q < QB; q++) {
                 const int ql = q0 + q;
@@ -448,25 +473,34 @@ __global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
 #pragma unroll
                 for (int side = HEADS ? 0 : 1; side < 2; side++) {
                     const float raw = side ? accT[q] : accH[q];
-                    if (qok && j != tgt[2 * ql + side] && raw < thr) {           // Test.h:59,62 / 168,171
-                        const float s = c_finish(a.model, raw, D);
-                        // known-true filter: is (j, t, r) / (h, j, r) in train+valid+test?  (Corrupt.h:104-115)
-                        const int4 rn = runs[ql];
-                        const i32 *lst = side ? a.known_t : a.known_h;
-                        const i32 end = side ? rn.y : rn.w;
-                        i32 lo = side ? rn.x : rn.z, hi = end;
-                        while (lo < hi) { const i32 mid = (lo + hi) >> 1; if (__ldg(lst + mid) < j) lo = mid + 1; else hi = mid; }
-                        const bool known = lo < end && __ldg(lst + lo) == j;
-                        const bool typed = (tf >> side) & 1u;
-                        const unsigned long long pk = ((unsigned long long)__float_as_uint(s) << 32) | (unsigned)j;
-                        unsigned *cq = cnt + (ql * 2 + side) * 4;
-                        unsigned long long *bq = bst + (ql * 2 + side) * 4;
-                        atomicAdd(cq + 0, 1u); atomicMin(bq + 0, pk);
-                        if (!known) { atomicAdd(cq + 1, 1u); atomicMin(bq + 1, pk); }
-                        if (typed) {
-                            atomicAdd(cq + 2, 1u); atomicMin(bq + 2, pk);
-                            if (!known) { atomicAdd(cq + 3, 1u); atomicMin(bq + 3, pk); }
-                        }
+                    const bool better = qok && j != tgt[2 * ql + side] && raw < thr;       // Test.h:59,62 / 168,171
+                    const unsigned mb = __ballot_sync(FULL, better);
+                    if (mb == 0u) continue;                                              // warp-uniform
+                    const int2 kr = krange[ql * 2 + side];
+                    const i32 *lst = side ? a.known_t : a.known_h;
+                    bool known = false;
+                    for (i32 i = kr.x; i < kr.y; i++) known |= __ldg(lst + i) == j;        // (j, t, r) / (h, j, r) in train+valid+test?
+                    const bool typed = (tf >> side) & 1u;
+                    const unsigned m1 = __ballot_sync(FULL, better && !known), m2 = __ballot_sync(FULL, better && typed),
+                                   m3 = __ballot_sync(FULL, better && typed && !known);
+                    unsigned *cq = cnt + (ql * 2 + side) * 4;
+                    unsigned long long *bq = bst + (ql * 2 + side) * 4;
+                    if (lane < 4) {
+                        const unsigned mm = lane == 0 ? mb : (lane == 1 ? m1 : (lane == 2 ? m2 : m3));
+                        if (mm) atomicAdd(cq + lane, (unsigned)__popc(mm));
+                    }
+                    // argmins: packed (finished score bits, id); scores are non-negative, so their bit patterns order like uints
+                    const float sfin = c_finish(a.model, raw, D);
+                    const unsigned long long pk = ((unsigned long long)__float_as_uint(sfin) << 32) | (unsigned)j;
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const bool in = v == 0 ? better : (v == 1 ? (better && !known) : (v == 2 ? (better && typed) : (better && typed && !known)));
+                        const bool cand = in && pk < bq[v];
+                        if (__ballot_sync(FULL, cand) == 0u) continue;
+                        const unsigned sb = cand ? __float_as_uint(sfin) : 0xffffffffu;
+                        const unsigned smin = __reduce_min_sync(FULL, sb);
+                        const unsigned idmin = __reduce_min_sync(FULL, (cand && sb == smin) ? (unsigned)j : 0xffffffffu);
+                        if (lane == 0) atomicMin(bq + v, ((unsigned long long)smin << 32) | idmin);
                     }
                 }
             }
@@ -477,7 +511,7 @@ __global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
             if (qb + q < qhi) {
                 const i64 o = (i64)(qb + q) * 8 + (idx & 7);
                 if (cnt[idx]) atomicAdd(a.counts + o, (unsigned long long)cnt[idx]);
-                if (bst[idx] != ~0ull) atomicMin(a.best + o, bst[idx]);
+                if (bst[idx] != ~0ull) atomicMin(a.best + o, bst[idx]);       // seeded from a.best: a no-op unless improved
             }
         }
     }
@@ -625,7 +659,8 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
     const int QGsel = avg_q >= 20 ? 4 : 2;
     const size_t NQ = (size_t)QGsel * QB;
     const size_t smem_rank = sizeof(float) * ((size_t)D * CT + ((D + 3) & ~3) + 2 * (size_t)D * NQ + NQ) + sizeof(i32) * 2 * NQ +
-                             sizeof(int4) * NQ + sizeof(unsigned) * NQ * 8 + sizeof(unsigned long long) * (NQ * 8 + 1) + 128;
+                             sizeof(int4) * NQ + sizeof(int2) * 2 * NQ + sizeof(unsigned) * NQ * 8 +
+                             sizeof(unsigned long long) * (NQ * 8 + 1) + 128;
     if (smem_rank > 227 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension too large for the ranking tile");
     static bool attr_done = false;
     if (!attr_done) {
