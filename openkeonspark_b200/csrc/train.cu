@@ -30,6 +30,22 @@
 // start while its predecessor drains; `wait` blocks until the predecessor grid has completed and flushed.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Spin until a peer's flag word reaches `epoch` (acquire, system scope).  A peer that died would otherwise hang this GPU
+// for good: after ~20 s without progress the kernel traps, which surfaces as a CUDA error in the host process.
+__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long epoch) {
+    unsigned long long v, t0 = 0;
+    unsigned polls = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= epoch) return;
+        if ((++polls & 0x3ffu) == 0u) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) __trap();
+        }
+    }
+}
 #define WARPS_PER_BLOCK 4
 #define PCH 8                  // long segments (> PCH rows) are pre-reduced in fixed chunks of PCH sorted positions
 // grad kernel: one warp per block so that residency is quantised in single warps: <= 120 registers
@@ -373,16 +389,6 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     const int lane = threadIdx.x & 31;
     const i32 b = a.b_lo + blockIdx.x * GRAD_WARPS + (threadIdx.x >> 5);
     if (b >= a.b_hi) return;
-    if (a.wait_flags) {                                    // peers still pushing updated rows of the previous step?
-        if (lane < a.wait_n) {
-            // this rank's previous owner-update kernel has completed (stream order): tell every peer, then wait for theirs
-            if (blockIdx.x == 0 && threadIdx.x < 32)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
-            unsigned long long v;
-            do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + lane) : "memory"); } while (v < a.wait_epoch);
-        }
-        __syncwarp();
-    }
     const int D = a.m.ent_dim;
     const int ce = MODEL == OKB_TRANSD ? 2 * D : D, cr = MODEL == OKB_TRANSE ? D : 2 * D;
     const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
@@ -393,6 +399,16 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     // kernel) are released only after the wait, so they can never start before the previous update has finished.
     pdl_wait();
     pdl_launch_dependents();
+    if (a.wait_flags) {                                    // owner-sharded data parallelism: peers still publishing rows?
+        if (lane < a.wait_n) {
+            // this rank's previous owner-update kernel has completed (griddepcontrol.wait above): tell every peer, then
+            // wait until every peer has said the same
+            if (blockIdx.x == 0 && threadIdx.x < 32)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
+            spin_until(a.wait_flags + lane, a.wait_epoch);
+        }
+        __syncwarp();
+    }
     if (lane < a.npf) {
         const unsigned off = (unsigned)(b - a.b_lo) * a.pf_slice[lane];
         if (off < a.pf_bytes[lane]) {
@@ -515,21 +531,20 @@ __global__ void __launch_bounds__(32, GRAD1_MIN_BLOCKS) grad_k1_kernel(GradArgs 
     const int lane = threadIdx.x & 31;
     const i32 b = a.b_lo + blockIdx.x;
     if (b >= a.b_hi) return;
-    if (a.wait_flags) {                                    // owner-sharded data parallelism: see grad_kernel
-        if (lane < a.wait_n) {
-            if (blockIdx.x == 0)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
-            unsigned long long v;
-            do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.wait_flags + lane) : "memory"); } while (v < a.wait_epoch);
-        }
-        __syncwarp();
-    }
     const int D = a.m.ent_dim;
     const int ce = MODEL == OKB_TRANSD ? 2 * D : D, cr = MODEL == OKB_TRANSE ? D : 2 * D;
     const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
     const i32 nh = a.bh[b + a.B], nt = a.bt[b + a.B];
     pdl_wait();
     pdl_launch_dependents();
+    if (a.wait_flags) {                                    // owner-sharded data parallelism: see grad_kernel
+        if (lane < a.wait_n) {
+            if (blockIdx.x == 0)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
+            spin_until(a.wait_flags + lane, a.wait_epoch);
+        }
+        __syncwarp();
+    }
     const bool head_rep = nh != ph, tail_rep = !head_rep && nt != pt;
 
     RelS<MODEL, N> R;
@@ -1551,8 +1566,7 @@ __device__ __forceinline__ void dp_announce_and_wait(char *const *arena, i64 off
                                                      unsigned long long epoch, bool announce) {
     if ((int)threadIdx.x < world) {
         if (announce) st_release_sys((unsigned long long *)(arena[threadIdx.x] + off_flags) + which + rank, epoch);
-        const unsigned long long *f = (const unsigned long long *)(arena[rank] + off_flags) + which + threadIdx.x;
-        while (ld_acquire_sys(f) < epoch) { }
+        spin_until((const unsigned long long *)(arena[rank] + off_flags) + which + threadIdx.x, epoch);
     }
     __syncthreads();
 }
@@ -1561,8 +1575,10 @@ template <int VW, int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) dp_reduce_push_kernel(UpdArgs a, DpPush d) {
     constexpr int N = VW * NV;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
     if ((i32)blockIdx.x >= a.work_blocks) {                // the extra block: this rank's hinge sum, in a fixed order
         __shared__ float sh[WARPS_PER_BLOCK];
+        pdl_wait();
         float x = 0.f;
         for (i32 i = threadIdx.x; i < d.Bl; i += WARPS_PER_BLOCK * 32) x += a.loss_terms[i];
         x = wsum(x);
@@ -1588,6 +1604,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) dp_reduce_push_kernel(Up
                          ((i64)d.rank * own_max + (row - lo[o])) * cols;
             const int4 seg = __ldg(a.rowhead + key);
             const int parts = cols / D;
+            pdl_wait();                                    // the grad kernel's rows are complete from here on
             for (int p = 0; p < parts; p++) {
                 Frag<VW, NV> f;
                 f.zero();
@@ -1617,6 +1634,8 @@ struct DpOwn {
 template <int VW>
 __global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
     typedef typename VecT<VW>::T V;
+    pdl_launch_dependents();
+    pdl_wait();                                            // this rank's reduce+push kernel is complete: announce it
     dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, blockIdx.x == 0);
     if (blockIdx.x == 0 && threadIdx.x == 0 && d.loss_out) {   // mean hinge over the GLOBAL batch, rank order
         const volatile float *lp = (const volatile float *)((unsigned long long *)(d.arena[d.rank] + d.off_flags) + DP_FLAG_LOSS);
@@ -1747,7 +1766,9 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     }
     if ((rc = ensure_rowhead(c, s))) return rc;
     const bool was_pdl = c->pdl;
-    c->pdl = false;                                        // kernels that spin on peer flags must not start early
+    cudaLaunchAttribute pat[1];
+    pat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pat[0].val.programmaticStreamSerializationAllowed = 1;
     const i64 own_e = (c->E + P.world - 1) / P.world, own_r = (c->R + P.world - 1) / P.world;
     for (INT i = 0; i < n; i++) {
         const INT step = step_lo + i;
@@ -1773,7 +1794,10 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         a.work_blocks = (i32)((a.key_limit + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         {
             ProfScope ps(c, PROF_UPDATE, s);
-#define CALL_PUSH(VW, NV) dp_reduce_push_kernel<VW, NV><<<a.work_blocks + 1, WARPS_PER_BLOCK * 32, 0, s>>>(a, d)
+            cudaLaunchConfig_t pc = {};
+            pc.gridDim = dim3((unsigned)(a.work_blocks + 1)); pc.blockDim = dim3(WARPS_PER_BLOCK * 32); pc.stream = s;
+            pc.attrs = pat; pc.numAttrs = c->pdl ? 1 : 0;
+#define CALL_PUSH(VW, NV) cudaLaunchKernelEx(&pc, dp_reduce_push_kernel<VW, NV>, a, d)
             { ProfScope pp(c, PROF_DP_PUSH, s); DISPATCH_LAYOUT(vw, nv, CALL_PUSH); }
             ProfScope po(c, PROF_DP_OWNER, s);
             DpOwn o;
@@ -1799,9 +1823,11 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
             add(P.off_rel, m->m_rel, m->v_rel, false, 0);
             if (m->model != OKB_TRANSE) add(P.off_rel_aux, m->m_rel_aux, m->v_rel_aux, false, 1);
             const unsigned og = (unsigned)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)148 * 8));
-            if (vw == 4) dp_owner_kernel<4><<<og, 256, 0, s>>>(o);
-            else if (vw == 2) dp_owner_kernel<2><<<og, 256, 0, s>>>(o);
-            else dp_owner_kernel<1><<<og, 256, 0, s>>>(o);
+            cudaLaunchConfig_t oc = {};
+            oc.gridDim = dim3(og); oc.blockDim = dim3(256); oc.stream = s; oc.attrs = pat; oc.numAttrs = c->pdl ? 1 : 0;
+            if (vw == 4) cudaLaunchKernelEx(&oc, dp_owner_kernel<4>, o);
+            else if (vw == 2) cudaLaunchKernelEx(&oc, dp_owner_kernel<2>, o);
+            else cudaLaunchKernelEx(&oc, dp_owner_kernel<1>, o);
         }
         OKB_LAUNCHED(2);
         c->dp_epoch = epoch;

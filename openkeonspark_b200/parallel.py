@@ -268,7 +268,8 @@ def attach(con, group=None, mode="auto"):
         if dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 16:      # peer memory needs GPUs
             con._ensure_model()
             dense = con.batch_size * (3 + con.negative_ent + con.negative_rel) * 4 >= con.entTotal + con.relTotal
-            if dense and con.trainModel.name != "TransR":
+            _, ranges = partition(con.batch_size, con.workThreads, dist.get_world_size(group))
+            if dense and con.trainModel.name != "TransR" and all(hi > lo for lo, hi in ranges):    # every rank must own positives
                 mode = "owner"
     con._world = OwnerSharded(con, group) if mode == "owner" else DataParallel(con, group)
     return con._world
