@@ -344,12 +344,12 @@ def main():
             kern[name] = {"ms": ms / cnt, "gbs": nbytes / (ms / cnt * 1e-3) / 1e9, "bytes": nbytes}
     dom = max(kern, key=lambda n: kern[n]["ms"]) if kern else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
-    # (profiles/r01d_ncu_full_train_kernels.txt; ncu invalidates the caches before every kernel replay, so the gradient
+    # (profiles/r01e_ncu_full_train_kernels.txt; ncu invalidates the caches before every kernel replay, so the gradient
     # rows the update kernel normally finds in L2 are counted as DRAM reads there; updated rows stay in L2 as dirty lines)
-    NCU_TRAFFIC = {"update": 31215104 + 212224, "grad": 5297408 + 1024}
+    NCU_TRAFFIC = {"update": 31213056 + 256, "grad": 5256704 + 0}
     roofline = None
     if dom:
-        roofline = {"kernel": "adam_kernel" if dom == "update" else "grad_kernel", "bound": "hbm", "achieved": kern[dom]["gbs"],
+        roofline = {"kernel": "adam_tile_kernel" if dom == "update" else "grad_k1_kernel", "bound": "hbm", "achieved": kern[dom]["gbs"],
                     "peak": peak, "unit": "GB/s", "frac": kern[dom]["gbs"] / peak,
                     "traffic": NCU_TRAFFIC[dom] if world == 1 else None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": kern[dom]["bytes"], "avg_launch_ms": kern[dom]["ms"],
