@@ -56,7 +56,7 @@ def _check_adam_slots(con, ref64):
 
 @pytest.mark.parametrize("model", ["TransE", "TransH", "TransD"])
 @pytest.mark.parametrize("opt", ["SGD", "Adam"])
-@pytest.mark.parametrize("D,k,kr", [(50, 1, 0), (100, 3, 1), (20, 2, 0), (200, 1, 0), (100, 1, 0)])
+@pytest.mark.parametrize("D,k,kr", [(50, 1, 0), (100, 3, 1), (20, 2, 0), (200, 1, 0), (100, 1, 0), (33, 1, 0), (33, 2, 1)])
 def test_train_step_parity(built, small_ds, model, opt, D, k, kr):
     import torch
     from oracle import models_ref
