@@ -209,6 +209,9 @@ int okb_dp_attach(okb_ctx *c, const okb_dp *cfg);
 int okb_dp_detach(okb_ctx *c);
 int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out,
                        void *cuda_stream);
+/* stream-ordered wait until every rank's row updates of all steps issued so far have landed in THIS rank's tables (a
+ * rank's last update kernel stores into its peers' arenas).  Not a collective. */
+int okb_dp_quiesce(okb_ctx *c, void *cuda_stream);
 
 /* ---- scoring = TransX.predict_def (TransE.py:53-58 ...).  h,t,r: device int64[n]; out: device
  *      float[n] (TransE: mean over d; others: sum).  Canonical evaluation order, see DESIGN.md. */

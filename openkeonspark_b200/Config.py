@@ -317,7 +317,7 @@ class Config(object):
 
     def get_parameters(self, mode="numpy"):
         if self._world is not None and self._world.mode == "owner":
-            self._world.quiesce()                     # collective: peers' last row updates have landed
+            self._world.quiesce(self)                 # peers' last row updates have landed (not a collective)
         res = {}
         for var_name in self.get_parameter_lists():
             v = self.get_parameters_by_name(var_name)

@@ -1688,6 +1688,17 @@ __global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
     }
 }
 
+// End of a library call: publish "my owner-update kernels up to `epoch` are complete" without waiting for the next step's
+// grad kernel to do it, so that a peer can find out ON ITS OWN (okb_dp_quiesce) when its tables are complete.
+__global__ void dp_announce_kernel(DpPush d) {
+    if ((int)threadIdx.x < d.world)
+        st_release_sys((unsigned long long *)(d.arena[threadIdx.x] + d.off_flags) + DP_FLAG_X + d.rank, d.epoch);
+}
+__global__ void dp_wait_kernel(DpPush d) {
+    if ((int)threadIdx.x < d.world)
+        spin_until((const unsigned long long *)(d.arena[d.rank] + d.off_flags) + DP_FLAG_X + threadIdx.x, d.epoch);
+}
+
 static void fill_upd_args(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
                           const float *loss_terms, UpdArgs &a) {
     const i64 n = c->plan_ne + c->plan_nr, total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
@@ -1833,6 +1844,27 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         c->dp_epoch = epoch;
     }
     c->pdl = was_pdl;
+    {
+        DpPush d;
+        for (int q = 0; q < OKB_DP_MAX; q++) d.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
+        d.off_flags = P.off_flags; d.world = P.world; d.rank = P.rank; d.epoch = c->dp_epoch;
+        dp_announce_kernel<<<1, 32, 0, s>>>(d);
+        OKB_LAUNCHED(1);
+    }
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+/* Returns (stream-ordered) once every rank's row updates of all steps issued so far have landed in THIS rank's tables.
+ * Not a collective: it only waits for flags the peers publish at the end of their own okb_dp_train_steps calls. */
+int okb_dp_quiesce(okb_ctx *c, void *stream) {
+    if (!c->dp_on) return 0;
+    const okb_dp &P = c->dp;
+    DpPush d;
+    for (int q = 0; q < OKB_DP_MAX; q++) d.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
+    d.off_flags = P.off_flags; d.world = P.world; d.rank = P.rank; d.epoch = c->dp_epoch;
+    dp_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d);
+    OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
     return 0;
 }

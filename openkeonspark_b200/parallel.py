@@ -227,14 +227,16 @@ class OwnerSharded(DataParallel):
     def train_step(self, con, m, hp, step):
         raise RuntimeError("owner-sharded mode steps through next_step()/train_chunk()")
 
-    def quiesce(self):
-        """Collective: returns when every rank's updates have landed in every table (a rank's last owner-update kernel
-        stores into its peers' arenas; nothing after it in the peers' streams waits for those stores)."""
+    def quiesce(self, con):
+        """Returns when every rank's row updates of all steps issued so far have landed in THIS rank's tables (a rank's
+        last owner-update kernel stores into its peers' arenas).  NOT a collective — `if rank == 0: con.get_parameters()`
+        is fine: it waits on flags the peers publish at the end of their own train calls."""
+        from .Config import _stream
+        con.ctx.call("okb_dp_quiesce", _stream())
         torch.cuda.synchronize()
-        dist.barrier(group=self.group)
 
     def link_prediction(self, con, q_lo=0, q_hi=None):
-        self.quiesce()
+        self.quiesce(con)
         return super().link_prediction(con, q_lo, q_hi)
 
     def sync_adam_slots(self, con):
@@ -252,7 +254,9 @@ class OwnerSharded(DataParallel):
             v.copy_(pad[:rows])
 
     def close(self, con):
-        self.quiesce()
+        """Collective: every rank must have stopped writing into its peers before the mappings go away."""
+        self.quiesce(con)
+        dist.barrier(group=self.group)
         con.ctx.call("okb_dp_detach")
         for p in self._opened:
             con.ctx.call("okb_peer_close", _vp(p))

@@ -1,0 +1,21 @@
+"""Two-rank data-parallel check as a pytest (needs >= 2 GPUs; skipped on the one-GPU box): spawns tests/dist_gpu_check.py
+under torchrun — exact mode bit-identical to one GPU, owner-sharded mode within tolerance and replicas bit-identical."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_two_rank_data_parallel(built):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("bit-identical to single GPU") == 3 and r.stdout.count("owner-sharded") == 4, r.stdout[-2000:]
