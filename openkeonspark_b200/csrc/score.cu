@@ -19,6 +19,7 @@
 // accumulators per side in registers: 2 FADD per (query, candidate, dim) — FP32-ALU bound; L1
 // distance has no tensor-core form.
 #include <algorithm>
+#include <cstdlib>
 
 #include "okb_internal.h"
 
@@ -358,15 +359,14 @@ struct RankArgs {
 // costs D*4 bytes of shared memory: sharing it between QG threads is what lifts residency from 12 to
 // 24-32 warps per SM.)
 template <bool HEADS, int QG>
-__global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
+__global__ void __launch_bounds__(CT * QG, 1024 / (CT * QG)) rank_kernel(RankArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
     constexpr int NQ = QG * QB;                            // queries per pass
     const int D = a.D, tid = threadIdx.x, jl = tid % CT, qg = tid / CT;
     float *tile = (float *)smraw;                          // [D][CT]
     float *rhat = tile + (size_t)D * CT;                   // [D]
-    float *qa = rhat + ((D + 3) & ~3);                     // [QG][D][8]  (the global blocked layout)
-    float *qt = qa + (size_t)D * NQ;                       // [QG][D][8]
-    float *refs = qt + (size_t)D * NQ;                     // [NQ] raw-sum thresholds
+    float *qbuf = rhat + ((D + 3) & ~3);                   // [2 buffers][qa | qt][QG][D][8]  (the global blocked layout)
+    float *refs = qbuf + 4 * (size_t)D * NQ;               // [NQ] raw-sum thresholds
     i32 *tgt = (i32 *)(refs + NQ);                         // [NQ][2]
     int4 *runs = (int4 *)(tgt + 2 * NQ);                   // [NQ]
     int2 *krange = (int2 *)(runs + NQ);                    // [NQ][2] known-true ids that fall inside this CTA's candidate tile
@@ -379,29 +379,37 @@ __global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
     const i32 tab = a.tab_per_group ? g : 0;
     const i32 qlo = a.g_qlo[g], qhi = a.g_qhi[g];
     const i32 nblk = (qhi - qlo + QB - 1) / QB, blk0 = a.g_blk[g];
-    unsigned phase = 0;
+    // The query vectors of a pass are double-buffered: pass p+1's vectors are requested while pass p is computed, and
+    // pass 0's go out together with the candidate tile, so a CTA exposes ONE bulk-copy latency instead of one per pass.
+    auto load_queries = [&](i32 pb, int buf) {             // thread 0
+        const i32 nb = min(QG, nblk - pb);
+        const unsigned bytes = (unsigned)(nb * D * QB * sizeof(float));
+        float *qa = qbuf + (size_t)buf * 2 * D * NQ, *qt = qa + (size_t)D * NQ;
+        mbar_expect_tx(bar + 1 + buf, HEADS ? 2 * bytes : bytes);
+        tma_load_1d(qa, a.qa + (i64)(blk0 + pb) * D * QB, bytes, bar + 1 + buf);
+        if (HEADS) tma_load_1d(qt, a.qt + (i64)(blk0 + pb) * D * QB, bytes, bar + 1 + buf);
+    };
     if (tid == 0) {
-        mbar_init(bar, 1);
+        mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);
         mbar_expect_tx(bar, (unsigned)(D * CT * sizeof(float)));
         const float *src = a.cand + (i64)tab * D * a.ncol + col0;
         for (int d = 0; d < D; d++) tma_load_1d(tile + (size_t)d * CT, src + (i64)d * a.ncol, CT * sizeof(float), bar);
+        if (nblk > 0) load_queries(0, 0);
     }
     for (int d = tid; d < D; d += CT * QG) rhat[d] = a.rv[(i64)g * 2 * D + d];
     const i32 j = a.j0 + col0 + jl;
     const bool valid = j >= a.cand_lo && j < a.cand_hi;
     const unsigned tf = valid ? a.tflag[(i64)g * a.ncol + col0 + jl] : 0u;
     __syncthreads();                                       // barrier init visible to all waiters
-    mbar_wait(bar, phase); phase ^= 1;
+    mbar_wait(bar, 0);
 
-    for (i32 pb = 0; pb < nblk; pb += QG) {                // a pass = QG consecutive 8-query blocks of the group
+    int pass = 0;
+    for (i32 pb = 0; pb < nblk; pb += QG, pass++) {        // a pass = QG consecutive 8-query blocks of the group
         const i32 nb = min(QG, nblk - pb), qb = qlo + pb * QB;
-        __syncthreads();                                   // previous pass fully consumed
-        if (tid == 0) {                                    // the pass's query vectors are contiguous: two bulk copies
-            const unsigned bytes = (unsigned)(nb * D * QB * sizeof(float));
-            mbar_expect_tx(bar, HEADS ? 2 * bytes : bytes);
-            tma_load_1d(qa, a.qa + (i64)(blk0 + pb) * D * QB, bytes, bar);
-            if (HEADS) tma_load_1d(qt, a.qt + (i64)(blk0 + pb) * D * QB, bytes, bar);
-        }
+        const int buf = pass & 1;
+        const float *qa = qbuf + (size_t)buf * 2 * D * NQ, *qt = qa + (size_t)D * NQ;
+        __syncthreads();                                   // previous pass fully consumed (its buffer is free again)
+        if (tid == 0 && pb + QG < nblk) load_queries(pb + QG, buf ^ 1);
         if (tid < NQ) {
             const bool ok = qb + tid < qhi;
             const i32 ti = a.q_lo + qb + tid;
@@ -435,7 +443,7 @@ __global__ void __launch_bounds__(CT * QG) rank_kernel(RankArgs a) {
             bst[idx] = (qb + (idx >> 3) < qhi) ? a.best[(i64)(qb + (idx >> 3)) * 8 + (idx & 7)] : ~0ull;
         }
         __syncthreads();
-        mbar_wait(bar, phase); phase ^= 1;
+        mbar_wait(bar + 1 + buf, (unsigned)(pass >> 1) & 1u);
 
         if (qg < nb) {
             const i32 q0 = qg * QB;                        // this thread group's queries within the pass
@@ -656,11 +664,19 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
     gmax = std::min<i64>(gmax, 8192);
     // thread groups per CTA: more groups = more warps per staged tile; 4 when groups are large enough to fill 32 queries
     const i64 avg_q = grel.empty() ? 1 : (q_hi - q_lo) / (i64)grel.size();
-    const int QGsel = avg_q >= 20 ? 4 : 2;
+    auto rank_smem = [&](int qg) {
+        const size_t nq = (size_t)qg * QB;
+        return sizeof(float) * ((size_t)D * CT + ((D + 3) & ~3) + 4 * (size_t)D * nq + nq) + sizeof(i32) * 2 * nq +
+               sizeof(int4) * nq + sizeof(int2) * 2 * nq + sizeof(unsigned) * nq * 8 + sizeof(unsigned long long) * (nq * 8 + 3) + 128;
+    };
+    // Thread groups per CTA: 4 when groups are large enough to fill 32 query slots per pass.  (Picking the QG in {2,3,4}
+    // that wastes the fewest 8-query block slots was measured and is within +-10 % of this rule either way: fewer idle
+    // thread groups but fewer warps sharing a staged tile.)
+    int QGsel = avg_q >= 20 ? 4 : 2;
+    if (QGsel == 4 && rank_smem(4) > 227 * 1024) QGsel = 2;          // wide embeddings: fewer query slots per pass
+    if (const char *e = getenv("OKB200_RANK_QG")) { const int v = atoi(e); if (v >= 2 && v <= 4 && rank_smem(v) <= 227 * 1024) QGsel = v; }   // A/B runs
     const size_t NQ = (size_t)QGsel * QB;
-    const size_t smem_rank = sizeof(float) * ((size_t)D * CT + ((D + 3) & ~3) + 2 * (size_t)D * NQ + NQ) + sizeof(i32) * 2 * NQ +
-                             sizeof(int4) * NQ + sizeof(int2) * 2 * NQ + sizeof(unsigned) * NQ * 8 +
-                             sizeof(unsigned long long) * (NQ * 8 + 1) + 128;
+    const size_t smem_rank = rank_smem(QGsel);
     if (smem_rank > 227 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension too large for the ranking tile");
     static bool attr_done = false;
     if (!attr_done) {
@@ -668,6 +684,8 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         cudaFuncSetAttribute(rank_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(rank_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(rank_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(rank_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(rank_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         cudaFuncSetAttribute(qvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
@@ -749,6 +767,7 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         const dim3 grid((unsigned)(ncol / CT), (unsigned)G);
         { ProfScope ps(c, PROF_RANK, s);
         if (QGsel == 4) { if (heads) rank_kernel<true, 4><<<grid, CT * 4, smem_rank, s>>>(ra); else rank_kernel<false, 4><<<grid, CT * 4, smem_rank, s>>>(ra); }
+        else if (QGsel == 3) { if (heads) rank_kernel<true, 3><<<grid, CT * 3, smem_rank, s>>>(ra); else rank_kernel<false, 3><<<grid, CT * 3, smem_rank, s>>>(ra); }
         else { if (heads) rank_kernel<true, 2><<<grid, CT * 2, smem_rank, s>>>(ra); else rank_kernel<false, 2><<<grid, CT * 2, smem_rank, s>>>(ra); } }
         OKB_LAUNCHED(5);
         OKB_CUDA(c, cudaGetLastError());
