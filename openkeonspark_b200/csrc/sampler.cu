@@ -222,10 +222,30 @@ int okb_batch_ptrs(okb_ctx *c, INT step, const int32_t **h, const int32_t **t, c
     return 0;
 }
 
+// Device-visible alias of a page-locked host pointer (nullptr for pageable memory).  Under unified addressing every
+// cudaHostAlloc / cudaHostRegister allocation is mapped, so a kernel can store the batch straight into the caller's
+// buffer (or read it from there): one launch instead of a staging kernel plus a DMA per array.
+static void *pinned_alias(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost) return at.devicePointer;
+    cudaGetLastError();
+    return nullptr;
+}
+
 int okb_batch_to_host(okb_ctx *c, INT step, INT *h, INT *t, INT *r, REAL *y, void *stream) {
     if (step < 0 || step >= c->steps) OKB_FAIL(c, OKB_ERR_ARG, "step out of range");
     cudaStream_t s = (cudaStream_t)stream;
     const i64 S = c->B * (1 + c->K + c->KR);
+    if (t == h + S && r == t + S && !y) {                  // one pinned block (Config's batch buffers): zero-copy stores
+        if (i64 *dh = (i64 *)pinned_alias(h)) {
+            if (c->host_io.ensure(sizeof(float) * S)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+            widen_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(c->batch.as<i32>() + step * 3 * S, dh, dh + S, dh + 2 * S,
+                                                                       c->host_io.as<float>(), (i32)S, (i32)c->B);
+            OKB_LAUNCHED(1);
+            OKB_CUDA(c, cudaStreamSynchronize(s));
+            return 0;
+        }
+    }
     if (c->host_io.ensure((sizeof(i64) * 3 + sizeof(float)) * S)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
     i64 *dh = c->host_io.as<i64>(), *dt = dh + S, *dr = dt + S;
     float *dy = (float *)(dr + S);
@@ -250,6 +270,14 @@ int okb_batch_from_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const IN
     if (c->host_io.ensure(sizeof(i64) * 3 * S)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
     c->B = B; c->K = k; c->KR = kr; c->steps = 1;
     c->plan_lo = c->plan_hi = 0;
+    if (t == h + S && r == t + S) {                        // one pinned block: the narrowing kernel reads it over PCIe itself
+        if (const i64 *ph = (const i64 *)pinned_alias(h)) {
+            narrow_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(ph, ph + S, ph + 2 * S, c->batch.as<i32>(), (i32)S);
+            OKB_LAUNCHED(1);
+            OKB_CUDA(c, cudaGetLastError());
+            return 0;
+        }
+    }
     i64 *dh = c->host_io.as<i64>(), *dt = dh + S, *dr = dt + S;
     if (t == h + S && r == t + S) {
         OKB_CUDA(c, cudaMemcpyAsync(dh, h, sizeof(i64) * 3 * S, cudaMemcpyHostToDevice, s));
