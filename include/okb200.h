@@ -199,6 +199,13 @@ typedef struct {
     INT off_stage_ent, off_stage_rel;                 /* staging slabs [world][ceil(rows/world)][cols] */
     INT off_flags;                                    /* 512-byte flag block */
     INT arena_bytes;
+    /* "pull" form of the update (optional; set plan_steps > 0 before okb_dp_layout): the rank's plan (row map, slot
+     * permutation), gradient rows and loss terms also live in the arena, so the row OWNER sums the partial rows of all
+     * ranks straight out of their gradient buffers (peer loads) and the separate reduce+push kernel disappears. */
+    INT plan_steps;                 /* steps planned per chunk at most (Config.plan_ahead) */
+    INT max_local;                  /* positives per rank at most */
+    INT neg_ent, neg_rel;
+    INT off_rowhead, off_perm, off_gent, off_grel, off_loss, off_partial;   /* -1 = not reserved */
 } okb_dp;
 int okb_peer_alloc(okb_ctx *c, INT bytes, void **dev_ptr, unsigned char *handle64);
 int okb_peer_open(okb_ctx *c, const unsigned char *handle64, void **dev_ptr);
@@ -263,7 +270,12 @@ enum { OKB_FLAG_TRANSR_TC = 1,
        /* OKB_FLAG_ADAM_LEGACY = 5 (default off): the first, grid-stride form of the dense Adam pass (A/B runs). */
        OKB_FLAG_ADAM_LEGACY = 5,
        /* OKB_FLAG_GRAD_GENERIC = 6 (default off): use the generic grad kernel even for the k = 1, kr = 0 batch (A/B runs). */
-       OKB_FLAG_GRAD_GENERIC = 6 };
+       OKB_FLAG_GRAD_GENERIC = 6,
+       /* OKB_FLAG_DP_PULL = 7 (default off): owner-sharded data parallelism lets the row owner PULL the partial rows from its
+        * peers' gradient buffers (peer loads) instead of running the reduce+push kernel (peer stores).  Bit-identical
+        * results; measured 65 vs 40 us per step at 2 GPUs — dependent loads over NVLink cost several us each — so it is
+        * kept for A/B runs only.  Needs the arena's optional plan / gradient slices (okb_dp.plan_steps > 0). */
+       OKB_FLAG_DP_PULL = 7 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:

@@ -35,7 +35,10 @@ OKB_DP_MAX = 16
 class okb_dp(C.Structure):
     _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("b_lo", _i64), ("b_hi", _i64), ("arena", _vp * OKB_DP_MAX),
                 ("off_ent", _i64), ("off_ent_aux", _i64), ("off_rel", _i64), ("off_rel_aux", _i64),
-                ("off_stage_ent", _i64), ("off_stage_rel", _i64), ("off_flags", _i64), ("arena_bytes", _i64)]
+                ("off_stage_ent", _i64), ("off_stage_rel", _i64), ("off_flags", _i64), ("arena_bytes", _i64),
+                ("plan_steps", _i64), ("max_local", _i64), ("neg_ent", _i64), ("neg_rel", _i64),
+                ("off_rowhead", _i64), ("off_perm", _i64), ("off_gent", _i64), ("off_grel", _i64), ("off_loss", _i64),
+                ("off_partial", _i64)]
 
 
 MODEL_ID = {"TransE": 0, "TransH": 1, "TransR": 2, "TransD": 3}

@@ -18,6 +18,7 @@
 // ------------------------------------------------------------------------------------------ DevBuf
 int DevBuf::ensure(size_t bytes) {
     if (bytes <= cap) return 0;
+    if (external) return 1;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
     size_t want = bytes + bytes / 4 + 256;
@@ -25,7 +26,7 @@ int DevBuf::ensure(size_t bytes) {
     cap = want;
     return 0;
 }
-void DevBuf::release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+void DevBuf::release() { if (p && !external) cudaFree(p); p = nullptr; cap = 0; external = false; }
 
 template <class T> static int upload(okb_ctx *c, T *&dst, const std::vector<T> &src) {
     if (dst) { cudaFree(dst); dst = nullptr; }

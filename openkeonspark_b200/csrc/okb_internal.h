@@ -15,8 +15,11 @@ typedef uint64_t u64;
 struct DevBuf {                       // grow-only device allocation
     void *p = nullptr;
     size_t cap = 0;
+    bool external = false;            // memory owned by someone else (a slice of the peer arena): never freed, never grown
     int ensure(size_t bytes);
     void release();
+    void adopt(void *ptr, size_t bytes) { release(); p = ptr; cap = bytes; external = true; }
+    void disown() { if (external) { p = nullptr; cap = 0; external = false; } }
     template <class T> T *as() const { return (T *)p; }
 };
 
@@ -76,6 +79,7 @@ struct okb_ctx {
     okb_dp dp = {};                   // owner-sharded data parallelism (okb_dp_attach)
     bool dp_on = false;
     unsigned long long dp_epoch = 0;
+    bool dp_pull = false;             // OKB_FLAG_DP_PULL: row owners pull partial rows from their peers instead of the reduce+push kernel
     bool pdl = true;                  // programmatic dependent launch between the grad and update kernels
     bool rowhead_ready = false;       // Adam: per-step row -> first sorted position map built for the planned chunk
     int ent_bits = 0, rel_bits = 0;

@@ -1699,6 +1699,132 @@ __global__ void dp_wait_kernel(DpPush d) {
         spin_until((const unsigned long long *)(d.arena[d.rank] + d.off_flags) + DP_FLAG_X + threadIdx.x, d.epoch);
 }
 
+// ---- "pull" form of the owner update: no reduce+push kernel.  Every rank's plan of the step (row map + slot permutation),
+// its gradient rows and its loss terms live in its peer arena; the OWNER of a table row walks each rank's segment of that
+// row with peer loads (ld.global.cv over NVLink), adds the per-rank sums in rank order — bit-identical to the push form —
+// applies SGD / TF1-Adam and publishes the row.  A step is then two kernels (grad, this one) and two flag barriers.
+// Hub rows (segments longer than PCH) keep the push form, whose pre-reduced block sums are local.
+struct PullTab {
+    float *m, *v;              // local Adam slots (full-size arrays; only the owned rows are maintained)
+    i64 x_off;                 // byte offset of the table in an arena
+    i64 vec_end;               // cumulative vector count over the OWNED rows of the table list
+    i32 D, cols, part, row_lo, key_off, is_ent;
+};
+struct DpPull {
+    okb_hyper hp;
+    char *arena[OKB_DP_MAX];
+    PullTab tab[4];
+    i64 off_flags, off_rowhead, off_perm, off_gent, off_grel, off_loss;
+    i32 nloc[OKB_DP_MAX], nes[OKB_DP_MAX], bl[OKB_DP_MAX];   // per rank: plan entries per step, entity slots, positives
+    i32 ntab, world, rank, adam, rows_all, step_rel, work_blocks;
+    unsigned long long epoch;
+    float *loss_out;
+    float w;
+};
+template <int VW>
+__global__ void __launch_bounds__(256) dp_pull_kernel(DpPull d) {
+    typedef typename VecT<VW>::T V;
+    pdl_launch_dependents();
+    pdl_wait();                                            // this rank's grad kernel is complete: announce it
+    dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, blockIdx.x == 0);
+    if ((i32)blockIdx.x >= d.work_blocks) {                // mean hinge over the GLOBAL batch: per-rank sums in a fixed order
+        if (!d.loss_out) return;
+        __shared__ float sh[8];
+        float tot = 0.f;
+        for (int p = 0; p < d.world; p++) {
+            const float *lt = (const float *)(d.arena[p] + d.off_loss);
+            float x = 0.f;
+            for (i32 i = threadIdx.x; i < d.bl[p]; i += 256) x += __ldcv(lt + i);
+            x = wsum(x);
+            if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = x;
+            __syncthreads();
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) t += sh[w];
+            tot += t;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) d.loss_out[0] = tot * d.w;
+        return;
+    }
+    const i64 total = d.tab[d.ntab - 1].vec_end;
+    const float b1 = d.hp.beta1, b2 = d.hp.beta2, lr = d.hp.lr, eps = d.hp.eps;
+    const char *own = d.arena[d.rank];
+    for (i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (i64)d.work_blocks * blockDim.x) {
+        int t = 0;
+        while (v >= d.tab[t].vec_end) t++;
+        const PullTab &T = d.tab[t];
+        const unsigned lv = (unsigned)(v - (t ? d.tab[t - 1].vec_end : 0));
+        const unsigned vpr = (unsigned)T.D / VW;
+        const unsigned rl = lv / vpr, col = (lv - rl * vpr) * VW;
+        const i32 row = T.row_lo + (i32)rl;
+        const i64 e = (i64)row * T.D + col;                 // element index inside the full table
+        const i64 key = (i64)d.step_rel * d.rows_all + T.key_off + row;
+        V xv = *reinterpret_cast<const V *>(own + T.x_off + e * 4);
+        V mv, vv;
+        if (d.adam) { mv = *reinterpret_cast<const V *>(T.m + e); vv = *reinterpret_cast<const V *>(T.v + e); }
+        float g[VW];
+#pragma unroll
+        for (int q = 0; q < VW; q++) g[q] = 0.f;
+        bool any = false;
+        for (int p0 = 0; p0 < d.world; p0 += 4) {           // four ranks at a time: their loads are in flight together
+            int4 seg[4];
+            V g0[4], g1[4];
+            const float *gb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                seg[u] = make_int4(-1, 0, 0, 0);
+                if (p0 + u < d.world) seg[u] = __ldg(reinterpret_cast<const int4 *>(d.arena[p0 + u] + d.off_rowhead) + key);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (seg[u].x < 0) continue;
+                const int p = p0 + u;
+                gb[u] = (const float *)(d.arena[p] + (T.is_ent ? d.off_gent : d.off_grel)) + T.part * T.D + col -
+                        (T.is_ent ? (i64)0 : (i64)d.nes[p] * T.cols);
+                g0[u] = __ldg(reinterpret_cast<const V *>(gb[u] + (i64)seg[u].z * T.cols));
+                if (seg[u].y - seg[u].x > 1) g1[u] = __ldg(reinterpret_cast<const V *>(gb[u] + (i64)seg[u].w * T.cols));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (seg[u].x < 0) continue;
+                const int p = p0 + u;
+                float sp[VW];                              // this rank's segment sum, in slot order
+                const float *q0 = reinterpret_cast<const float *>(&g0[u]), *q1 = reinterpret_cast<const float *>(&g1[u]);
+                const i32 cnt = seg[u].y - seg[u].x;
+#pragma unroll
+                for (int q = 0; q < VW; q++) { sp[q] = 0.f + q0[q]; if (cnt > 1) sp[q] += q1[q]; }
+                const i32 *perm = reinterpret_cast<const i32 *>(d.arena[p] + d.off_perm) + (i64)d.step_rel * d.nloc[p];
+                for (i32 j = seg[u].x + 2; j < seg[u].y; j++) {
+                    const V gj = __ldg(reinterpret_cast<const V *>(gb[u] + (i64)__ldg(perm + j) * T.cols));
+                    const float *pj = reinterpret_cast<const float *>(&gj);
+#pragma unroll
+                    for (int q = 0; q < VW; q++) sp[q] += pj[q];
+                }
+#pragma unroll
+                for (int q = 0; q < VW; q++) { g[q] += sp[q]; any |= sp[q] != 0.f; }
+            }
+        }
+        float *xs = reinterpret_cast<float *>(&xv);
+        if (d.adam) {
+            float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+            for (int q = 0; q < VW; q++) {
+                const float mq = ms[q] * b1 + g[q] * (1.f - b1);
+                const float vq = vs[q] * b2 + (g[q] * g[q]) * (1.f - b2);
+                ms[q] = mq; vs[q] = vq;
+                xs[q] -= lr * mq / (sqrtf(vq) + eps);
+            }
+            *reinterpret_cast<V *>(T.m + e) = mv; *reinterpret_cast<V *>(T.v + e) = vv;
+        } else {
+            if (!any) continue;                            // SGD leaves rows without gradient untouched: nothing to publish
+#pragma unroll
+            for (int q = 0; q < VW; q++) xs[q] -= lr * g[q];
+        }
+        for (int p = 0; p < d.world; p++) *reinterpret_cast<V *>(d.arena[p] + T.x_off + e * 4) = xv;
+    }
+}
+
 static void fill_upd_args(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
                           const float *loss_terms, UpdArgs &a) {
     const i64 n = c->plan_ne + c->plan_nr, total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
@@ -1727,9 +1853,26 @@ int okb_dp_attach(okb_ctx *c, const okb_dp *cfg) {
     c->dp = *cfg;
     c->dp_on = true;
     c->dp_epoch = 0;
+    if (cfg->off_rowhead >= 0 && cfg->plan_steps > 0) {    // pull form: the plan / gradient buffers are slices of the arena
+        char *own = (char *)cfg->arena[cfg->rank];
+        const i64 NE = 2 + cfg->neg_ent, NR = 1 + cfg->neg_rel, Bl = cfg->max_local;
+        c->rowseg_e.adopt(own + cfg->off_rowhead, (size_t)(cfg->plan_steps * (c->E + c->R) * (i64)sizeof(int4)));
+        c->perm_ent.adopt(own + cfg->off_perm, (size_t)(cfg->plan_steps * Bl * (NE + NR) * 4));
+        c->gent.adopt(own + cfg->off_gent, (size_t)(cfg->off_grel - cfg->off_gent));
+        c->grel.adopt(own + cfg->off_grel, (size_t)(cfg->off_loss - cfg->off_grel));
+        c->lossterms.adopt(own + cfg->off_loss, (size_t)(Bl * 4));
+        c->plan_lo = c->plan_hi = 0;
+        c->rowhead_ready = false;
+    }
     return 0;
 }
-int okb_dp_detach(okb_ctx *c) { c->dp_on = false; return 0; }
+int okb_dp_detach(okb_ctx *c) {
+    c->dp_on = false;
+    for (DevBuf *b : {&c->rowseg_e, &c->perm_ent, &c->gent, &c->grel, &c->lossterms}) b->disown();
+    c->plan_lo = c->plan_hi = 0;
+    c->rowhead_ready = false;
+    return 0;
+}
 
 /* bytes a rank's arena needs, and the offsets of its parts (all 256-byte aligned) */
 int okb_dp_layout(okb_ctx *c, const okb_model *m, INT world, okb_dp *out) {
@@ -1748,6 +1891,15 @@ int okb_dp_layout(okb_ctx *c, const okb_model *m, INT world, okb_dp *out) {
     out->off_stage_ent = take(world * own_e * ce * 4);
     out->off_stage_rel = take(world * own_r * cr * 4);
     out->off_flags = take(DP_FLAG_BYTES);
+    out->off_rowhead = out->off_perm = out->off_gent = out->off_grel = out->off_loss = out->off_partial = -1;
+    if (out->plan_steps > 0 && out->max_local > 0) {       // pull form: plan, gradient rows and loss terms in the arena too
+        const i64 NE = 2 + out->neg_ent, NR = 1 + out->neg_rel, Bl = out->max_local;
+        out->off_rowhead = take(out->plan_steps * (c->E + c->R) * (i64)sizeof(int4));
+        out->off_perm = take(out->plan_steps * Bl * (NE + NR) * 4);
+        out->off_gent = take(Bl * NE * ce * 4);
+        out->off_grel = take(Bl * NR * cr * 4);
+        out->off_loss = take(Bl * 4);
+    }
     out->arena_bytes = off;
     out->world = (int32_t)world;
     return 0;
@@ -1772,7 +1924,18 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     if ((rc = okb_grad_sizes(c, m, Bl, c->K, c->KR, &er, &ec, &rr, &rcn))) return rc;
     if (c->gent.ensure(sizeof(float) * er * ec) || c->grel.ensure(sizeof(float) * rr * rcn) || c->lossterms.ensure(sizeof(float) * Bl))
         OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (gradient rows)");
+    const bool pull_ok = c->dp_pull && P.off_rowhead >= 0 && c->rowseg_e.external;
     if (!planned(c, step_lo, step_lo + n, P.b_lo, P.b_hi)) {      // plan everything that is sampled from here on with one sort
+        if (pull_ok && c->dp_epoch > 0) {
+            // peers read this rank's plan in their update kernels: do not overwrite it before they have all finished the last
+            // step (they announce that at the end of their own call)
+            DpPush w;
+            for (int q = 0; q < OKB_DP_MAX; q++) w.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
+            w.off_flags = P.off_flags; w.world = P.world; w.rank = P.rank; w.epoch = c->dp_epoch;
+            dp_wait_kernel<<<1, 32, 0, s>>>(w);
+            OKB_LAUNCHED(1);
+        }
+        if (c->steps - step_lo > P.plan_steps && pull_ok) OKB_FAIL(c, OKB_ERR_ARG, "more steps sampled than the arena's plan_steps");
         if ((rc = plan_steps(c, step_lo, c->steps, P.b_lo, P.b_hi, stream))) return rc;
     }
     if ((rc = ensure_rowhead(c, s))) return rc;
@@ -1789,6 +1952,54 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
                               xflags, c->dp_epoch, P.world, stream))) { c->pdl = was_pdl; return rc; }
         UpdArgs a;
         fill_upd_args(c, m, hp + i, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), a);
+        // the choice must be the same on every rank: judge hub rows by the LARGEST rank's share of the batch
+        const bool hub_any = (double)(P.max_local * (2 + c->K)) * c->max_ent_share > PCH || (double)(P.max_local * (1 + c->KR)) * c->max_rel_share > PCH;
+        if (pull_ok && !hub_any) {                         // two-kernel step: the row owners pull the partial rows
+            DpPull o;
+            o.hp = hp[i];
+            for (int q = 0; q < OKB_DP_MAX; q++) o.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
+            o.off_flags = P.off_flags; o.off_rowhead = P.off_rowhead; o.off_perm = P.off_perm; o.off_gent = P.off_gent;
+            o.off_grel = P.off_grel; o.off_loss = P.off_loss;
+            const i64 NE = 2 + c->K, NR = 1 + c->KR, per = c->B / c->W + (c->B % c->W ? 1 : 0), chunk = per * (c->W / P.world);
+            for (int q = 0; q < P.world; q++) {            // the slice geometry of parallel.partition (Base.cpp:85-92)
+                const i64 lo = std::min<i64>(c->B, q * chunk), hi = std::min<i64>(c->B, (q + 1) * chunk);
+                o.bl[q] = (i32)(hi - lo); o.nloc[q] = (i32)((hi - lo) * (NE + NR)); o.nes[q] = (i32)((hi - lo) * NE);
+            }
+            if (o.bl[P.rank] != (i32)Bl) { c->pdl = was_pdl; OKB_FAIL(c, OKB_ERR_ARG, "rank's positive range does not follow the stream-slice geometry"); }
+            o.world = P.world; o.rank = P.rank; o.adam = m->optimizer == OKB_ADAM; o.epoch = epoch;
+            o.rows_all = (i32)(c->E + c->R); o.step_rel = (i32)(step - c->plan_lo);
+            o.loss_out = loss_out ? loss_out + i : nullptr;
+            o.w = 1.0f / (float)(c->B * (c->K + c->KR));
+            o.ntab = 0;
+            i64 acc = 0;
+            auto addt = [&](i64 x_off, float *mm, float *vv, bool is_ent, int part) {
+                if (x_off < 0) return;
+                const int D = is_ent ? m->ent_dim : m->rel_dim;
+                const i64 rows = is_ent ? c->E : c->R, own = (rows + P.world - 1) / P.world;
+                const i64 lo = std::min<i64>(rows, P.rank * own), hi = std::min<i64>(rows, (P.rank + 1) * own);
+                acc += (hi - lo) * D / vw;
+                PullTab T;
+                T.m = mm; T.v = vv; T.x_off = x_off; T.vec_end = acc; T.D = D; T.cols = is_ent ? a.ce : a.cr; T.part = part;
+                T.row_lo = (i32)lo; T.key_off = is_ent ? 0 : (i32)c->E; T.is_ent = is_ent ? 1 : 0;
+                o.tab[o.ntab++] = T;
+            };
+            addt(P.off_ent, m->m_ent, m->v_ent, true, 0);
+            if (m->model == OKB_TRANSD) addt(P.off_ent_aux, m->m_ent_aux, m->v_ent_aux, true, 1);
+            addt(P.off_rel, m->m_rel, m->v_rel, false, 0);
+            if (m->model != OKB_TRANSE) addt(P.off_rel_aux, m->m_rel_aux, m->v_rel_aux, false, 1);
+            o.work_blocks = (i32)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)148 * 8));
+            cudaLaunchConfig_t oc = {};
+            oc.gridDim = dim3((unsigned)o.work_blocks + 1); oc.blockDim = dim3(256); oc.stream = s; oc.attrs = pat; oc.numAttrs = c->pdl ? 1 : 0;
+            {
+                ProfScope po(c, PROF_DP_OWNER, s);
+                if (vw == 4) cudaLaunchKernelEx(&oc, dp_pull_kernel<4>, o);
+                else if (vw == 2) cudaLaunchKernelEx(&oc, dp_pull_kernel<2>, o);
+                else cudaLaunchKernelEx(&oc, dp_pull_kernel<1>, o);
+            }
+            OKB_LAUNCHED(1);
+            c->dp_epoch = epoch;
+            continue;
+        }
         if (a.hub) {
             const i64 nblocks = a.n / PCH;
             if (c->partial.ensure(sizeof(float) * (size_t)(nblocks + 1) * a.pcols)) { c->pdl = was_pdl; OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (partial sums)"); }

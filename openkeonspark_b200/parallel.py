@@ -142,8 +142,10 @@ class OwnerSharded(DataParallel):
     """Owner-sharded synchronous data parallelism over peer memory (see the module docstring)."""
     mode = "owner"
 
-    def __init__(self, con, group=None):
+    def __init__(self, con, group=None, pull=None):
         super().__init__(con, group)
+        import os
+        pull = os.environ.get("OKB200_DP_PULL") == "1" if pull is None else pull      # measured slower: A/B runs only
         from ._native import okb_dp
         from .Config import _AUX_ENT, _AUX_REL
         con._ensure_model()
@@ -153,6 +155,10 @@ class OwnerSharded(DataParallel):
             raise ValueError("owner-sharded mode supports up to 16 ranks per box")
         m = con._cmodel()
         lay = okb_dp()
+        if pull:   # reserve the "pull" slices: the plan of up to plan_ahead steps, this rank's gradient rows and loss terms
+            lay.plan_steps, lay.max_local = int(con.plan_ahead), int(self.chunk)
+            lay.neg_ent, lay.neg_rel = int(con.negative_ent), int(con.negative_rel)
+            con.ctx.call("okb_set_flag", 7, 1)
         con.ctx.call("okb_dp_layout", ctypes.byref(m), self.world, ctypes.byref(lay))
         own, handle = _vp(), (ctypes.c_ubyte * 64)()
         con.ctx.call("okb_peer_alloc", lay.arena_bytes, ctypes.byref(own), handle)
@@ -263,7 +269,7 @@ class OwnerSharded(DataParallel):
         self._opened = []
 
 
-def attach(con, group=None, mode="auto"):
+def attach(con, group=None, mode="auto", pull=None):
     """Enable data-parallel mode on a Config whose init() has run (torch.distributed initialised).
     mode: "owner" (peer-memory owner-sharded update), "exact" (all-gather of gradient rows, bit-identical to one GPU),
     "auto" = owner on NCCL/GPU for TransE/H/D when the batch touches a sizeable share of the rows, else exact."""
@@ -275,5 +281,5 @@ def attach(con, group=None, mode="auto"):
             _, ranges = partition(con.batch_size, con.workThreads, dist.get_world_size(group))
             if dense and con.trainModel.name != "TransR" and all(hi > lo for lo, hi in ranges):    # every rank must own positives
                 mode = "owner"
-    con._world = OwnerSharded(con, group) if mode == "owner" else DataParallel(con, group)
+    con._world = OwnerSharded(con, group, pull) if mode == "owner" else DataParallel(con, group)
     return con._world

@@ -112,6 +112,40 @@ def main():
         a._world.close(a)
         if rank == 0:
             print("dp%d owner-sharded %s/%s: losses match single GPU to 2e-5, tables within tolerance, replicas bit-identical" % (world, model, opt))
+    # the "pull" form of the owner update (uniform graph: no hub rows) must reproduce the reduce+push form bit for bit
+    obj = [None]
+    if rank == 0:
+        d2 = tempfile.mkdtemp() + "/"
+        datagen.write_dataset(datagen.make_shape("small", seed=2), d2, ontology=True)
+        obj = [d2]
+    dist.broadcast_object_list(obj, src=0)
+    d2 = obj[0]
+    for model, opt in (("TransH", "Adam"), ("TransD", "SGD"), ("TransE", "Adam")):
+        res = []
+        for push in (0, 1):
+            a = make(d2, model, opt, 8, False)
+            a.set_ent_neg_rate(1); a.set_rel_neg_rate(0)
+            a.init()
+            a.set_model_and_session(__import__("openkeonspark_b200").__dict__[model])
+            from conftest import make_params
+            a.set_parameters(make_params(model, a.entTotal, a.relTotal, 100, seed=4))
+            seeds = np.arange(1, 9, dtype=np.uint64) * np.uint64(7919)
+            a.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), 8)
+            from openkeonspark_b200 import parallel
+            parallel.attach(a, mode="owner", pull=not push)
+            a.plan_ahead = 4
+            losses = [float(a.next_step_device().item()) for _ in range(4)] + [float(x) for x in a.train_chunk_device(4)]
+            res.append((losses, a.get_parameters()))
+            a._world.close(a)
+        assert res[0][0] == res[1][0], (model, opt, res[0][0], res[1][0])
+        for k in res[0][1]:
+            assert np.array_equal(res[0][1][k], res[1][1][k]), (model, opt, k)
+            t = torch.as_tensor(res[0][1][k]).cuda()
+            ref = t.clone()
+            dist.broadcast(ref, src=0)
+            assert torch.equal(t, ref), (model, opt, k, "replicas differ")
+        if rank == 0:
+            print("dp%d owner-sharded pull == push %s/%s: losses and tables bit-identical, replicas bit-identical" % (world, model, opt))
     dist.barrier()
     dist.destroy_process_group()
 

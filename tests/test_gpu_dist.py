@@ -18,4 +18,5 @@ def test_two_rank_data_parallel(built):
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("bit-identical to single GPU") == 3 and r.stdout.count("owner-sharded") == 4, r.stdout[-2000:]
+    assert r.stdout.count("bit-identical to single GPU") == 3 and r.stdout.count("owner-sharded") == 7, r.stdout[-2000:]
+    assert r.stdout.count("pull == push") == 3, r.stdout[-2000:]
