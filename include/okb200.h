@@ -220,6 +220,14 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
  * rank's last update kernel stores into its peers' arenas).  Not a collective. */
 int okb_dp_quiesce(okb_ctx *c, void *cuda_stream);
 
+/* ---- chunk pipeline.  Sampling and planning depend only on the RNG streams, so the next chunk of steps can be produced on
+ *      an internal side stream while the current chunk trains.  okb_chunk_begin makes `steps` sampled + planned steps
+ *      current (swapping in a matching prefetched chunk, else producing them on cuda_stream); okb_chunk_prefetch starts
+ *      the following chunk.  Any call that observes or changes the RNG streams discards a prefetched chunk and restores
+ *      the streams first, so results never depend on prefetching. */
+int okb_chunk_begin(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, void *cuda_stream);
+int okb_chunk_prefetch(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, void *cuda_stream);
+
 /* ---- scoring = TransX.predict_def (TransE.py:53-58 ...).  h,t,r: device int64[n]; out: device
  *      float[n] (TransE: mean over d; others: sum).  Canonical evaluation order, see DESIGN.md. */
 int okb_predict(okb_ctx *c, const okb_model *m, const int64_t *h, const int64_t *t, const int64_t *r, INT n,

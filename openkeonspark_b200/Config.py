@@ -299,8 +299,15 @@ class Config(object):
         if self._chunk_pos >= self._chunk_len:
             n = self.batch_size * (3 + self.negative_ent + self.negative_rel)
             C = max(1, min(int(self.plan_ahead), (1 << 24) // n))
-            self.sampling_device(C)
-            self.ctx.call("okb_plan_steps", 0, C, _stream())
+            if self._world is None:
+                # current chunk: a prefetched one if it matches, else sampled + planned now; then start the next one on the
+                # library's side stream — it overlaps the train kernels of this chunk
+                a = (self.batch_size, self.negative_ent, self.negative_rel, C, _stream())
+                self.ctx.call("okb_chunk_begin", *a)
+                self.ctx.call("okb_chunk_prefetch", *a)
+            else:
+                self.sampling_device(C)
+                self.ctx.call("okb_plan_steps", 0, C, _stream())
             self._chunk_pos, self._chunk_len = 0, C
         loss = self.train_step_device(self._chunk_pos)
         self._chunk_pos += 1
@@ -449,7 +456,7 @@ class Config(object):
         self._step += 1
         return self._loss_dev
 
-    def train_chunk_device(self, n=None):
+    def train_chunk_device(self, n=None, n_next=None):
         """`n` iterations of the train loop in ONE library call: sample n batches, plan them with one sort,
         then n x (grad + update).  Returns the device tensor of the n losses.  Same results as n calls of
         next_step_device(); exists because a Python round trip per step costs more than the step."""
@@ -460,7 +467,11 @@ class Config(object):
             return self._world.train_chunk(self, n)
         if self._world is not None:
             return torch.stack([self.next_step_device().clone() for _ in range(n)]).reshape(-1)
-        self.sampling_device(n)
+        a = (self.batch_size, self.negative_ent, self.negative_rel)
+        self.ctx.call("okb_chunk_begin", *a, n, _stream())
+        n_next = n if n_next is None else max(0, min(int(n_next), cap))
+        if n_next > 0:                                # sample + plan the next chunk on the side stream while this one trains
+            self.ctx.call("okb_chunk_prefetch", *a, n_next, _stream())
         m = self._cmodel()
         hps = (okb_hyper * n)(*[self._hyper() for _ in range(n)])
         if getattr(self, "_loss_chunk", None) is None or self._loss_chunk.numel() < n:
@@ -539,7 +550,11 @@ class Config(object):
                 n = min(self.plan_ahead, self.nbatches - batch)
                 if es and self._step < to_reach:
                     n = min(n, to_reach - self._step)  # a check falls right after step `to_reach`
-                losses_dev = self.train_chunk_device(n)
+                left = self.nbatches - batch - n
+                nxt = min(self.plan_ahead, left) if left > 0 else (min(self.plan_ahead, self.nbatches) if epoch + 1 < self.train_times else 0)
+                if es:
+                    nxt = 0                           # early-stop checks cut chunks at data-dependent points: no look-ahead
+                losses_dev = self.train_chunk_device(n, nxt)
                 acc += losses_dev.sum()
                 batch += losses_dev.numel()
                 if self.log_every and (self._step // self.log_every != (self._step - losses_dev.numel()) // self.log_every):

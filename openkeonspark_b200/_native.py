@@ -85,6 +85,8 @@ _SIGS = {
     "okb_dp_detach": (_int, [_vp]),
     "okb_dp_train_steps": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _vp, _vp]),
     "okb_dp_quiesce": (_int, [_vp, _vp]),
+    "okb_chunk_begin": (_int, [_vp, _i64, _i64, _i64, _i64, _vp]),
+    "okb_chunk_prefetch": (_int, [_vp, _i64, _i64, _i64, _i64, _vp]),
     "okb_predict": (_int, [_vp, C.POINTER(okb_model), _vp, _vp, _vp, _i64, _vp, _vp]),
     "okb_rank": (_int, [_vp, C.POINTER(okb_model), _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "okb_rank_finalize": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -45,6 +45,11 @@ int okb_destroy(okb_ctx *c) {
     for (DevBuf *b : {&c->batch, &c->keys_ent, &c->keys_rel, &c->perm_ent, &c->perm_rel, &c->sort_tmp, &c->hist, &c->gent, &c->grel,
                       &c->flags, &c->lossterms, &c->rowseg_e, &c->rowseg_r, &c->rank_ws, &c->host_io, &c->partial})
         b->release();
+    for (DevBuf *b : {&c->alt.batch, &c->alt.keys_ent, &c->alt.perm_ent, &c->alt.rowseg_e, &c->alt.sort_tmp, &c->alt.hist}) b->release();
+    if (c->d_state_saved) cudaFree(c->d_state_saved);
+    if (c->side) cudaStreamDestroy(c->side);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c == g_ctx) g_ctx = nullptr;
     delete c;
     return 0;

@@ -29,6 +29,14 @@ struct Lists {
     i32 *d_lef = nullptr, *d_rig = nullptr, *d_ids = nullptr;
 };
 
+// One set of sampled batches + their plan.  The context works on the set held in its own fields; `alt` is a second set the
+// next chunk is sampled and planned into on a side stream while the train kernels of the current chunk run.
+struct PlanSlot {
+    DevBuf batch, keys_ent, perm_ent, rowseg_e, sort_tmp, hist;
+    i64 B = 0, K = 0, KR = 0, steps = 0, plan_ne = 0, plan_nr = 0, plan_lo = 0, plan_hi = 0, plan_b_lo = 0, plan_b_hi = 0;
+    bool rowhead_ready = false;
+};
+
 struct okb_ctx {
     std::string in_path = "../data/FB15K/", out_path = "../data/FB15K/", err;
     i64 W = 1, bern = 0;
@@ -80,6 +88,12 @@ struct okb_ctx {
     bool dp_on = false;
     unsigned long long dp_epoch = 0;
     bool dp_pull = false;             // OKB_FLAG_DP_PULL: row owners pull partial rows from their peers instead of the reduce+push kernel
+    PlanSlot alt;                     // prefetched chunk (okb_chunk_prefetch)
+    bool alt_ready = false, in_prefetch = false;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    size_t saved_n = 0;
+    u64 *d_state_saved = nullptr;     // RNG streams as they were before the prefetched chunk was sampled
     bool pdl = true;                  // programmatic dependent launch between the grad and update kernels
     bool rowhead_ready = false;       // Adam: per-step row -> first sorted position map built for the planned chunk
     int ent_bits = 0, rel_bits = 0;
@@ -119,6 +133,9 @@ int okb_upload_test(okb_ctx *c);
 int okb_upload_lists(okb_ctx *c);
 bool okb_host_find(const okb_ctx *c, i64 h, i64 t, i64 r);
 i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(0, h, r) on stream 0
+
+// train.cu: forget a prefetched chunk (restores the RNG streams); every entry point that touches the streams calls it
+int okb_discard_prefetch(okb_ctx *c);
 
 // radix.cu
 int okb_sort_pairs(okb_ctx *c, const i32 *keys, i32 *keys_out, i32 *perm_out, i64 n, int bits, cudaStream_t s);

@@ -124,6 +124,7 @@ __global__ void narrow_kernel(const i64 *__restrict__ h, const i64 *__restrict__
 }
 
 static int push_state(okb_ctx *c) {
+    okb_discard_prefetch(c);
     if (c->d_state) { cudaFree(c->d_state); c->d_state = nullptr; }
     OKB_CUDA(c, cudaMalloc((void **)&c->d_state, sizeof(u64) * c->state.size()));
     OKB_CUDA(c, cudaMemcpy(c->d_state, c->state.data(), sizeof(u64) * c->state.size(), cudaMemcpyHostToDevice));
@@ -131,6 +132,7 @@ static int push_state(okb_ctx *c) {
     return 0;
 }
 static int pull_state(okb_ctx *c) {
+    okb_discard_prefetch(c);
     if (c->state_dirty) {
         OKB_CUDA(c, cudaDeviceSynchronize());
         OKB_CUDA(c, cudaMemcpy(c->state.data(), c->d_state, sizeof(u64) * c->state.size(), cudaMemcpyDeviceToHost));
@@ -190,6 +192,7 @@ int okb_sample(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT s
     if ((i64)c->state.size() != c->W) OKB_FAIL(c, OKB_ERR_STATE, "call randReset / okb_set_streams after setWorkThreads");
     if (B < 1 || k < 0 || kr < 0 || steps < 1) OKB_FAIL(c, OKB_ERR_ARG, "bad batch geometry");
     if (B * (1 + k + kr) * steps > 0x7fffffffLL / 4) OKB_FAIL(c, OKB_ERR_ARG, "batch too large for int32 indexing");
+    if (!c->in_prefetch) okb_discard_prefetch(c);          // a chunk sampled ahead is no longer the continuation of the streams
     cudaStream_t s = (cudaStream_t)stream;
     const i64 S = B * (1 + k + kr);
     if (c->batch.ensure(sizeof(i32) * 3 * S * steps)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (batch)");

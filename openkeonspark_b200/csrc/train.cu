@@ -2080,6 +2080,76 @@ int okb_dp_quiesce(okb_ctx *c, void *stream) {
     return 0;
 }
 
+/* ---- chunk pipeline: sampling and planning depend only on the RNG streams, never on the parameters, so the NEXT chunk of
+ * steps is sampled and planned on a side stream while the train kernels of the current chunk run.
+ *   okb_chunk_begin    makes `steps` sampled + planned steps current: a matching prefetched chunk is swapped in (the caller's
+ *                      stream waits for the side stream's event), otherwise they are produced on the caller's stream
+ *   okb_chunk_prefetch starts producing the following chunk on the side stream
+ * The RNG streams are saved before a prefetch; any call that observes or changes them (okb_sample, okb_get_streams,
+ * randReset ...) first discards the prefetched chunk and restores them, so results never depend on prefetching. */
+static void swap_slot(okb_ctx *c) {
+    PlanSlot &a = c->alt;
+    std::swap(c->batch, a.batch); std::swap(c->keys_ent, a.keys_ent); std::swap(c->perm_ent, a.perm_ent);
+    std::swap(c->rowseg_e, a.rowseg_e); std::swap(c->sort_tmp, a.sort_tmp); std::swap(c->hist, a.hist);
+    std::swap(c->B, a.B); std::swap(c->K, a.K); std::swap(c->KR, a.KR); std::swap(c->steps, a.steps);
+    std::swap(c->plan_ne, a.plan_ne); std::swap(c->plan_nr, a.plan_nr); std::swap(c->plan_lo, a.plan_lo); std::swap(c->plan_hi, a.plan_hi);
+    std::swap(c->plan_b_lo, a.plan_b_lo); std::swap(c->plan_b_hi, a.plan_b_hi); std::swap(c->rowhead_ready, a.rowhead_ready);
+}
+}  // extern "C"
+int okb_discard_prefetch(okb_ctx *c) {
+    if (!c->alt_ready) return 0;
+    c->alt_ready = false;
+    OKB_CUDA(c, cudaStreamSynchronize(c->side));
+    OKB_CUDA(c, cudaMemcpy(c->d_state, c->d_state_saved, sizeof(u64) * c->state.size(), cudaMemcpyDeviceToDevice));
+    c->state_dirty = true;
+    return 0;
+}
+extern "C" {
+int okb_chunk_begin(okb_ctx *c, INT B, INT k, INT kr, INT steps, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->alt_ready && c->alt.B == B && c->alt.K == k && c->alt.KR == kr && c->alt.steps == steps && !c->dp_on) {
+        OKB_CUDA(c, cudaStreamWaitEvent(s, c->ev_side, 0));
+        swap_slot(c);
+        c->alt_ready = false;
+        return 0;
+    }
+    int rc = okb_discard_prefetch(c);
+    if (rc) return rc;
+    if ((rc = okb_sample(c, B, k, kr, steps, 0, c->W, stream))) return rc;
+    if ((rc = okb_plan_steps(c, 0, steps, stream))) return rc;
+    return ensure_rowhead(c, s);
+}
+int okb_chunk_prefetch(okb_ctx *c, INT B, INT k, INT kr, INT steps, void *stream) {
+    if (c->dp_on || steps < 1) return 0;
+    int rc = okb_discard_prefetch(c);
+    if (rc) return rc;
+    if (!c->side) {
+        OKB_CUDA(c, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    }
+    if (!c->d_state_saved || c->saved_n != c->state.size()) {
+        if (c->d_state_saved) cudaFree(c->d_state_saved);
+        c->saved_n = c->state.size();
+        OKB_CUDA(c, cudaMalloc((void **)&c->d_state_saved, sizeof(u64) * std::max<size_t>(c->saved_n, 1)));
+    }
+    // the side stream starts after everything issued so far: the slot it overwrites was read by the previous chunk's steps
+    OKB_CUDA(c, cudaEventRecord(c->ev_main, (cudaStream_t)stream));
+    OKB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_main, 0));
+    OKB_CUDA(c, cudaMemcpyAsync(c->d_state_saved, c->d_state, sizeof(u64) * c->state.size(), cudaMemcpyDeviceToDevice, c->side));
+    swap_slot(c);
+    c->in_prefetch = true;
+    rc = okb_sample(c, B, k, kr, steps, 0, c->W, c->side);
+    if (!rc) rc = okb_plan_steps(c, 0, steps, c->side);
+    if (!rc) rc = ensure_rowhead(c, c->side);
+    c->in_prefetch = false;
+    swap_slot(c);
+    if (rc) return rc;
+    OKB_CUDA(c, cudaEventRecord(c->ev_side, c->side));
+    c->alt_ready = true;
+    return 0;
+}
+
 /* ---- peer memory: allocations other processes of the box map over NVLink (CUDA IPC) */
 int okb_peer_alloc(okb_ctx *c, INT bytes, void **ptr, unsigned char *handle64) {
     if (bytes <= 0 || !ptr || !handle64) OKB_FAIL(c, OKB_ERR_ARG, "bad peer allocation request");
