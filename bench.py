@@ -32,6 +32,7 @@ import numpy as np  # noqa: E402
 MODEL, DIM, OPT, NBATCHES, NEG, MARGIN, ALPHA, BERN, W_PER_GPU = "TransH", 100, "Adam", 100, 1, 1.0, 0.001, 0, 8
 SHAPE = "fb15k"
 METRIC = "train triples/s (+ link-pred queries/s)"
+CPU_LP = None
 
 
 def peaks():
@@ -117,7 +118,7 @@ class native_stdout_to_stderr:
         os.close(self.saved)
 
 
-def cpu_reference_path(g, steps, warmup, B, threads):
+def cpu_reference_path(g, steps, warmup, B, threads, budget_s=None):
     """The reference's serial loop on host cores: sampling() by the reference's own Base.so
     (oracle/_ref, compiled from /root/reference/base/Base.cpp; the C restatement if absent) followed
     by the TF-graph step restated in torch-CPU (TensorFlow 1.x is not installable).  Returns
@@ -132,7 +133,7 @@ def cpu_reference_path(g, steps, warmup, B, threads):
     datagen.write_dataset(g, d)
     kind = "port"
     if os.path.exists(harness.REF_SO):
-        ref = harness.RefLib().init(d, bern=BERN, W=min(threads, 8), test=False)
+        ref = harness.RefLib().init(d, bern=BERN, W=min(threads, 8), test=True, ontology=True)   # a missing ontology file is fine (Reader.h)
         sample = lambda: ref.sampling(B, NEG, 0)
         native = "reference Base.so sampling() at workThreads=%d" % min(threads, 8)
     else:
@@ -142,13 +143,33 @@ def cpu_reference_path(g, steps, warmup, B, threads):
         native = "C restatement of sampling() (1 thread)"
     tr = models_ref.Trainer(MODEL, params_for(g, np.random.default_rng(0)), margin=MARGIN, lr=ALPHA, opt=OPT)
     ts = []
-    for i in range(warmup + steps):
+    i, t_start = 0, time.perf_counter()
+    while i < warmup + steps or (budget_s is not None and time.perf_counter() - t_start < budget_s):
         t0 = time.perf_counter()
         h, t, r, _ = sample()
         tr.step(h, t, r, B, NEG, 0)
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
+        i += 1
+    steps = len(ts)
     sec = sum(ts) / len(ts)
+    # link prediction on the CPU the way distribute_training.py:464-590 does it: getHead/TailBatch -> predict -> testHead/Tail,
+    # one query at a time, single-threaded native ranking (the reference parallelises it only across Spark workers)
+    global CPU_LP
+    CPU_LP = None
+    if kind == "port" and os.path.exists(harness.REF_SO):
+        try:
+            nq, t0 = 0, time.perf_counter()
+            while nq < 16 or time.perf_counter() - t0 < 3.0:
+                i = (nq // 2) * 97 % ref.L.getTestTotal()
+                side = nq % 2
+                ch, ct, cr = ref.candidates(side, i)
+                ref.rank(side, i, tr.predict(ch, ct, cr))
+                nq += 1
+            CPU_LP = {"queries_per_s": nq / (time.perf_counter() - t0), "queries": nq,
+                      "what": "reference Base.so getHead/TailBatch + testHead/testTail (1 thread) around the torch-CPU predict_def (%d threads)" % threads}
+        except Exception as e:  # noqa: BLE001
+            CPU_LP = {"error": str(e)}
     desc = "%d steps of B=%d: %s + torch-CPU fp32 restatement of TransH loss_def/Adam (%d threads)" % (steps, B, native, threads)
     return B / sec, desc, sec, kind
 
@@ -167,7 +188,7 @@ def run_reference(args):
             "warmup": min(args.warmup, 3), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "TransH dim=100 Adam k=1 margin=1, FB15K-shaped 14951/1345/483142, B=4831 (nbatches=100)"},
-            "cpu_baseline": {"value": val, "unit": "triples/s", "cores": cores, "kind": kind, "sample": desc},
+            "cpu_baseline": {"value": val, "unit": "triples/s", "cores": cores, "kind": kind, "sample": desc, "link_prediction": CPU_LP},
             "e2e": {"value": val, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -384,8 +405,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         with native_stdout_to_stderr():
-            val, desc, sec, kind = cpu_reference_path(g, 12, 2, B_local, cores)
-        cpu = {"value": val, "unit": "triples/s", "cores": cores, "kind": kind, "sample": desc}
+            val, desc, sec, kind = cpu_reference_path(g, 12, 2, B_local, cores, budget_s=10.0)     # ~10 s of CPU work
+        cpu = {"value": val, "unit": "triples/s", "cores": cores, "kind": kind, "sample": desc, "link_prediction": CPU_LP}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
