@@ -365,9 +365,9 @@ def main():
             kern[name] = {"ms": ms / cnt, "gbs": nbytes / (ms / cnt * 1e-3) / 1e9, "bytes": nbytes}
     dom = max(kern, key=lambda n: kern[n]["ms"]) if kern else None
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this command
-    # (profiles/r01e_ncu_full_train_kernels.txt; ncu invalidates the caches before every kernel replay, so the gradient
+    # (profiles/r01f_ncu_full_train_kernels.txt; ncu invalidates the caches before every kernel replay, so the gradient
     # rows the update kernel normally finds in L2 are counted as DRAM reads there; updated rows stay in L2 as dirty lines)
-    NCU_TRAFFIC = {"update": 31213056 + 256, "grad": 5256704 + 0}
+    NCU_TRAFFIC = {"update": 31213312 + 0, "grad": 5256192 + 0}
     roofline = None
     if dom:
         roofline = {"kernel": "adam_tile_kernel" if dom == "update" else "grad_k1_kernel", "bound": "hbm", "achieved": kern[dom]["gbs"],
