@@ -163,12 +163,12 @@ __global__ void relvec_kernel(okb_model m, const i32 *__restrict__ grp_rel, floa
 // projection e . M_r changes the dimension).  aux: TransH n_hat / TransD rel_transfer; et_row: TransD
 // ent_transfer[e]; Msm: TransR matrix of the group, row-major [Din][D] in shared memory.
 __device__ __forceinline__ void canon_row(int model, const float *in, float *out, const float *aux, const float *et_row,
-                                          const float *Msm, int Din, int D) {
+                                          const float *Msm, int Din, int D, const float *pre_dot = nullptr) {
     if (model == OKB_TRANSH) {
         const float dh = c_dot(in, 1, aux, 1, D);
         for (int d = 0; d < D; d++) out[d] = __fsub_rn(in[d], __fmul_rn(dh, aux[d]));
     } else if (model == OKB_TRANSD) {
-        const float ch = c_dot(in, 1, et_row, 1, D);
+        const float ch = pre_dot ? *pre_dot : c_dot(in, 1, et_row, 1, D);      // e . e_transfer does not depend on the relation
         for (int d = 0; d < D; d++) out[d] = __fadd_rn(in[d], __fmul_rn(ch, aux[d]));
     } else if (model == OKB_TRANSR) {
         for (int k = 0; k < D; k++) {
@@ -189,8 +189,21 @@ struct CandArgs {
     const float *rv;           // [G][2][D]
     const i32 *grp_rel;        // relation of each group (TransR: selects M_r)
     float *out;                // [ntab][D][ncol]
+    const float *entdot;       // TransD: canonical e . ent_transfer[e] per candidate column, computed once per call
     i32 j0, ncol, E, ntab;
 };
+// TransD: the dot e . e_transfer of every candidate (sequential canonical order), shared by all relation groups
+__global__ void entdot_kernel(okb_model m, float *out, i32 j0, i32 ncol, i32 E) {
+    const i32 col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    const i32 j = j0 + col;
+    float s = 0.f;
+    if (j < E) {
+        const float *e = m.ent + (i64)j * m.ent_dim, *t = m.ent_aux + (i64)j * m.ent_dim;
+        for (int d = 0; d < m.ent_dim; d++) s = __fadd_rn(s, __fmul_rn(__ldg(e + d), __ldg(t + d)));
+    }
+    out[col] = s;
+}
 // dynamic shared memory: per warp 32 input rows [Din+1] (+32 rows of a second array: TransD ent_transfer /
 // TransR projected output [D+1]); per block the group's aux vector [D] (+ TransR: M_r [Din*D])
 __global__ void __launch_bounds__(128) cand_kernel(CandArgs a) {
@@ -198,7 +211,7 @@ __global__ void __launch_bounds__(128) cand_kernel(CandArgs a) {
     const int wpb = blockDim.x >> 5;
     const int Din = a.m.ent_dim, D = a.m.rel_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int sin = Din + 1, s2 = (a.m.model == OKB_TRANSR ? D : Din) + 1;
-    const bool second = a.m.model == OKB_TRANSD || a.m.model == OKB_TRANSR;
+    const bool second = (a.m.model == OKB_TRANSD && !a.entdot) || a.m.model == OKB_TRANSR;
     const size_t per_warp = (size_t)32 * sin + (second ? (size_t)32 * s2 : 0);
     float *rows = sm + (size_t)w * per_warp;
     float *rows2 = rows + 32 * sin;
@@ -216,12 +229,13 @@ __global__ void __launch_bounds__(128) cand_kernel(CandArgs a) {
         const int rr = idx / Din, d = idx - rr * Din;
         const i32 j = jbase + rr;
         rows[rr * sin + d] = j < a.E ? a.m.ent[(i64)j * Din + d] : 0.f;
-        if (a.m.model == OKB_TRANSD) rows2[rr * s2 + d] = j < a.E ? a.m.ent_aux[(i64)j * Din + d] : 0.f;
+        if (a.m.model == OKB_TRANSD && !a.entdot) rows2[rr * s2 + d] = j < a.E ? a.m.ent_aux[(i64)j * Din + d] : 0.f;
     }
     __syncthreads();
     const i32 j = jbase + lane;
     float *res = a.m.model == OKB_TRANSR ? rows2 + lane * s2 : rows + lane * sin;
-    if (j < a.E) canon_row(a.m.model, rows + lane * sin, res, aux, rows2 + lane * s2, Msm, Din, D);
+    if (j < a.E) canon_row(a.m.model, rows + lane * sin, res, aux, rows2 + lane * s2, Msm, Din, D,
+                           a.entdot ? a.entdot + (jbase - a.j0 + lane) : nullptr);
     __syncwarp();
     const i32 col = jbase - a.j0 + lane;
     if (col < a.ncol)
@@ -692,7 +706,9 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
     }
     const bool second = m->model == OKB_TRANSD || m->model == OKB_TRANSR;
     const size_t s2 = (m->model == OKB_TRANSR ? D : Din) + 1;
-    const size_t warp_c = (size_t)32 * (Din + 1) + (second ? 32 * s2 : 0), warp_q = 2 * warp_c;
+    const size_t warp_q = 2 * ((size_t)32 * (Din + 1) + (second ? 32 * s2 : 0));
+    // candidate kernel: TransD's second staged array (ent_transfer rows) is replaced by one precomputed dot per candidate
+    const size_t warp_c = (size_t)32 * (Din + 1) + (m->model == OKB_TRANSR ? 32 * s2 : 0);
     const size_t blk_c = ((D + 3) & ~3) + (m->model == OKB_TRANSR ? (size_t)Din * D : 0);
     int wpb_c = 4, wpb_q = 4;
     while (wpb_c > 1 && sizeof(float) * (wpb_c * warp_c + blk_c) > 160 * 1024) wpb_c >>= 1;
@@ -713,7 +729,7 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         for (i64 g = 0; g < G; g++) { gblk[g] = (i32)NBq; NBq += (gqhi[g0 + g] - gqlo[g0 + g] + QB - 1) / QB; }
         const size_t o_cand = take(tab_bytes * ntab), o_rv = take(sizeof(float) * G * 2 * D), o_qa = take(sizeof(float) * NBq * QB * D),
                      o_qt = take(sizeof(float) * NBq * QB * D), o_ref = take(sizeof(float) * nq), o_thr = take(sizeof(float) * nq),
-                     o_tf = take((size_t)G * ncol), o_grel = take(sizeof(i32) * G), o_gqlo = take(sizeof(i32) * G),
+                     o_ed = take(sizeof(float) * ncol), o_tf = take((size_t)G * ncol), o_grel = take(sizeof(i32) * G), o_gqlo = take(sizeof(i32) * G),
                      o_gqhi = take(sizeof(i32) * G), o_gblk = take(sizeof(i32) * G), o_qg = take(sizeof(i32) * nq);
         if (c->rank_ws.ensure(off)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (ranking workspace)");
         char *ws = c->rank_ws.as<char>();
@@ -737,6 +753,12 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
         CandArgs ca;
         ca.m = *m; ca.rv = (const float *)(ws + o_rv); ca.out = (float *)(ws + o_cand); ca.grp_rel = (const i32 *)(ws + o_grel);
         ca.j0 = (i32)j0; ca.ncol = (i32)ncol; ca.E = (i32)c->E; ca.ntab = (i32)ntab;
+        ca.entdot = nullptr;
+        if (m->model == OKB_TRANSD) {
+            entdot_kernel<<<(unsigned)((ncol + 127) / 128), 128, 0, s>>>(*m, (float *)(ws + o_ed), (i32)j0, (i32)ncol, (i32)c->E);
+            OKB_LAUNCHED(1);
+            ca.entdot = (const float *)(ws + o_ed);
+        }
         if (m->model == OKB_TRANSR && c->transr_tc && okb_transr_tc_supported(m)) {
             int rc2 = okb_transr_project_tc(c, m, (const i32 *)(ws + o_grel), G, (float *)(ws + o_cand), j0, ncol, s);
             if (rc2) return rc2;
