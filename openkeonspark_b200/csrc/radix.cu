@@ -8,16 +8,18 @@
 #define RADIX_BITS 8
 #define RADIX 256
 #define SORT_THREADS 256
-#define SORT_ITEMS 8
-#define SORT_TILE (SORT_THREADS * SORT_ITEMS)
+// items per thread: 8 for large sorts; 2 when a whole sort is only a few tiles (a single planned step: 24 k pairs = 12 tiles
+// of 2,048 would leave 136 SMs idle for the four kernels of a pass)
 
 // Segmented form: the input is `nseg` independent segments of `seg` items each (one per planned train step),
 // every segment is cut into T tiles of SORT_TILE items, and the tile histograms are laid out
 // [segment][digit][tile].  An exclusive scan of that array in storage order, plus segment * seg, is then each
 // (segment, digit, tile)'s output position — segments never mix, so one sort call plans a whole chunk of steps
 // with the pass count of ONE step's key range.
+template <int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS) radix_hist(const i32 *__restrict__ keys, i32 *__restrict__ ghist,
                                                            i32 seg, i32 T, i32 shift) {
+    constexpr int SORT_ITEMS = ITEMS, SORT_TILE = SORT_THREADS * ITEMS;
     __shared__ i32 h[RADIX];
     h[threadIdx.x] = 0;
     __syncthreads();
@@ -86,10 +88,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(i32 *__restrict__ a, 
 
 // Stable scatter.  Item order inside a tile: warp-contiguous chunks of 256, striped across lanes
 // (item = warp*256 + j*32 + lane), so ranking rounds j = 0..7 visit items in ascending index.
+template <int ITEMS>
 __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const i32 *__restrict__ keys, const i32 *__restrict__ vals,
                                                               i32 *__restrict__ keys_out, i32 *__restrict__ vals_out,
                                                               const i32 *__restrict__ gscan, i32 seg, i32 T, i32 shift,
                                                               i32 iota_vals) {
+    constexpr int SORT_ITEMS = ITEMS, SORT_TILE = SORT_THREADS * ITEMS;
     __shared__ i32 wh[SORT_THREADS / 32][RADIX];
     const i32 lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (i32 i = threadIdx.x; i < (SORT_THREADS / 32) * RADIX; i += SORT_THREADS) (&wh[0][0])[i] = 0;
@@ -138,6 +142,8 @@ __global__ void __launch_bounds__(SORT_THREADS) radix_scatter(const i32 *__restr
 int okb_sort_pairs_seg(okb_ctx *c, const i32 *keys, i32 *keys_out, i32 *perm_out, i64 seg, i64 nseg, int bits, cudaStream_t s) {
     const i64 n = seg * nseg;
     if (n <= 0) return 0;
+    const bool small = n <= 262144;
+    const i64 SORT_TILE = SORT_THREADS * (small ? 2 : 8);
     const i32 T = (i32)((seg + SORT_TILE - 1) / SORT_TILE);
     const i64 nblk = (i64)T * nseg, len = (i64)RADIX * T;
     const i32 sblk = (i32)((len + SCAN_TILE - 1) / SCAN_TILE);
@@ -152,10 +158,12 @@ int okb_sort_pairs_seg(okb_ctx *c, const i32 *keys, i32 *keys_out, i32 *perm_out
     i32 *dst_k = (passes & 1) ? keys_out : tk, *dst_v = (passes & 1) ? perm_out : tv;
     for (int p = 0; p < passes; p++) {
         const i32 shift = p * RADIX_BITS;
-        radix_hist<<<(unsigned)nblk, SORT_THREADS, 0, s>>>(src_k, gh, (i32)seg, T, shift);
+        if (small) radix_hist<2><<<(unsigned)nblk, SORT_THREADS, 0, s>>>(src_k, gh, (i32)seg, T, shift);
+        else radix_hist<8><<<(unsigned)nblk, SORT_THREADS, 0, s>>>(src_k, gh, (i32)seg, T, shift);
         scan_reduce<<<dim3(sblk, (unsigned)nseg), SCAN_THREADS, 0, s>>>(gh, bsum, (i32)len);
         scan_apply<<<dim3(sblk, (unsigned)nseg), SCAN_THREADS, 0, s>>>(gh, bsum, (i32)len, (i32)seg);
-        radix_scatter<<<(unsigned)nblk, SORT_THREADS, 0, s>>>(src_k, src_v, dst_k, dst_v, gh, (i32)seg, T, shift, p == 0);
+        if (small) radix_scatter<2><<<(unsigned)nblk, SORT_THREADS, 0, s>>>(src_k, src_v, dst_k, dst_v, gh, (i32)seg, T, shift, p == 0);
+        else radix_scatter<8><<<(unsigned)nblk, SORT_THREADS, 0, s>>>(src_k, src_v, dst_k, dst_v, gh, (i32)seg, T, shift, p == 0);
         OKB_LAUNCHED(4);
         src_k = dst_k; src_v = dst_v;
         if (dst_k == keys_out) { dst_k = tk; dst_v = tv; } else { dst_k = keys_out; dst_v = perm_out; }
