@@ -1,5 +1,6 @@
+"""Link-prediction timing (not the driver bench): python tools/lp_bench.py MODEL DIM N_TEST_TRIPLES HEADS [tc]\nPrints rank-kernel / prep milliseconds (CUDA events) and queries/s on the FB15K-shaped graph."""
 import sys, time, ctypes, numpy as np, torch, contextlib, io
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import os; ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import openkeonspark_b200 as okb
 from openkeonspark_b200 import datagen
 from conftest import make_params
