@@ -283,7 +283,10 @@ enum { OKB_FLAG_TRANSR_TC = 1,
         * peers' gradient buffers (peer loads) instead of running the reduce+push kernel (peer stores).  Bit-identical
         * results; measured 65 vs 40 us per step at 2 GPUs — dependent loads over NVLink cost several us each — so it is
         * kept for A/B runs only.  Needs the arena's optional plan / gradient slices (okb_dp.plan_steps > 0). */
-       OKB_FLAG_DP_PULL = 7 };
+       OKB_FLAG_DP_PULL = 7,
+       /* OKB_FLAG_GRAD_SINGLE_WARP = 8 (default off): the generic grad kernel never splits a positive's negatives over several
+        * warps (A/B runs; the split changes the association of the shared rows' gradient sums). */
+       OKB_FLAG_GRAD_SINGLE_WARP = 8 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:

@@ -383,18 +383,25 @@ struct GradArgs {
 };
 
 // ------------------------------------------------------------------------------------------ grad
-template <int MODEL, int VW, int NV>
-__global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(GradArgs a) {
+// WPPMAX = 1: one warp per positive (GRAD_WARPS positives per block).  WPPMAX = 4: ONE positive per block and blockDim / 32
+// (2..4) warps share its entity negatives — small batches with many negatives (WN18-shaped: B = 1,414, k = 10) otherwise
+// leave most warp slots empty while each warp walks its negatives one after the other.  Every warp recomputes the
+// positive's forward pass, takes the negatives m = w, w + wpp, ..., and warp 0 adds the other warps' accumulators in warp
+// order (through shared memory) before the positive's own backward pass.
+template <int MODEL, int VW, int NV, int WPPMAX>
+__global__ void __launch_bounds__(WPPMAX == 1 ? GRAD_WARPS * 32 : WPPMAX * 32, WPPMAX == 1 ? GRAD_MIN_BLOCKS : 5) grad_kernel(GradArgs a) {
     constexpr int N = VW * NV;
+    extern __shared__ float grad_sm[];
     const int lane = threadIdx.x & 31;
-    const i32 b = a.b_lo + blockIdx.x * GRAD_WARPS + (threadIdx.x >> 5);
+    const int wpp = WPPMAX == 1 ? 1 : (int)(blockDim.x >> 5), wid = WPPMAX == 1 ? 0 : (int)(threadIdx.x >> 5);
+    const i32 b = WPPMAX == 1 ? a.b_lo + blockIdx.x * GRAD_WARPS + (threadIdx.x >> 5) : a.b_lo + (i32)blockIdx.x;
     if (b >= a.b_hi) return;
     const int D = a.m.ent_dim;
     const int ce = MODEL == OKB_TRANSD ? 2 * D : D, cr = MODEL == OKB_TRANSE ? D : 2 * D;
     const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
     // entity that replaces a side in negative m (Base.cpp:118-126): the new head if the head changed, else the tail
     i32 nh = 0, nt = 0;
-    if (a.k > 0) { nh = a.bh[b + a.B]; nt = a.bt[b + a.B]; }
+    if (wid < a.k) { nh = a.bh[b + (wid + 1) * a.B]; nt = a.bt[b + (wid + 1) * a.B]; }
     // The batch ids do not depend on the previous update kernel; the table rows do.  Dependents (this step's update
     // kernel) are released only after the wait, so they can never start before the previous update has finished.
     pdl_wait();
@@ -422,7 +429,7 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     rel_load<MODEL, VW, NV>(Rp, a.m, pr, lane);            // all gathers of the group go out before the first reduction
     ent_load<MODEL, VW, NV>(Hp, a.m, ph, lane);
     ent_load<MODEL, VW, NV>(Tp, a.m, pt, lane);
-    if (a.k > 0) ent_load<MODEL, VW, NV>(Nx, a.m, nh != ph ? nh : nt, lane);
+    if (wid < a.k) ent_load<MODEL, VW, NV>(Nx, a.m, nh != ph ? nh : nt, lane);
     rel_math<MODEL, N>(Rp);
     ent_math<MODEL, N>(Hp, Rp);
     ent_math<MODEL, N>(Tp, Rp);
@@ -436,11 +443,11 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
     float hinge_sum = 0.f;
     i32 active = 0;
 
-    for (i32 m = 0; m < a.k; m++) {                        // entity negatives (Base.cpp:113-131)
+    for (i32 m = wid; m < a.k; m += wpp) {                 // entity negatives (Base.cpp:113-131)
         const i32 cnh = nh, cnt_ = nt;
         EntS<MODEL, N> Nn = Nx;
-        if (m + 1 < a.k) {                                 // next negative's row is in flight while this one is scored
-            const i32 at = b + (m + 2) * a.B;
+        if (m + wpp < a.k) {                               // next negative's row is in flight while this one is scored
+            const i32 at = b + (m + wpp + 1) * a.B;
             nh = a.bh[at]; nt = a.bt[at];
             ent_load<MODEL, VW, NV>(Nx, a.m, nh != ph ? nh : nt, lane);
         }
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
         }
         put_ent<MODEL, VW, NV>(ge + (i64)(2 + m) * ce, gnew, D, lane);
     }
-    for (i32 m = 0; m < a.kr; m++) {                       // relation negatives (Base.cpp:133-139)
+    for (i32 m = 0; m < (wid == 0 ? a.kr : 0); m++) {      // relation negatives (Base.cpp:133-139): warp 0
         const i32 nr = a.br[b + (1 + a.k + m) * a.B];
         RelG<MODEL, N> gnew;
         gnew.zero();
@@ -488,6 +495,38 @@ __global__ void __launch_bounds__(GRAD_WARPS * 32, GRAD_MIN_BLOCKS) grad_kernel(
             if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rp, gp, -a.w, accH, accT, accR); }
         }
         put_rel<MODEL, VW, NV>(gr + (i64)(1 + m) * cr, gnew, D, lane);
+    }
+    if (WPPMAX > 1 && wpp > 1) {                           // warps 1.. hand their accumulators to warp 0, which adds them in warp order
+        constexpr int F = 2 * (MODEL == OKB_TRANSD ? 2 : 1) + (MODEL == OKB_TRANSE ? 1 : 2);      // fragments per warp
+        float *slab = grad_sm + (size_t)(wid > 0 ? wid - 1 : 0) * (F * 32 * N + 64);
+        if (wid > 0) {
+            int f = 0;
+            auto out = [&](const float *v) {
+#pragma unroll
+                for (int i = 0; i < N; i++) slab[(f * 32 + lane) * N + i] = v[i];
+                f++;
+            };
+            out(accH.d); out(accT.d); out(accR.d);
+            if (MODEL == OKB_TRANSD) { out(accH.da); out(accT.da); }
+            if (MODEL != OKB_TRANSE) out(accR.da);
+            if (lane == 0) { slab[F * 32 * N] = hinge_sum; slab[F * 32 * N + 1] = (float)active; }
+        }
+        __syncthreads();
+        if (wid > 0) return;
+        for (int w = 1; w < wpp; w++) {
+            const float *sl = grad_sm + (size_t)(w - 1) * (F * 32 * N + 64);
+            int f = 0;
+            auto in = [&](float *v) {
+#pragma unroll
+                for (int i = 0; i < N; i++) v[i] += sl[(f * 32 + lane) * N + i];
+                f++;
+            };
+            in(accH.d); in(accT.d); in(accR.d);
+            if (MODEL == OKB_TRANSD) { in(accH.da); in(accT.da); }
+            if (MODEL != OKB_TRANSE) in(accR.da);
+            hinge_sum += sl[F * 32 * N];
+            active += (i32)sl[F * 32 * N + 1];
+        }
     }
     if (active) score_bw<MODEL, N>(Hp, Tp, Rp, gp, a.w * (float)active, accH, accT, accR);
     put_ent<MODEL, VW, NV>(ge, accH, D, lane);
@@ -1362,16 +1401,30 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
 #define CALL_GRAD(VW, NV)                                                                              \
-    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV>, a);          \
-    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV>, a);     \
-    else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV>, a)
+    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV, 1>, a);       \
+    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV, 1>, a);  \
+    else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV, 1>, a)
+#define CALL_GRADW(VW, NV)                                                                             \
+    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV, 4>, a);       \
+    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV, 4>, a);  \
+    else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV, 4>, a)
 #define CALL_GRAD1(VW, NV)                                                                             \
     if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSE, VW, NV>, a);       \
     else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSH, VW, NV>, a);  \
     else cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSD, VW, NV>, a)
     const bool k1 = c->K == 1 && c->KR == 0 && !c->grad_generic && a.npf == 0;
     if (k1) { cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32); }
-    { ProfScope ps(c, PROF_GRAD, s); if (k1) { DISPATCH_LAYOUT(vw, nv, CALL_GRAD1); } else { DISPATCH_LAYOUT(vw, nv, CALL_GRAD); } }
+    // small batches with several negatives: 2..4 warps per positive, as many as fill ~20 warp slots per SM
+    int wpp = 1;
+    // (a function of the GLOBAL batch, so that a data-parallel rank's slice is computed exactly like the same positives on one GPU)
+    if (!k1 && c->K >= 2 && !c->grad_single_warp) wpp = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(4, c->K), (i64)148 * 20 / std::max<i64>(1, c->B)));
+    if (wpp > 1) {
+        const int N = vw * nv, F = 2 * (m->model == OKB_TRANSD ? 2 : 1) + (m->model == OKB_TRANSE ? 1 : 2);
+        cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32 * wpp);
+        cfg.dynamicSmemBytes = sizeof(float) * (size_t)(wpp - 1) * (F * 32 * N + 64);
+    }
+    { ProfScope ps(c, PROF_GRAD, s);
+      if (k1) { DISPATCH_LAYOUT(vw, nv, CALL_GRAD1); } else if (wpp > 1) { DISPATCH_LAYOUT(vw, nv, CALL_GRADW); } else { DISPATCH_LAYOUT(vw, nv, CALL_GRAD); } }
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
     return 0;
