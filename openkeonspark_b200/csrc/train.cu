@@ -2,19 +2,29 @@
 // (TransE.py:26-51, TransH.py:33-69, TransD.py:46-84 on the batch layout of Model.py:55-74)
 // plus optimizer.minimize (distribute_training.py:94-101), as three phases:
 //
-//   plan   (integer)  gradient-row keys of the batch -> stable radix sort -> (sorted keys, perm)
-//   grad   (fused)    one warp per positive: 128-bit gathers of the h/t/r rows (+ the model's
-//                     auxiliary rows), projection, l2-normalise, L1, margin hinge against each of
-//                     its negatives, and the backward pass; rows shared between a positive and its
-//                     negatives (the uncorrupted side and the relation) are gathered ONCE and their
-//                     gradients are accumulated in registers, so a positive group emits exactly
-//                     (2 + k) entity gradient rows and (1 + kr) relation gradient rows
-//   update (fused)    one warp per distinct table row: sum its gradient rows in sorted (slot) order
-//                     — a fixed fp32 order, so runs and replicas are bit-identical — and apply SGD
-//                     or the TF1 sparse-Adam rule in the same pass
+//   plan   (integer)  gradient-row keys of the batch -> segmented stable radix sort (radix.cu) -> per step
+//                     (sorted keys, slot permutation, row map {first, end, slot0, slot1} per table row);
+//                     whole chunks of steps are planned at once and, through okb_chunk_prefetch, one chunk
+//                     ahead on a side stream (sampling and planning never depend on the parameters)
+//   grad   (fused)    one warp per positive: 128-bit gathers of the h/t/r rows (+ the model's auxiliary
+//                     rows) issued before the first reduction, projection, l2-normalise, L1, margin hinge
+//                     against each of its negatives, and the backward pass; rows shared between a positive
+//                     and its negatives are gathered ONCE and their gradients accumulate in registers, so a
+//                     positive group emits exactly (2 + k) entity and (1 + kr) relation gradient rows.
+//                     grad_k1_kernel: the k = 1, kr = 0 batch with interleaved reduction chains;
+//                     grad_kernel<..., 4>: 2-4 warps per positive for small batches with many negatives
+//   update (fused)    segmented sum of the gradient rows in sorted (slot) order — a fixed fp32 order, so runs
+//                     and replicas are bit-identical — and SGD (sgd_kernel: one warp per touched row) or the
+//                     TF1 dense-decay Adam rule over every row (adam_tile_kernel: one 256-vector tile of one
+//                     table per CTA) in the same pass
 //
-// Roofline: HBM-bound gather/scatter of fp32 rows; no dense contraction, so no tensor cores here
-// (TransR's projection lives in transr.cu).
+// The grad and update kernels are chained with programmatic dependent launch (griddepcontrol): each one's
+// parameter-independent prologue overlaps the tail of its predecessor.
+// The last section is the owner-sharded data-parallel form of the update over NVLink peer memory
+// (dp_reduce_push_kernel / dp_owner_kernel; dp_pull_kernel as the measured-slower alternative).
+//
+// Roofline: latency-bound gathers and an HBM/L2 stream of fp32 rows; no dense contraction, so no tensor cores
+// here (TransR's projection lives in transr.cu / transr_tc.cu).
 #include <algorithm>
 #include <cstring>
 
