@@ -171,10 +171,39 @@ __device__ __forceinline__ void canon_row(int model, const float *in, float *out
         const float ch = pre_dot ? *pre_dot : c_dot(in, 1, et_row, 1, D);      // e . e_transfer does not depend on the relation
         for (int d = 0; d < D; d++) out[d] = __fadd_rn(in[d], __fmul_rn(ch, aux[d]));
     } else if (model == OKB_TRANSR) {
-        for (int k = 0; k < D; k++) {
-            float a = 0.f;
-            for (int d = 0; d < Din; d++) a = __fadd_rn(a, __fmul_rn(in[d], Msm[d * D + k]));
-            out[k] = a;
+        if ((D & 3) == 0 && (((size_t)Msm) & 15) == 0) {
+            // four outputs per pass over the input row: one broadcast 128-bit load of M_r per 4 multiply-adds instead of one
+            // 32-bit load each; every output still accumulates d = 0..Din-1 in order with individually rounded operations
+            int k = 0;
+            for (; k + 8 <= D; k += 8) {                       // eight outputs per pass where they fit
+                float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (int d = 0; d < Din; d++) {
+                    const float x = in[d];
+                    const float4 m0 = *reinterpret_cast<const float4 *>(Msm + d * D + k), m1 = *reinterpret_cast<const float4 *>(Msm + d * D + k + 4);
+                    a[0] = __fadd_rn(a[0], __fmul_rn(x, m0.x)); a[1] = __fadd_rn(a[1], __fmul_rn(x, m0.y));
+                    a[2] = __fadd_rn(a[2], __fmul_rn(x, m0.z)); a[3] = __fadd_rn(a[3], __fmul_rn(x, m0.w));
+                    a[4] = __fadd_rn(a[4], __fmul_rn(x, m1.x)); a[5] = __fadd_rn(a[5], __fmul_rn(x, m1.y));
+                    a[6] = __fadd_rn(a[6], __fmul_rn(x, m1.z)); a[7] = __fadd_rn(a[7], __fmul_rn(x, m1.w));
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) out[k + q] = a[q];
+            }
+            for (; k < D; k += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int d = 0; d < Din; d++) {
+                    const float x = in[d];
+                    const float4 m4 = *reinterpret_cast<const float4 *>(Msm + d * D + k);
+                    a0 = __fadd_rn(a0, __fmul_rn(x, m4.x)); a1 = __fadd_rn(a1, __fmul_rn(x, m4.y));
+                    a2 = __fadd_rn(a2, __fmul_rn(x, m4.z)); a3 = __fadd_rn(a3, __fmul_rn(x, m4.w));
+                }
+                out[k] = a0; out[k + 1] = a1; out[k + 2] = a2; out[k + 3] = a3;
+            }
+        } else {
+            for (int k = 0; k < D; k++) {
+                float a = 0.f;
+                for (int d = 0; d < Din; d++) a = __fadd_rn(a, __fmul_rn(in[d], Msm[d * D + k]));
+                out[k] = a;
+            }
         }
     }
     const float inv = c_inv_norm(c_dot(out, 1, out, 1, D));
