@@ -202,7 +202,7 @@ def main():
     ap.add_argument("--impl", default="okb200")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--lp-queries", type=int, default=4096)
+    ap.add_argument("--lp-queries", type=int, default=1 << 30, help="test triples ranked for the link-prediction figure (default: the whole test set)")
     ap.add_argument("--no-kernel-events", action="store_true", help="do not record per-kernel CUDA events (no roofline object)")
     ap.add_argument("--plan-ahead", type=int, default=64)
     args = ap.parse_args()
