@@ -2002,7 +2002,6 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         if ((rc = plan_steps(c, step_lo, c->steps, P.b_lo, P.b_hi, stream))) return rc;
     }
     if ((rc = ensure_rowhead(c, s))) return rc;
-    const bool was_pdl = c->pdl;
     cudaLaunchAttribute pat[1];
     pat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pat[0].val.programmaticStreamSerializationAllowed = 1;
@@ -2012,7 +2011,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         const unsigned long long epoch = c->dp_epoch + 1;
         const unsigned long long *xflags = (const unsigned long long *)(own + P.off_flags) + DP_FLAG_X;
         if ((rc = launch_grad(c, m, hp + i, step, P.b_lo, P.b_hi, P.b_lo, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(),
-                              xflags, c->dp_epoch, P.world, stream))) { c->pdl = was_pdl; return rc; }
+                              xflags, c->dp_epoch, P.world, stream))) return rc;
         UpdArgs a;
         fill_upd_args(c, m, hp + i, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), a);
         // the choice must be the same on every rank: judge hub rows by the LARGEST rank's share of the batch
@@ -2028,7 +2027,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
                 const i64 lo = std::min<i64>(c->B, q * chunk), hi = std::min<i64>(c->B, (q + 1) * chunk);
                 o.bl[q] = (i32)(hi - lo); o.nloc[q] = (i32)((hi - lo) * (NE + NR)); o.nes[q] = (i32)((hi - lo) * NE);
             }
-            if (o.bl[P.rank] != (i32)Bl) { c->pdl = was_pdl; OKB_FAIL(c, OKB_ERR_ARG, "rank's positive range does not follow the stream-slice geometry"); }
+            if (o.bl[P.rank] != (i32)Bl) { OKB_FAIL(c, OKB_ERR_ARG, "rank's positive range does not follow the stream-slice geometry"); }
             o.world = P.world; o.rank = P.rank; o.adam = m->optimizer == OKB_ADAM; o.epoch = epoch;
             o.rows_all = (i32)(c->E + c->R); o.step_rel = (i32)(step - c->plan_lo);
             o.loss_out = loss_out ? loss_out + i : nullptr;
@@ -2065,7 +2064,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         }
         if (a.hub) {
             const i64 nblocks = a.n / PCH;
-            if (c->partial.ensure(sizeof(float) * (size_t)(nblocks + 1) * a.pcols)) { c->pdl = was_pdl; OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (partial sums)"); }
+            if (c->partial.ensure(sizeof(float) * (size_t)(nblocks + 1) * a.pcols)) { OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (partial sums)"); }
             a.partial = c->partial.as<float>();
             const unsigned pg = (unsigned)((nblocks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK + 1);
             DISPATCH_LAYOUT(vw, nv, CALL_PRE);
@@ -2117,7 +2116,6 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         OKB_LAUNCHED(2);
         c->dp_epoch = epoch;
     }
-    c->pdl = was_pdl;
     {
         DpPush d;
         for (int q = 0; q < OKB_DP_MAX; q++) d.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
