@@ -286,7 +286,10 @@ enum { OKB_FLAG_TRANSR_TC = 1,
        OKB_FLAG_DP_PULL = 7,
        /* OKB_FLAG_GRAD_SINGLE_WARP = 8 (default off): the generic grad kernel never splits a positive's negatives over several
         * warps (A/B runs; the split changes the association of the shared rows' gradient sums). */
-       OKB_FLAG_GRAD_SINGLE_WARP = 8 };
+       OKB_FLAG_GRAD_SINGLE_WARP = 8,
+       /* OKB_FLAG_PLAN_MULTI = 9 (default off): plan a single step with the general multi-kernel segmented sort instead of the
+          one-CTA single-kernel plan (A/B and test switch; results are identical). */
+       OKB_FLAG_PLAN_MULTI = 9 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:

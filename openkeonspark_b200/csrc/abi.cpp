@@ -64,6 +64,7 @@ int okb_set_flag(okb_ctx *c, int flag, INT value) {
     if (flag == OKB_FLAG_ADAM_LEGACY) { c->adam_legacy = value != 0; return 0; }
     if (flag == OKB_FLAG_GRAD_GENERIC) { c->grad_generic = value != 0; return 0; }
     if (flag == OKB_FLAG_GRAD_SINGLE_WARP) { c->grad_single_warp = value != 0; return 0; }
+    if (flag == OKB_FLAG_PLAN_MULTI) { c->plan_multi = value != 0; return 0; }
     if (flag == OKB_FLAG_DP_PULL) { c->dp_pull = value != 0; return 0; }
     OKB_FAIL(c, OKB_ERR_ARG, "unknown flag");
 }

@@ -25,6 +25,7 @@
 //
 // Roofline: latency-bound gathers and an HBM/L2 stream of fp32 rows; no dense contraction, so no tensor cores
 // here (TransR's projection lives in transr.cu / transr_tc.cu).
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cstring>
 
@@ -95,6 +96,191 @@ __global__ void plan_keys_kernel(PlanArgs a) {
     for (i32 m = 0; m < a.kr; m++) {
         const i32 nr = br[b + (1 + a.k + m) * a.B];
         kr_[1 + m] = nr != pr ? off + a.E + nr : none;
+    }
+}
+
+// ---- one-step plan in ONE kernel (the host-buffer path plans a single step per call: keys + 8 sort launches + memset +
+// head marking were ~11 launches of 2-8 us kernels; launch-bound).  One CLUSTER of 8 CTAs x 1024 threads: every thread
+// keeps its <= 4 packed items (key << ib | index) in registers; warp g of the cluster owns the contiguous index range
+// [g*chunk, (g+1)*chunk), so warp-private counter columns + a ballot-built peer mask give a STABLE two-pass LSD sort
+// (digit = half the key bits).  Per pass: local histogram -> per-CTA digit totals exchanged through distributed shared
+// memory -> every CTA derives its own bases -> scatter.  Pass 1 scatters registers -> the owning CTA's shared-memory
+// slice (remote stores), pass 2 local slice -> sorted keys / permutation in global memory, then the
+// row -> {first, end, slot0, slot1} map.  Output is identical to plan_keys + okb_sort_pairs_seg + mark_heads.
+// (MATCH.ANY issues about once per 64 cycles per SM -- measured: a one-CTA version built on it took 90 us -- hence ballots.)
+struct PlanSmallArgs {
+    PlanArgs p;
+    i32 *skeys, *perm;         // [n] sorted keys, original index of every sorted entry
+    int4 *rowhead;             // [rows]
+    i32 n, rows, ib, db;
+};
+#define PS_CTAS 8
+#define PS_THREADS 1024
+#define PS_WARPS (PS_THREADS / 32)
+#define PS_ITEMS 4
+#define PS_MAX_N (PS_CTAS * PS_THREADS * PS_ITEMS)
+__device__ __forceinline__ i32 plan_key(const PlanArgs &a, const i32 *bh, const i32 *bt, const i32 *br, i32 i) {
+    const i32 ne_tot = a.Bl * a.NE, none = a.E + a.R;
+    if (i < ne_tot) {
+        const i32 bl = i / a.NE, j = i - bl * a.NE, b = a.b_lo + bl;
+        if (j == 0) return bh[b];
+        if (j == 1) return bt[b];
+        const i32 at = b + (j - 1) * a.B;
+        const i32 nh = bh[at], nt = bt[at];
+        return nh != bh[b] ? nh : (nt != bt[b] ? nt : none);
+    }
+    const i32 i2 = i - ne_tot, bl = i2 / a.NR, j = i2 - bl * a.NR, b = a.b_lo + bl;
+    const i32 pr = br[b];
+    if (j == 0) return a.E + pr;
+    const i32 nr = br[b + (a.k + j) * a.B];
+    return nr != pr ? a.E + nr : none;
+}
+// lanes of the warp that hold a valid item with the same digit as this lane (meaningful for valid lanes only)
+__device__ __forceinline__ unsigned plan_peers(unsigned dg, bool ok, int db) {
+    unsigned m = __ballot_sync(FULL, ok);
+#pragma unroll
+    for (int b = 0; b < 8; b++)
+        if (b < db) {
+            const bool bit = (dg >> b) & 1u;
+            const unsigned v = __ballot_sync(FULL, bit);
+            m &= bit ? v : ~v;
+        }
+    return m;
+}
+struct PlanSmem { unsigned *items, *cnt, *tot, *base, *wtot; };
+// cnt[w][d] (this CTA's warp histograms) -> cnt[w][d] = entries of digit d in lower warps of this CTA, and
+// base[d] = first output position of this CTA's entries of digit d (digit-major, then CTA, then warp order)
+__device__ __forceinline__ void plan_bases(cooperative_groups::cluster_group &cl, const PlanSmem &S, int ndig, int t) {
+    const int lane = t & 31, w = t >> 5, stride = ndig + 1;
+    if (t < ndig) {
+        unsigned run = 0;
+#pragma unroll
+        for (int q = 0; q < PS_WARPS; q++) { const unsigned v = S.cnt[q * stride + t]; S.cnt[q * stride + t] = run; run += v; }
+        S.tot[t] = run;
+    }
+    cl.sync();
+    unsigned total = 0, lower = 0;
+    if (t < ndig) {
+        const unsigned me = cl.block_rank();
+#pragma unroll
+        for (unsigned q = 0; q < PS_CTAS; q++) {
+            const unsigned v = cl.map_shared_rank(S.tot, q)[t];
+            total += v;
+            if (q < me) lower += v;
+        }
+    }
+    unsigned inc = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += y; }
+    if (lane == 31) S.wtot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const unsigned x = lane < PS_WARPS ? S.wtot[lane] : 0u;
+        unsigned i2 = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(FULL, i2, o); if (lane >= o) i2 += y; }
+        if (lane < PS_WARPS) S.wtot[lane] = i2 - x;
+    }
+    __syncthreads();
+    if (t < ndig) S.base[t] = S.wtot[w] + inc - total + lower;
+    __syncthreads();
+}
+__global__ void __cluster_dims__(PS_CTAS, 1, 1) __launch_bounds__(PS_THREADS, 1) plan_small_kernel(PlanSmallArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned psm[];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, cta = (int)cl.block_rank();
+    const i32 n = a.n, ndig = 1 << a.db, stride = ndig + 1;
+    const i32 chunk = ((n + PS_CTAS * PS_THREADS - 1) / (PS_CTAS * PS_THREADS)) * 32, slice = chunk * PS_WARPS;
+    PlanSmem S;
+    S.items = psm; S.cnt = psm + slice; S.tot = S.cnt + PS_WARPS * stride; S.base = S.tot + ndig; S.wtot = S.base + ndig;
+    unsigned *col = S.cnt + w * stride;
+    const unsigned dmask = ndig - 1, imask = (1u << a.ib) - 1, lt = (1u << lane) - 1;
+    const i32 lo = (cta * PS_WARPS + w) * chunk, hi = min(n, lo + chunk);
+    const int ib = a.ib, db = a.db, gt = cta * PS_THREADS + t;
+    for (i32 i = t; i < PS_WARPS * stride; i += PS_THREADS) S.cnt[i] = 0;
+    for (i32 i = gt; i < a.rows; i += PS_CTAS * PS_THREADS) a.rowhead[i] = make_int4(-1, -1, -1, -1);
+    const i32 *bh = a.p.batch + (i64)a.p.step_lo * 3 * a.p.S, *bt = bh + a.p.S, *br = bt + a.p.S;
+    unsigned x[PS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < PS_ITEMS; it++) {
+        const i32 i = lo + it * 32 + lane;
+        x[it] = i < hi ? ((unsigned)plan_key(a.p, bh, bt, br, i) << ib) | (unsigned)i : 0xffffffffu;
+    }
+    __syncthreads();
+    // ---- pass 1 (low digit): registers -> the cluster's distributed item array
+#pragma unroll
+    for (int it = 0; it < PS_ITEMS; it++) {
+        if (lo + it * 32 < hi) {
+            const bool ok = x[it] != 0xffffffffu;
+            const unsigned dg = ok ? (x[it] >> ib) & dmask : 0u;
+            const unsigned m = plan_peers(dg, ok, db);
+            if (ok && lane == __ffs(m) - 1) col[dg] += __popc(m);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    plan_bases(cl, S, ndig, t);
+#pragma unroll
+    for (int it = 0; it < PS_ITEMS; it++) {
+        if (lo + it * 32 < hi) {
+            const bool ok = x[it] != 0xffffffffu;
+            const unsigned dg = ok ? (x[it] >> ib) & dmask : 0u;
+            const unsigned m = plan_peers(dg, ok, db);
+            const int leader = ok ? __ffs(m) - 1 : 0;
+            unsigned b0 = 0;
+            if (ok && lane == leader) { const unsigned cur = col[dg]; col[dg] = cur + __popc(m); b0 = S.base[dg] + cur; }
+            b0 = __shfl_sync(FULL, b0, leader);
+            if (ok) {
+                const unsigned pos = b0 + __popc(m & lt);
+                cl.map_shared_rank(S.items, pos / slice)[pos % slice] = x[it];
+            }
+            __syncwarp();
+        }
+    }
+    cl.sync();
+    // ---- pass 2 (high digit): local slice -> sorted keys / permutation
+    for (i32 i = t; i < PS_WARPS * stride; i += PS_THREADS) S.cnt[i] = 0;
+    __syncthreads();
+    const i32 off0 = cta * slice;                            // items[i - off0] = item at global position i
+    for (i32 base = lo; base < hi; base += 32) {
+        const i32 i = base + lane;
+        const bool ok = i < hi;
+        const unsigned dg = ok ? (S.items[i - off0] >> (ib + db)) & dmask : 0u;
+        const unsigned m = plan_peers(dg, ok, db);
+        if (ok && lane == __ffs(m) - 1) col[dg] += __popc(m);
+        __syncwarp();
+    }
+    __syncthreads();
+    plan_bases(cl, S, ndig, t);
+    for (i32 base = lo; base < hi; base += 32) {
+        const i32 i = base + lane;
+        const bool ok = i < hi;
+        const unsigned v = ok ? S.items[i - off0] : 0u;
+        const unsigned dg = ok ? (v >> (ib + db)) & dmask : 0u;
+        const unsigned m = plan_peers(dg, ok, db);
+        const int leader = ok ? __ffs(m) - 1 : 0;
+        unsigned b0 = 0;
+        if (ok && lane == leader) { const unsigned cur = col[dg]; col[dg] = cur + __popc(m); b0 = S.base[dg] + cur; }
+        b0 = __shfl_sync(FULL, b0, leader);
+        if (ok) {
+            const unsigned pos = b0 + __popc(m & lt);
+            a.skeys[pos] = (i32)(v >> ib);
+            a.perm[pos] = (i32)(v & imask);
+        }
+        __syncwarp();
+    }
+    __threadfence();
+    cl.sync();
+    // ---- row map (mark_heads_kernel); the sorted arrays were written by all 8 CTAs: read them from L2
+    for (i32 i = gt; i < n; i += PS_CTAS * PS_THREADS) {
+        const i32 key = __ldcg(a.skeys + i);
+        if (key >= a.rows) continue;
+        int4 *o = a.rowhead + key;
+        const bool first = i == 0 || __ldcg(a.skeys + i - 1) != key;
+        if (first) { o->x = i; o->z = __ldcg(a.perm + i); }
+        else if (i == 1 || __ldcg(a.skeys + i - 2) != key) o->w = __ldcg(a.perm + i);
+        if (i == n - 1 || __ldcg(a.skeys + i + 1) != key) o->y = i + 1;
     }
 }
 
@@ -1338,11 +1524,26 @@ static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, 
     a.keys = c->keys_ent.as<i32>();
     a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)NE; a.NR = (i32)NR; a.E = (i32)c->E; a.R = (i32)c->R;
     a.S = (i32)S; a.step_lo = (i32)step_lo; a.C = (i32)C; a.b_lo = (i32)b_lo; a.Bl = (i32)B;
-    plan_keys_kernel<<<(unsigned)((C * B + 127) / 128), 128, 0, s>>>(a);
-    OKB_LAUNCHED(1);
     c->plan_ne = B * NE; c->plan_nr = B * NR; c->plan_lo = step_lo; c->plan_hi = step_hi;
     c->plan_b_lo = b_lo; c->plan_b_hi = b_hi;
     c->rowhead_ready = false;
+    const int kb = bits_for(ks);
+    if (C == 1 && n <= PS_MAX_N && kb <= 16 && !c->plan_multi) {               // one step: the single-kernel plan
+        const i64 rows = c->E + c->R;
+        if (c->rowseg_e.ensure(sizeof(int4) * rows)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (rowhead)");
+        PlanSmallArgs q;
+        q.p = a; q.skeys = a.keys + total; q.perm = c->perm_ent.as<i32>(); q.rowhead = c->rowseg_e.as<int4>();
+        q.n = (i32)n; q.rows = (i32)rows; q.ib = bits_for(n); q.db = (kb + 1) / 2 < 5 ? 5 : (kb + 1) / 2;
+        const i64 chunk = ((n + PS_CTAS * PS_THREADS - 1) / (PS_CTAS * PS_THREADS)) * 32, ndig = 1 << q.db;
+        const size_t smem = (size_t)(chunk * PS_WARPS + PS_WARPS * (ndig + 1) + 2 * ndig + PS_WARPS) * 4;
+        plan_small_kernel<<<PS_CTAS, PS_THREADS, smem, s>>>(q);
+        OKB_LAUNCHED(1);
+        OKB_CUDA(c, cudaGetLastError());
+        c->rowhead_ready = true;
+        return 0;
+    }
+    plan_keys_kernel<<<(unsigned)((C * B + 127) / 128), 128, 0, s>>>(a);
+    OKB_LAUNCHED(1);
     int rc = okb_sort_pairs_seg(c, a.keys, a.keys + total, c->perm_ent.as<i32>(), n, C, bits_for(ks), s);
     if (rc) return rc;
     OKB_CUDA(c, cudaGetLastError());

@@ -224,3 +224,27 @@ def test_short_segment_path_parity(built, wide_ds, model, opt):
             assert np.abs(got[name] - exp[name]).max() <= 1e-4 * np.abs(exp[name] - P[name]).max() + 2e-6, name
         else:
             _check_adam_slots(con, ref64)
+
+
+@pytest.mark.parametrize("model,opt,D,k,kr,nbatches,ds", [
+    ("TransH", "Adam", 100, 1, 0, 6, "small"), ("TransE", "SGD", 50, 3, 2, 6, "small"), ("TransD", "Adam", 33, 2, 1, 40, "small"),
+    ("TransR", "Adam", 20, 2, 0, 6, "small"), ("TransE", "SGD", 16, 2, 0, 4, "tiny"), ("TransH", "SGD", 64, 1, 0, 3, "wide"),
+    ("TransE", "Adam", 32, 10, 0, 1, "small")])
+def test_single_kernel_plan_equals_multi_kernel_plan(built, small_ds, tiny_ds, wide_ds, model, opt, D, k, kr, nbatches, ds):
+    """A one-step plan runs as ONE kernel (plan_small_kernel: keys, stable 2-pass sort, row map) when it fits one CTA;
+    OKB_FLAG_PLAN_MULTI routes it through the general multi-kernel segmented sort.  Both are stable sorts of the same
+    keys, so losses and tables must be bit-identical (the last case exceeds the one-CTA limit and checks the fallback)."""
+    path = {"small": small_ds, "tiny": tiny_ds, "wide": wide_ds}[ds]
+    outs = []
+    for multi in (0, 1):
+        con = _config(path, model, D, k, kr, opt, nbatches=nbatches)
+        con.ctx.call("okb_set_flag", 9, multi)
+        con.set_parameters(make_params(model, con.entTotal, con.relTotal, D, seed=5))
+        losses = []
+        for it in range(4):
+            con.sampling_device()
+            losses.append(float(con.train_step_device(0).item()))
+        outs.append((losses, con.get_parameters()))
+    assert outs[0][0] == outs[1][0]
+    for name in outs[0][1]:
+        assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
