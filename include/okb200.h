@@ -178,6 +178,13 @@ int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
  * per step), loss_out: device float[n] or NULL. */
 int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out,
                     void *cuda_stream);
+/* loss_out may also be PAGE-LOCKED HOST memory (it is written with one plain store followed by a system fence).  The
+ * host-batch path (Config.train_step, the reference's feed_dict call that returns the loss, Config.py:464-475) uses
+ * that instead of a device->host copy: the caller stores `sentinel` (a bit pattern no loss can have) in *word, launches
+ * the step, and okb_wait_word spins until the word changes — the Adam kernel's loss blocks are the FIRST blocks of its
+ * grid, so the loss arrives while the table update is still running and the next batch is prepared under it.  Falls
+ * back to a stream synchronize if the stream goes idle first; returns OKB_ERR_CUDA if the stream failed. */
+int okb_wait_word(okb_ctx *c, const void *host_word, unsigned sentinel, void *cuda_stream);
 
 /* ---- synchronous data-parallel training inside one box, one process per GPU (replaces the asynchronous
  *      parameter-server path of distribute_training.py:161-364).  Owner-sharded: every rank keeps the full tables in a

@@ -81,6 +81,7 @@ struct okb_ctx {
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
     bool plan_multi = false;          // OKB_FLAG_PLAN_MULTI: one-step plans use the multi-kernel sort too
+    bool plan_small_attr = false;     // dynamic shared memory limit of plan_small_kernel raised on this device
     bool grad_single_warp = false;    // OKB_FLAG_GRAD_SINGLE_WARP: never split a positive's negatives over several warps
     bool grad_generic = false;        // OKB_FLAG_GRAD_GENERIC: never use the k = 1 specialisation of the grad kernel
     bool adam_legacy = false;         // OKB_FLAG_ADAM_LEGACY: grid-stride register kernel instead of the tile kernel

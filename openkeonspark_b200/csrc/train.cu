@@ -104,36 +104,36 @@ __global__ void plan_keys_kernel(PlanArgs a) {
 // keeps its <= 4 packed items (key << ib | index) in registers; warp g of the cluster owns the contiguous index range
 // [g*chunk, (g+1)*chunk), so warp-private counter columns + a ballot-built peer mask give a STABLE two-pass LSD sort
 // (digit = half the key bits).  Per pass: local histogram -> per-CTA digit totals exchanged through distributed shared
-// memory -> every CTA derives its own bases -> scatter.  Pass 1 scatters registers -> the owning CTA's shared-memory
-// slice (remote stores), pass 2 local slice -> sorted keys / permutation in global memory, then the
-// row -> {first, end, slot0, slot1} map.  Output is identical to plan_keys + okb_sort_pairs_seg + mark_heads.
+// memory -> every CTA derives its own bases -> scatter.  Both passes scatter into the owning CTA's shared-memory slice
+// by remote stores (pass 1 from registers, pass 2 from the local slice); the sorted slice is then written out coalesced
+// (keys, permutation) and the row -> {first, end, slot0, slot1} map is marked straight from shared memory.
+// Output is identical to plan_keys + okb_sort_pairs_seg + mark_heads.
 // (MATCH.ANY issues about once per 64 cycles per SM -- measured: a one-CTA version built on it took 90 us -- hence ballots.)
 struct PlanSmallArgs {
     PlanArgs p;
     i32 *skeys, *perm;         // [n] sorted keys, original index of every sorted entry
     int4 *rowhead;             // [rows]
     i32 n, rows, ib, db;
+    unsigned magic_e, magic_r; // ceil(2^32 / NE), ceil(2^32 / NR): exact division of an index < 2^16 by one multiply
+    i32 chunk;                 // entries per warp: 32, 64 or 128 (a power of two, so that position -> owning CTA is a shift)
 };
 #define PS_CTAS 8
 #define PS_THREADS 1024
 #define PS_WARPS (PS_THREADS / 32)
 #define PS_ITEMS 4
 #define PS_MAX_N (PS_CTAS * PS_THREADS * PS_ITEMS)
-__device__ __forceinline__ i32 plan_key(const PlanArgs &a, const i32 *bh, const i32 *bt, const i32 *br, i32 i) {
+// key of sort entry i of the step (plan_keys_kernel's layout), branch-free so that a thread's entries load together
+__device__ __forceinline__ i32 plan_key(const PlanArgs &a, unsigned magic_e, unsigned magic_r, const i32 *bh, const i32 *bt,
+                                        const i32 *br, i32 i) {
     const i32 ne_tot = a.Bl * a.NE, none = a.E + a.R;
-    if (i < ne_tot) {
-        const i32 bl = i / a.NE, j = i - bl * a.NE, b = a.b_lo + bl;
-        if (j == 0) return bh[b];
-        if (j == 1) return bt[b];
-        const i32 at = b + (j - 1) * a.B;
-        const i32 nh = bh[at], nt = bt[at];
-        return nh != bh[b] ? nh : (nt != bt[b] ? nt : none);
-    }
-    const i32 i2 = i - ne_tot, bl = i2 / a.NR, j = i2 - bl * a.NR, b = a.b_lo + bl;
-    const i32 pr = br[b];
-    if (j == 0) return a.E + pr;
-    const i32 nr = br[b + (a.k + j) * a.B];
-    return nr != pr ? a.E + nr : none;
+    const bool ent = i < ne_tot;
+    const i32 i2 = ent ? i : i - ne_tot, per = ent ? a.NE : a.NR;
+    const i32 bl = per == 1 ? i2 : (i32)__umulhi((unsigned)i2, ent ? magic_e : magic_r), j = i2 - bl * per, b = a.b_lo + bl;
+    const i32 plane = ent ? (j >= 2 ? j - 1 : 0) : (j >= 1 ? a.k + j : 0), at = b + plane * a.B;
+    const i32 *p0 = ent ? bh : br;
+    const i32 v0 = p0[b], v1 = bt[b], w0 = p0[at], w1 = bt[at];
+    if (ent) return j == 0 ? v0 : (j == 1 ? v1 : (w0 != v0 ? w0 : (w1 != v1 ? w1 : none)));
+    return j == 0 ? a.E + v0 : (w0 != v0 ? a.E + w0 : none);
 }
 // lanes of the warp that hold a valid item with the same digit as this lane (meaningful for valid lanes only)
 __device__ __forceinline__ unsigned plan_peers(unsigned dg, bool ok, int db) {
@@ -147,7 +147,7 @@ __device__ __forceinline__ unsigned plan_peers(unsigned dg, bool ok, int db) {
         }
     return m;
 }
-struct PlanSmem { unsigned *items, *cnt, *tot, *base, *wtot; };
+struct PlanSmem { unsigned *items, *items2, *cnt, *tot, *base, *wtot; };
 // cnt[w][d] (this CTA's warp histograms) -> cnt[w][d] = entries of digit d in lower warps of this CTA, and
 // base[d] = first output position of this CTA's entries of digit d (digit-major, then CTA, then warp order)
 __device__ __forceinline__ void plan_bases(cooperative_groups::cluster_group &cl, const PlanSmem &S, int ndig, int t) {
@@ -185,103 +185,114 @@ __device__ __forceinline__ void plan_bases(cooperative_groups::cluster_group &cl
     if (t < ndig) S.base[t] = S.wtot[w] + inc - total + lower;
     __syncthreads();
 }
+// stable scatter of one 32-entry row of a warp: entry v (digit dg) of every valid lane goes to position
+// base[dg] + (entries of dg before it in this CTA), into the slice of the cluster-distributed array `dst` that owns it
+__device__ __forceinline__ void plan_scatter(cooperative_groups::cluster_group &cl, const PlanSmem &S, unsigned *col, unsigned *dst,
+                                             unsigned v, unsigned dg, bool ok, int db, int lane, int ss) {
+    const unsigned m = plan_peers(dg, ok, db);
+    const int leader = ok ? __ffs(m) - 1 : 0;
+    unsigned b0 = 0;
+    if (ok && lane == leader) { const unsigned cur = col[dg]; col[dg] = cur + __popc(m); b0 = S.base[dg] + cur; }
+    b0 = __shfl_sync(FULL, b0, leader);
+    if (ok) {
+        const unsigned pos = b0 + __popc(m & ((1u << lane) - 1));
+        cl.map_shared_rank(dst, pos >> ss)[pos & ((1u << ss) - 1)] = v;
+    }
+    __syncwarp();
+}
 __global__ void __cluster_dims__(PS_CTAS, 1, 1) __launch_bounds__(PS_THREADS, 1) plan_small_kernel(PlanSmallArgs a) {
     namespace cg = cooperative_groups;
+#ifdef PS_TIMING                                            // per-phase globaltimer stamps of CTA 0 (tools/build_variant.sh)
+    unsigned long long ts[12]; int nts = 0;
+#define PS_STAMP() do { if (threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[nts])); nts++; } while (0)
+#else
+#define PS_STAMP() do { } while (0)
+#endif
+    PS_STAMP();
     cg::cluster_group cl = cg::this_cluster();
     extern __shared__ __align__(16) unsigned psm[];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, cta = (int)cl.block_rank();
     const i32 n = a.n, ndig = 1 << a.db, stride = ndig + 1;
-    const i32 chunk = ((n + PS_CTAS * PS_THREADS - 1) / (PS_CTAS * PS_THREADS)) * 32, slice = chunk * PS_WARPS;
+    const i32 chunk = a.chunk, slice = chunk * PS_WARPS, ss = 31 - __clz(slice);     // slice is a power of two
     PlanSmem S;
-    S.items = psm; S.cnt = psm + slice; S.tot = S.cnt + PS_WARPS * stride; S.base = S.tot + ndig; S.wtot = S.base + ndig;
+    S.items = psm; S.items2 = psm + slice; S.cnt = S.items2 + slice; S.tot = S.cnt + PS_WARPS * stride; S.base = S.tot + ndig;
+    S.wtot = S.base + ndig;
     unsigned *col = S.cnt + w * stride;
-    const unsigned dmask = ndig - 1, imask = (1u << a.ib) - 1, lt = (1u << lane) - 1;
-    const i32 lo = (cta * PS_WARPS + w) * chunk, hi = min(n, lo + chunk);
+    const unsigned dmask = ndig - 1, imask = (1u << a.ib) - 1;
+    const i32 s_lo = cta * slice, s_hi = min(n, s_lo + slice);               // this CTA's slice of the index / position space
+    const i32 lo = s_lo + w * chunk, hi = min(n, lo + chunk);                // this warp's entries
     const int ib = a.ib, db = a.db, gt = cta * PS_THREADS + t;
     for (i32 i = t; i < PS_WARPS * stride; i += PS_THREADS) S.cnt[i] = 0;
+    pdl_wait();                   // the batch comes from the previous kernel; the previous step's update still reads the row map
+    pdl_launch_dependents();      // the grad kernel may become resident now: it waits for this grid before it touches the plan
     for (i32 i = gt; i < a.rows; i += PS_CTAS * PS_THREADS) a.rowhead[i] = make_int4(-1, -1, -1, -1);
     const i32 *bh = a.p.batch + (i64)a.p.step_lo * 3 * a.p.S, *bt = bh + a.p.S, *br = bt + a.p.S;
     unsigned x[PS_ITEMS];
 #pragma unroll
     for (int it = 0; it < PS_ITEMS; it++) {
         const i32 i = lo + it * 32 + lane;
-        x[it] = i < hi ? ((unsigned)plan_key(a.p, bh, bt, br, i) << ib) | (unsigned)i : 0xffffffffu;
+        x[it] = i < hi ? ((unsigned)plan_key(a.p, a.magic_e, a.magic_r, bh, bt, br, i) << ib) | (unsigned)i : 0xffffffffu;
     }
     __syncthreads();
-    // ---- pass 1 (low digit): registers -> the cluster's distributed item array
+    PS_STAMP();
+    // ---- pass 1 (low digit): registers -> the cluster's distributed array `items`
 #pragma unroll
-    for (int it = 0; it < PS_ITEMS; it++) {
-        if (lo + it * 32 < hi) {
-            const bool ok = x[it] != 0xffffffffu;
-            const unsigned dg = ok ? (x[it] >> ib) & dmask : 0u;
-            const unsigned m = plan_peers(dg, ok, db);
-            if (ok && lane == __ffs(m) - 1) col[dg] += __popc(m);
-            __syncwarp();
-        }
-    }
+    for (int it = 0; it < PS_ITEMS; it++)
+        if (x[it] != 0xffffffffu) atomicAdd(&col[(x[it] >> ib) & dmask], 1u);
     __syncthreads();
+    PS_STAMP();
     plan_bases(cl, S, ndig, t);
+    PS_STAMP();
 #pragma unroll
-    for (int it = 0; it < PS_ITEMS; it++) {
+    for (int it = 0; it < PS_ITEMS; it++)
         if (lo + it * 32 < hi) {
             const bool ok = x[it] != 0xffffffffu;
-            const unsigned dg = ok ? (x[it] >> ib) & dmask : 0u;
-            const unsigned m = plan_peers(dg, ok, db);
-            const int leader = ok ? __ffs(m) - 1 : 0;
-            unsigned b0 = 0;
-            if (ok && lane == leader) { const unsigned cur = col[dg]; col[dg] = cur + __popc(m); b0 = S.base[dg] + cur; }
-            b0 = __shfl_sync(FULL, b0, leader);
-            if (ok) {
-                const unsigned pos = b0 + __popc(m & lt);
-                cl.map_shared_rank(S.items, pos / slice)[pos % slice] = x[it];
-            }
-            __syncwarp();
+            plan_scatter(cl, S, col, S.items, x[it], ok ? (x[it] >> ib) & dmask : 0u, ok, db, lane, ss);
         }
-    }
     cl.sync();
-    // ---- pass 2 (high digit): local slice -> sorted keys / permutation
+    PS_STAMP();
+    // ---- pass 2 (high digit): local slice of `items` -> the distributed array `items2`
     for (i32 i = t; i < PS_WARPS * stride; i += PS_THREADS) S.cnt[i] = 0;
     __syncthreads();
-    const i32 off0 = cta * slice;                            // items[i - off0] = item at global position i
-    for (i32 base = lo; base < hi; base += 32) {
-        const i32 i = base + lane;
-        const bool ok = i < hi;
-        const unsigned dg = ok ? (S.items[i - off0] >> (ib + db)) & dmask : 0u;
-        const unsigned m = plan_peers(dg, ok, db);
-        if (ok && lane == __ffs(m) - 1) col[dg] += __popc(m);
-        __syncwarp();
-    }
+    for (i32 i = lo + lane; i < hi; i += 32) atomicAdd(&col[(S.items[i - s_lo] >> (ib + db)) & dmask], 1u);
     __syncthreads();
+    PS_STAMP();
     plan_bases(cl, S, ndig, t);
+    PS_STAMP();
     for (i32 base = lo; base < hi; base += 32) {
         const i32 i = base + lane;
         const bool ok = i < hi;
-        const unsigned v = ok ? S.items[i - off0] : 0u;
-        const unsigned dg = ok ? (v >> (ib + db)) & dmask : 0u;
-        const unsigned m = plan_peers(dg, ok, db);
-        const int leader = ok ? __ffs(m) - 1 : 0;
-        unsigned b0 = 0;
-        if (ok && lane == leader) { const unsigned cur = col[dg]; col[dg] = cur + __popc(m); b0 = S.base[dg] + cur; }
-        b0 = __shfl_sync(FULL, b0, leader);
-        if (ok) {
-            const unsigned pos = b0 + __popc(m & lt);
-            a.skeys[pos] = (i32)(v >> ib);
-            a.perm[pos] = (i32)(v & imask);
-        }
-        __syncwarp();
+        const unsigned v = ok ? S.items[i - s_lo] : 0u;
+        plan_scatter(cl, S, col, S.items2, v, ok ? (v >> (ib + db)) & dmask : 0u, ok, db, lane, ss);
     }
-    __threadfence();
     cl.sync();
-    // ---- row map (mark_heads_kernel); the sorted arrays were written by all 8 CTAs: read them from L2
-    for (i32 i = gt; i < n; i += PS_CTAS * PS_THREADS) {
-        const i32 key = __ldcg(a.skeys + i);
+    PS_STAMP();
+    // ---- sorted keys / permutation (coalesced) and the row map (mark_heads_kernel) out of shared memory; the three
+    // neighbours of an entry at a slice boundary are read from the adjacent CTA's slice
+    auto sorted_key = [&](i32 j) -> i32 {
+        if (j < 0 || j >= n) return -1;
+        const unsigned v = (j >= s_lo && j < s_hi) ? S.items2[j - s_lo] : cl.map_shared_rank(S.items2, j >> ss)[j & (slice - 1)];
+        return (i32)(v >> ib);
+    };
+    for (i32 i = s_lo + t; i < s_hi; i += PS_THREADS) {
+        const unsigned v = S.items2[i - s_lo];
+        const i32 key = (i32)(v >> ib), idx = (i32)(v & imask);
+        a.skeys[i] = key;
+        a.perm[i] = idx;
         if (key >= a.rows) continue;
         int4 *o = a.rowhead + key;
-        const bool first = i == 0 || __ldcg(a.skeys + i - 1) != key;
-        if (first) { o->x = i; o->z = __ldcg(a.perm + i); }
-        else if (i == 1 || __ldcg(a.skeys + i - 2) != key) o->w = __ldcg(a.perm + i);
-        if (i == n - 1 || __ldcg(a.skeys + i + 1) != key) o->y = i + 1;
+        if (sorted_key(i - 1) != key) { o->x = i; o->z = idx; }
+        else if (sorted_key(i - 2) != key) o->w = idx;               // second entry of its segment
+        if (sorted_key(i + 1) != key) o->y = i + 1;
     }
+    cl.sync();                                                       // no CTA exits while a neighbour may still read its slice
+#ifdef PS_TIMING
+    PS_STAMP();
+    if (cta == 0 && t == 0)
+        printf("plan_small ns: keys %llu hist1 %llu bases1 %llu scat1 %llu hist2 %llu bases2 %llu scat2 %llu heads %llu total %llu\n",
+               ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5], ts[7] - ts[6], ts[8] - ts[7],
+               ts[8] - ts[0]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ row fragments
@@ -970,11 +981,10 @@ struct UpdArgs {
 // mean hinge over B*(k+kr) pairs in a fixed order, by `loss_blocks` extra blocks of the update launch: each
 // sums a fixed contiguous range of the per-positive terms; the block that finishes last adds the partial
 // sums in index order (so the result does not depend on which block that is).
-__device__ __forceinline__ void loss_block(const UpdArgs &a) {
+__device__ __forceinline__ void loss_block(const UpdArgs &a, i32 lb) {
     __shared__ float sh[32];
     __shared__ unsigned ticket;
     if (!a.loss_out) return;
-    const i32 lb = (i32)blockIdx.x - a.work_blocks;
     const i32 per = (a.B + a.loss_blocks - 1) / a.loss_blocks;
     const i32 lo = lb * per, hi = min(a.B, lo + per);
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -1003,6 +1013,7 @@ __device__ __forceinline__ void loss_block(const UpdArgs &a) {
         for (i32 q = 0; q < a.loss_blocks; q++) tot += ((volatile float *)a.loss_part)[q];
         a.loss_out[0] = tot * a.w;
         *a.loss_ctr = 0u;
+        __threadfence_system();                            // loss_out may be page-locked host memory a waiting caller polls
     }
 }
 
@@ -1078,7 +1089,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) prereduce_kernel(UpdArgs
 template <int VW, int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
     constexpr int N = VW * NV;
-    if ((i32)blockIdx.x >= a.work_blocks) { loss_block(a); return; }
+    if ((i32)blockIdx.x >= a.work_blocks) { loss_block(a, (i32)blockIdx.x - a.work_blocks); return; }
     const int lane = threadIdx.x & 31;
     const i32 w = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     i32 key, i, end;
@@ -1123,7 +1134,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
 template <int VW>
 __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
     pdl_launch_dependents();
-    if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a); return; }
+    if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a, (i32)blockIdx.x - a.work_blocks); return; }
     typedef typename VecT<VW>::T V;
     const i64 total = a.tab[a.ntab - 1].vec_end;
     const i64 stride = (i64)a.work_blocks * blockDim.x;
@@ -1209,13 +1220,16 @@ __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
 template <int VW>
 __global__ void __launch_bounds__(256, ADAM_TILE_MIN_BLOCKS) adam_tile_kernel(UpdArgs a) {
     pdl_launch_dependents();                               // next step's grad kernel may prefetch its batch ids
-    if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a); return; }
+    // the loss blocks come FIRST in the grid: the step's loss is out a few microseconds after the grad kernel has
+    // finished, so a caller waiting for it (okb_wait_word) gets on with the next batch while the tables are updated
+    const i32 bid = (i32)blockIdx.x - a.loss_blocks;
+    if (bid < 0) { pdl_wait(); loss_block(a, (i32)blockIdx.x); return; }
     typedef typename VecT<VW>::T V;
     int t = 0;
-    while ((i32)blockIdx.x >= a.tab[t].blk_end) t++;       // block-uniform
+    while (bid >= a.tab[t].blk_end) t++;                   // block-uniform
     const DenseTab &T = a.tab[t];
     const unsigned nvec = (unsigned)(T.vec_end - (t ? a.tab[t - 1].vec_end : 0));
-    const unsigned lv = ((unsigned)blockIdx.x - (unsigned)(t ? a.tab[t - 1].blk_end : 0)) * 256u + threadIdx.x;
+    const unsigned lv = ((unsigned)bid - (unsigned)(t ? a.tab[t - 1].blk_end : 0)) * 256u + threadIdx.x;
     if (lv >= nvec) return;
     const unsigned vpr = (unsigned)T.D / VW;
     const unsigned row = T.magic ? (__umulhi(lv, T.magic) >> T.shift) : (lv >> T.shift);
@@ -1301,7 +1315,7 @@ __global__ void __launch_bounds__(AP_TILE, 2) adam_pipe_kernel(UpdArgs a, int nt
     ApStage *st = reinterpret_cast<ApStage *>(adam_sm);
     unsigned long long *full = reinterpret_cast<unsigned long long *>(st + AP_STAGES);
     const int G = a.work_blocks, tid = threadIdx.x;
-    if ((int)blockIdx.x >= G) { pdl_launch_dependents(); pdl_wait(); loss_block(a); return; }
+    if ((int)blockIdx.x >= G) { pdl_launch_dependents(); pdl_wait(); loss_block(a, (i32)blockIdx.x - G); return; }
     const int my_n = (ntiles - (int)blockIdx.x + G - 1) / G;         // this CTA's tiles: blockIdx.x + j * G
     if (tid == 0) {
         for (int s = 0; s < AP_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_smem(full + s)));
@@ -1534,9 +1548,23 @@ static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, 
         PlanSmallArgs q;
         q.p = a; q.skeys = a.keys + total; q.perm = c->perm_ent.as<i32>(); q.rowhead = c->rowseg_e.as<int4>();
         q.n = (i32)n; q.rows = (i32)rows; q.ib = bits_for(n); q.db = (kb + 1) / 2 < 5 ? 5 : (kb + 1) / 2;
-        const i64 chunk = ((n + PS_CTAS * PS_THREADS - 1) / (PS_CTAS * PS_THREADS)) * 32, ndig = 1 << q.db;
-        const size_t smem = (size_t)(chunk * PS_WARPS + PS_WARPS * (ndig + 1) + 2 * ndig + PS_WARPS) * 4;
-        plan_small_kernel<<<PS_CTAS, PS_THREADS, smem, s>>>(q);
+        i64 chunk = 32;
+        while (chunk * PS_CTAS * PS_WARPS < n) chunk *= 2;
+        const i64 ndig = 1 << q.db;
+        q.chunk = (i32)chunk;
+        q.magic_e = (unsigned)(((1ull << 32) + NE - 1) / NE); q.magic_r = (unsigned)(((1ull << 32) + NR - 1) / NR);
+        const size_t smem = (size_t)(2 * chunk * PS_WARPS + PS_WARPS * (ndig + 1) + 2 * ndig + PS_WARPS) * 4;
+        if (!c->plan_small_attr) {                         // up to 2 x 16 KB of items + 33 KB of counters
+            OKB_CUDA(c, cudaFuncSetAttribute(plan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+            c->plan_small_attr = true;
+        }
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(PS_CTAS); cfg.blockDim = dim3(PS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
+        OKB_CUDA(c, cudaLaunchKernelEx(&cfg, plan_small_kernel, q));
         OKB_LAUNCHED(1);
         OKB_CUDA(c, cudaGetLastError());
         c->rowhead_ready = true;
@@ -1550,6 +1578,20 @@ static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, 
     return 0;
 }
 extern "C" {
+int okb_wait_word(okb_ctx *c, const void *host_word, unsigned sentinel, void *stream) {
+    const volatile unsigned *w = (const volatile unsigned *)host_word;
+    for (unsigned spins = 1;; spins++) {
+        if (*w != sentinel) return 0;
+        if ((spins & 0x3ffu) == 0) {                       // every ~1k polls: has the stream finished or failed meanwhile?
+            cudaError_t e = cudaStreamQuery((cudaStream_t)stream);
+            if (e == cudaSuccess) {
+                if (*w != sentinel) return 0;
+                OKB_FAIL(c, OKB_ERR_STATE, "stream is idle but the awaited word was never written");
+            }
+            if (e != cudaErrorNotReady) { OKB_CUDA(c, e); }
+        }
+    }
+}
 int okb_plan(okb_ctx *c, INT step, void *stream) {
     if (planned(c, step, step + 1, 0, c->B)) return 0;          // already planned as part of a chunk
     return okb_plan_steps(c, step, step + 1, stream);
