@@ -125,6 +125,12 @@ int okb_sample(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, 
 int okb_batch_ptrs(okb_ctx *c, INT step, const int32_t **h, const int32_t **t, const int32_t **r);
 /* Copy step `step` to host in the reference's types (int64 ids, float labels +1/-1). */
 int okb_batch_to_host(okb_ctx *c, INT step, INT *h, INT *t, INT *r, REAL *y, void *cuda_stream);
+/* One reference sampling() call (Base.cpp:153-177) returning the batch in the caller's int64 arrays: okb_sample of ONE
+ * step followed by okb_batch_to_host, as one launch when h/t/r are one page-locked block [3][S] (the sample kernel then
+ * stores the int64 copy into it over PCIe itself and the call returns as soon as that kernel has finished).  The batch
+ * also stays resident on the device as step 0.  Labels are the fixed +1/-1 pattern and are not written. */
+int okb_sample_to_host(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT stream_lo, INT stream_hi, INT *h, INT *t,
+                       INT *r, void *cuda_stream);
 /* Replace the device batch of step 0 with caller-provided host ids (Config.train_step path). */
 int okb_batch_from_host(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, const INT *h, const INT *t,
                         const INT *r, void *cuda_stream);

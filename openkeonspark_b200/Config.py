@@ -277,13 +277,14 @@ class Config(object):
     # ------------------------------------------------------------------ sampling (Config.py:343-347)
     def sampling(self):
         """One reference sampling() call on the GPU; results land in batch_h/t/r/y like the reference's."""
-        self.sampling_device()
         # labels are the fixed pattern of Base.cpp:110,129,138 (+1 for the B positives, -1 for every negative plane):
         # written here instead of crossing PCIe as a second copy
         self.batch_y[:self.batch_size] = 1.0
         self.batch_y[self.batch_size:] = -1.0
-        self.ctx.call("okb_batch_to_host", 0, _vp(self.batch_h_addr), _vp(self.batch_t_addr), _vp(self.batch_r_addr),
-                      None, _stream())
+        # one launch: the sample kernel stores the int64 batch straight into the page-locked batch_h/t/r block
+        self.ctx.call("okb_sample_to_host", self.batch_size, self.negative_ent, self.negative_rel, 0, self.workThreads,
+                      _vp(self.batch_h_addr), _vp(self.batch_t_addr), _vp(self.batch_r_addr), _stream())
+        self._chunk_pos = self._chunk_len = 0
 
     def sampling_device(self, steps=1):
         """Sample `steps` consecutive batches, leaving them resident in HBM (no host copy)."""

@@ -68,6 +68,7 @@ _SIGS = {
     "okb_sample": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "okb_batch_ptrs": (_int, [_vp, _i64, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "okb_batch_to_host": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "okb_sample_to_host": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "okb_batch_from_host": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "okb_grad_sizes": (_int, [_vp, C.POINTER(okb_model), _i64, _i64, _i64] + [C.POINTER(_i64)] * 4),
     "okb_plan": (_int, [_vp, _i64, _vp]),

@@ -50,6 +50,7 @@ int okb_destroy(okb_ctx *c) {
     if (c->side) cudaStreamDestroy(c->side);
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_side) cudaEventDestroy(c->ev_side);
+    if (c->ev_sampled) cudaEventDestroy(c->ev_sampled);
     if (c == g_ctx) g_ctx = nullptr;
     delete c;
     return 0;

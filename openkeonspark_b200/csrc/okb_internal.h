@@ -94,7 +94,7 @@ struct okb_ctx {
     PlanSlot alt;                     // prefetched chunk (okb_chunk_prefetch)
     bool alt_ready = false, in_prefetch = false;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_sampled = nullptr;
     size_t saved_n = 0;
     u64 *d_state_saved = nullptr;     // RNG streams as they were before the prefetched chunk was sampled
     bool pdl = true;                  // programmatic dependent launch between the grad and update kernels

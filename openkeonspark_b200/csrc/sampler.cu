@@ -37,6 +37,8 @@ struct SampleArgs {
     const float *prob;
     const u64 *state;
     i32 *out;            // [steps][3][S]
+    i64 *mh, *mt, *mr;   // optional mirror of step 0 in page-locked HOST memory (int64, the reference's batch_h/t/r): the batch
+                         // crosses PCIe as posted stores while the kernel is still sampling (okb_sample_to_host)
     i64 n_raw, new_batch;
     i32 E, R, B, k, kr, W, per, bern, steps, stream_lo, stream_hi;
 };
@@ -74,7 +76,12 @@ __global__ void __launch_bounds__(128) sample_kernel(SampleArgs a) {
     else row = (i64)(lcg_next(s) % (u64)a.n_raw);
     const int4 p = __ldg(a.raw + row);                      // {h, t, r, -}
     const int4 rn = __ldg(a.run + row);                     // {llH, rrH, llT, rrT}
-    oh[b] = p.x; ot[b] = p.y; orl[b] = p.z;
+    const bool mir = a.mh != nullptr;
+    auto put = [&](i32 at, i32 h, i32 t, i32 r) {
+        oh[at] = h; ot[at] = t; orl[at] = r;
+        if (mir) { a.mh[at] = h; a.mt[at] = t; a.mr[at] = r; }
+    };
+    put(b, p.x, p.y, p.z);
     const float prob = a.bern ? __ldg(a.prob + p.z) : 500.0f;
     i32 at = b + a.B;
     for (i32 m = 0; m < a.k; m++, at += a.B) {
@@ -82,17 +89,17 @@ __global__ void __launch_bounds__(128) sample_kernel(SampleArgs a) {
         const u64 d = lcg_next(s);
         if ((float)coin < prob) {                           // keep (h,r): new tail  (Base.cpp:118-121)
             const i32 tmp = (i32)(d % (u64)(a.E - (rn.y - rn.x + 1)));
-            oh[at] = p.x; ot[at] = kth_absent(a.byh_t, rn.x, rn.y, tmp); orl[at] = p.z;
+            put(at, p.x, kth_absent(a.byh_t, rn.x, rn.y, tmp), p.z);
         } else {                                            // keep (t,r): new head  (Base.cpp:122-126)
             const i32 tmp = (i32)(d % (u64)(a.E - (rn.w - rn.z + 1)));
-            oh[at] = kth_absent(a.byt_h, rn.z, rn.w, tmp); ot[at] = p.y; orl[at] = p.z;
+            put(at, kth_absent(a.byt_h, rn.z, rn.w, tmp), p.y, p.z);
         }
     }
     if (a.kr > 0) {
         const int2 rh = __ldg(a.run_ht + row);
         for (i32 m = 0; m < a.kr; m++, at += a.B) {          // Base.cpp:133-139
             const i32 tmp = (i32)(lcg_next(s) % (u64)(a.R - (rh.y - rh.x + 1)));
-            oh[at] = p.x; ot[at] = p.y; orl[at] = kth_absent(a.byht_r, rh.x, rh.y, tmp);
+            put(at, p.x, p.y, kth_absent(a.byht_r, rh.x, rh.y, tmp));
         }
     }
 }
@@ -187,7 +194,8 @@ int okb_get_streams(okb_ctx *c, uint64_t *out, INT w) {
     return 0;
 }
 
-int okb_sample(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT stream_hi, void *stream) {
+static int sample_impl(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT stream_hi, i64 *mirror, cudaEvent_t sampled,
+                       void *stream) {
     if (!c->d_raw) OKB_FAIL(c, OKB_ERR_STATE, "import the training files first");
     if ((i64)c->state.size() != c->W) OKB_FAIL(c, OKB_ERR_STATE, "call randReset / okb_set_streams after setWorkThreads");
     if (B < 1 || k < 0 || kr < 0 || steps < 1) OKB_FAIL(c, OKB_ERR_ARG, "bad batch geometry");
@@ -202,6 +210,7 @@ int okb_sample(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT s
     a.raw = c->d_raw; a.run = c->d_run; a.run_ht = c->d_run_ht;
     a.byh_t = c->d_byh_t; a.byt_h = c->d_byt_h; a.byht_r = c->d_byht_r;
     a.prob = c->d_prob; a.state = c->d_state; a.out = c->batch.as<i32>();
+    a.mh = mirror; a.mt = mirror ? mirror + S : nullptr; a.mr = mirror ? mirror + 2 * S : nullptr;
     a.n_raw = c->n_raw; a.new_batch = c->new_batch;
     a.E = (i32)c->E; a.R = (i32)c->R; a.B = (i32)B; a.k = (i32)k; a.kr = (i32)kr; a.W = (i32)c->W;
     a.per = (i32)(B / c->W + (B % c->W ? 1 : 0));
@@ -209,12 +218,16 @@ int okb_sample(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT s
     const i64 total = B * steps;
     { ProfScope ps(c, PROF_SAMPLE, s);
     sample_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a); }
+    if (sampled) OKB_CUDA(c, cudaEventRecord(sampled, s));   // the batch is complete here; the stream advance below is not waited for
     advance_kernel<<<(unsigned)((c->W + 63) / 64), 64, 0, s>>>(c->d_state, a.W, a.B, a.per, 1 + 2 * (u64)k + (u64)kr,
                                                               a.steps, 0, a.W);   // every rank advances ALL streams
     OKB_LAUNCHED(2);
     c->state_dirty = true;
     OKB_CUDA(c, cudaGetLastError());
     return 0;
+}
+int okb_sample(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT stream_hi, void *stream) {
+    return sample_impl(c, B, k, kr, steps, stream_lo, stream_hi, nullptr, nullptr, stream);
 }
 
 int okb_batch_ptrs(okb_ctx *c, INT step, const int32_t **h, const int32_t **t, const int32_t **r) {
@@ -263,6 +276,23 @@ int okb_batch_to_host(okb_ctx *c, INT step, INT *h, INT *t, INT *r, REAL *y, voi
     }
     if (y) OKB_CUDA(c, cudaMemcpyAsync(y, dy, sizeof(float) * S, cudaMemcpyDeviceToHost, s));
     OKB_CUDA(c, cudaStreamSynchronize(s));
+    return 0;
+}
+
+// sampling() of the reference in one launch: sample one batch and return it in the caller's int64 arrays.  With one
+// page-locked block (Config's batch buffers) the sample kernel itself stores the int64 mirror over PCIe and the call
+// returns when that kernel is done (the stream advance runs behind it); otherwise okb_sample + okb_batch_to_host.
+int okb_sample_to_host(okb_ctx *c, INT B, INT k, INT kr, INT stream_lo, INT stream_hi, INT *h, INT *t, INT *r, void *stream) {
+    const i64 S = B * (1 + k + kr);
+    i64 *dh = (t == h + S && r == t + S) ? (i64 *)pinned_alias(h) : nullptr;
+    if (!dh) {
+        int rc = sample_impl(c, B, k, kr, 1, stream_lo, stream_hi, nullptr, nullptr, stream);
+        return rc ? rc : okb_batch_to_host(c, 0, h, t, r, nullptr, stream);
+    }
+    if (!c->ev_sampled) OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_sampled, cudaEventDisableTiming));
+    int rc = sample_impl(c, B, k, kr, 1, stream_lo, stream_hi, dh, c->ev_sampled, stream);
+    if (rc) return rc;
+    OKB_CUDA(c, cudaEventSynchronize(c->ev_sampled));
     return 0;
 }
 

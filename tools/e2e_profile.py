@@ -20,6 +20,12 @@ def timeit(f):
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / N * 1e6
 print("sampling()            %.1f us" % timeit(con.sampling))
 print("  sampling_device()   %.1f us (async)" % timeit(con.sampling_device))
+from openkeonspark_b200.Config import _vp, _stream
+def _y():
+    con.batch_y[:con.batch_size] = 1.0; con.batch_y[con.batch_size:] = -1.0
+print("  label fill          %.1f us" % timeit(_y))
+print("  okb_sample_to_host  %.1f us (sync)" % timeit(lambda: con.ctx.call("okb_sample_to_host", con.batch_size, con.negative_ent, con.negative_rel, 0, con.workThreads, _vp(con.batch_h_addr), _vp(con.batch_t_addr), _vp(con.batch_r_addr), _stream())))
+print("  okb_sample + okb_batch_to_host %.1f us (sync)" % timeit(lambda: (con.sampling_device(), con.ctx.call("okb_batch_to_host", 0, _vp(con.batch_h_addr), _vp(con.batch_t_addr), _vp(con.batch_r_addr), None, _stream()))))
 print("train_step()          %.1f us" % timeit(lambda: con.train_step(con.batch_h, con.batch_t, con.batch_r, con.batch_y)))
 print("  _hyper()            %.1f us" % timeit(lambda: con._hyper(False)))
 print("  train_step_device   %.1f us (async, incl. 1-step plan)" % timeit(lambda: con.train_step_device(0)))
