@@ -112,3 +112,35 @@ def test_reference_abi_sampling(built, small_ds):
         assert np.array_equal(a, b)
     lib.getEntityTotal.restype = ctypes.c_int64
     assert lib.getEntityTotal() == orc.E
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("B,k,kr,W", [(100, 1, 0, 8), (37, 2, 1, 5), (4831, 1, 0, 8)])
+def test_sample_to_host_bit_exact(built, small_ds, pinned, B, k, kr, W):
+    """okb_sample_to_host = one reference sampling() call (Base.cpp:153-177) into the caller's int64 arrays: with one
+    page-locked block the sample kernel mirrors the batch over PCIe itself, otherwise okb_sample + okb_batch_to_host.
+    Ids, the device-resident copy and the stream states must match the CPU oracle bit for bit in both forms."""
+    import torch
+    from oracle.harness import COracle
+    orc = COracle(small_ds)
+    orc.set_streams(SEEDS[:W], 1)
+    c = _ctx(small_ds, W, 1)
+    S = B * (1 + k + kr)
+    blk = torch.zeros(3 * S, dtype=torch.int64)
+    if pinned:
+        blk = blk.pin_memory()
+    a = blk.numpy()
+    p = lambda off: ctypes.c_void_p(blk.data_ptr() + 8 * off)
+    for it in range(3):
+        exp = orc.sampling(B, k, kr)
+        a[:] = -7
+        c.call("okb_sample_to_host", B, k, kr, 0, W, p(0), p(S), p(2 * S), None)
+        for j, nm in enumerate("htr"):
+            assert np.array_equal(exp[j], a[j * S:(j + 1) * S]), (nm, it)
+        dev = _gpu_batch(c, B, k, kr)                 # the batch also stays resident as step 0
+        for x, y_, nm in zip(exp, dev, "htry"):
+            assert np.array_equal(x, y_), ("device", nm, it)
+    st = np.zeros(W, np.uint64)
+    c.call("okb_get_streams", ctypes.c_void_p(st.ctypes.data), W)
+    assert np.array_equal(st, orc.streams())
+    c.close()
