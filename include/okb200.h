@@ -191,6 +191,10 @@ int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT ste
  * grid, so the loss arrives while the table update is still running and the next batch is prepared under it.  Falls
  * back to a stream synchronize if the stream goes idle first; returns OKB_ERR_CUDA if the stream failed. */
 int okb_wait_word(okb_ctx *c, const void *host_word, unsigned sentinel, void *cuda_stream);
+/* The whole host-batch step as one call: okb_batch_from_host + okb_train_step(step 0, loss -> loss_word) + okb_wait_word.
+ * loss_word: one page-locked host float (cudaHostAlloc / cudaHostRegister / torch pin_memory). */
+int okb_train_step_host(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT batch_size, INT neg_ent, INT neg_rel,
+                        const INT *h, const INT *t, const INT *r, float *loss_word, void *cuda_stream);
 
 /* ---- synchronous data-parallel training inside one box, one process per GPU (replaces the asynchronous
  *      parameter-server path of distribute_training.py:161-364).  Owner-sharded: every rank keeps the full tables in a

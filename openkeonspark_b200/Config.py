@@ -26,7 +26,6 @@ from . import _native, metrics
 from ._native import MODEL_ID, OkbError, okb_hyper, okb_model
 
 _vp = ctypes.c_void_p
-_LOSS_SENTINEL = 0xFFC0DEAD          # a NaN payload no computed loss has: "not written yet" in the page-locked loss word
 _AUX_ENT = {"TransD": "ent_transfer"}
 _AUX_REL = {"TransH": "normal_vectors", "TransR": "transfer_matrix", "TransD": "rel_transfer"}
 
@@ -491,20 +490,20 @@ class Config(object):
         r = np.ascontiguousarray(batch_r, dtype=np.int64)
         if h.size != self.batch_seq_size:
             raise OkbError("batch has %d rows, expected batch_seq_size=%d" % (h.size, self.batch_seq_size))
-        self.ctx.call("okb_batch_from_host", self.batch_size, self.negative_ent, self.negative_rel, _addr(h), _addr(t), _addr(r), _stream())
-        self._chunk_pos = self._chunk_len = 0
         if self._world is not None:
+            self.ctx.call("okb_batch_from_host", self.batch_size, self.negative_ent, self.negative_rel, _addr(h), _addr(t), _addr(r), _stream())
+            self._chunk_pos = self._chunk_len = 0
             return float(self.train_step_device(0).item())
-        # the loss comes back through one page-locked host word the update kernel stores into (no device->host copy):
-        # okb_wait_word returns as soon as it is there, while the table update of this step is still running
+        # one library call; the loss comes back through one page-locked host word the update kernel stores into (no
+        # device->host copy) and the call returns as soon as it is there, while the table update is still running
         if getattr(self, "_loss_pin", None) is None:
             self._loss_pin = torch.zeros(1, dtype=torch.float32).pin_memory()
             self._loss_pin_np = self._loss_pin.numpy()
-        self._loss_pin_np.view(np.uint32)[0] = _LOSS_SENTINEL
         m, hp = self._cmodel(), self._hyper()
-        self.ctx.call("okb_train_step", ctypes.byref(m), ctypes.byref(hp), 0, _vp(self._loss_pin.data_ptr()), _stream())
+        self._chunk_pos = self._chunk_len = 0
+        self.ctx.call("okb_train_step_host", ctypes.byref(m), ctypes.byref(hp), self.batch_size, self.negative_ent, self.negative_rel,
+                      _addr(h), _addr(t), _addr(r), _vp(self._loss_pin.data_ptr()), _stream())
         self._step += 1
-        self.ctx.call("okb_wait_word", _vp(self._loss_pin.data_ptr()), _LOSS_SENTINEL, _stream())
         return float(self._loss_pin_np[0])
 
     def _snapshot(self):

@@ -78,6 +78,7 @@ _SIGS = {
     "okb_train_step": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _vp, _vp]),
     "okb_train_steps": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _vp, _vp]),
     "okb_wait_word": (_int, [_vp, _vp, C.c_uint, _vp]),
+    "okb_train_step_host": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "okb_peer_alloc": (_int, [_vp, _i64, C.POINTER(_vp), _vp]),
     "okb_peer_open": (_int, [_vp, _vp, C.POINTER(_vp)]),
     "okb_peer_close": (_int, [_vp, _vp]),

@@ -1592,6 +1592,19 @@ int okb_wait_word(okb_ctx *c, const void *host_word, unsigned sentinel, void *st
         }
     }
 }
+int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, float *loss_out, void *stream);
+// Config.train_step(batch_h, batch_t, batch_r, batch_y) of the reference (Config.py:464-475) as ONE library call: feed the
+// host batch, run the step, return as soon as the loss has arrived in the caller's page-locked word.
+int okb_train_step_host(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT B, INT k, INT kr, const INT *h, const INT *t,
+                        const INT *r, float *loss_word, void *stream) {
+    const unsigned sentinel = 0xFFC0DEADu;                 // a NaN payload no computed loss has
+    if (!loss_word) OKB_FAIL(c, OKB_ERR_ARG, "loss_word must be a page-locked host float");
+    int rc = okb_batch_from_host(c, B, k, kr, h, t, r, stream);
+    if (rc) return rc;
+    *(volatile unsigned *)loss_word = sentinel;
+    if ((rc = okb_train_step(c, m, hp, 0, loss_word, stream))) return rc;
+    return okb_wait_word(c, loss_word, sentinel, stream);
+}
 int okb_plan(okb_ctx *c, INT step, void *stream) {
     if (planned(c, step, step + 1, 0, c->B)) return 0;          // already planned as part of a chunk
     return okb_plan_steps(c, step, step + 1, stream);
