@@ -331,7 +331,7 @@ def main():
     # ---------------- e2e: the reference-shaped loop through the public API with HOST buffers
     # con.sampling() fills the numpy batch_h/t/r/y (D2H); con.train_step(...) feeds them back (H2D) and
     # returns the loss as a Python float (D2H) — distribute_training.py:274-282.
-    e2e_steps = max(10, min(args.steps, 100))
+    e2e_steps = max(10, min(args.steps, 500))
     for _ in range(3):
         con.sampling(); con.train_step(con.batch_h, con.batch_t, con.batch_r, con.batch_y)
     barrier()
