@@ -5,7 +5,8 @@
 //   plan   (integer)  gradient-row keys of the batch -> segmented stable radix sort (radix.cu) -> per step
 //                     (sorted keys, slot permutation, row map {first, end, slot0, slot1} per table row);
 //                     whole chunks of steps are planned at once and, through okb_chunk_prefetch, one chunk
-//                     ahead on a side stream (sampling and planning never depend on the parameters)
+//                     ahead on a side stream (sampling and planning never depend on the parameters); a plan of
+//                     ONE step (the host-batch API) is a single cluster kernel (plan_small_kernel)
 //   grad   (fused)    one warp per positive: 128-bit gathers of the h/t/r rows (+ the model's auxiliary
 //                     rows) issued before the first reduction, projection, l2-normalise, L1, margin hinge
 //                     against each of its negatives, and the backward pass; rows shared between a positive
@@ -16,7 +17,9 @@
 //   update (fused)    segmented sum of the gradient rows in sorted (slot) order — a fixed fp32 order, so runs
 //                     and replicas are bit-identical — and SGD (sgd_kernel: one warp per touched row) or the
 //                     TF1 dense-decay Adam rule over every row (adam_tile_kernel: one 256-vector tile of one
-//                     table per CTA) in the same pass
+//                     table per CTA) in the same pass; the mean hinge loss is reduced by a few extra blocks of
+//                     the same launch (the FIRST blocks of the Adam grid, so that a host waiting for the loss in
+//                     a page-locked word — okb_wait_word / okb_train_step_host — gets it while the update runs)
 //
 // The grad and update kernels are chained with programmatic dependent launch (griddepcontrol): each one's
 // parameter-independent prologue overlaps the tail of its predecessor.
