@@ -70,3 +70,28 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 for needle in ("from oracle", "import oracle", "libkge_oracle", "oracle.harness", "_ref/Base.so", "orc_"):
                     assert needle not in txt, (f, needle)
+
+
+def test_ctypes_signatures_match_the_header(built):
+    """Every okb_* prototype of include/okb200.h has a ctypes signature with the same number of parameters, pointers bound
+    as pointers and 64-bit INTs as c_int64 (a drift here corrupts arguments silently and only shows on the GPU box)."""
+    from openkeonspark_b200 import _native
+    src = open(os.path.join(ROOT, "include", "okb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = re.findall(r"\b(okb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    assert len(protos) > 50
+    checked = 0
+    for name, args in protos:
+        if name not in _native._SIGS:
+            continue
+        params = [a.strip() for a in args.replace("\n", " ").split(",") if a.strip() and a.strip() != "void"]
+        res, sig = _native._SIGS[name]
+        assert len(sig) == len(params), (name, len(sig), params)
+        for p, ct in zip(params, sig):
+            is_ptr = "*" in p
+            ct_ptr = ct in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(ct, "contents")
+            assert is_ptr == ct_ptr, (name, p, ct)
+            if not is_ptr and re.match(r"(const\s+)?INT\b", p):
+                assert ct is ctypes.c_int64, (name, p, ct)
+        checked += 1
+    assert checked > 50
