@@ -248,3 +248,35 @@ def test_single_kernel_plan_equals_multi_kernel_plan(built, small_ds, tiny_ds, w
     assert outs[0][0] == outs[1][0]
     for name in outs[0][1]:
         assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
+
+
+@pytest.mark.parametrize("E,R,n_train,nbatches,k,kr", [(3000, 200, 9000, 3, 1, 0),      # 12-bit keys: 6-bit digits
+                                                        (20000, 100, 12000, 3, 2, 1),    # 15-bit keys: 8-bit digits
+                                                        (40000, 18, 20000, 4, 1, 0)])    # 16-bit keys (WN18-sized id space)
+def test_single_kernel_plan_digit_widths(built, E, R, n_train, nbatches, k, kr):
+    """The one-step plan kernel with the digit widths the file-based fixtures do not reach (they give 5 and 7 bits)."""
+    import contextlib, io
+    import openkeonspark_b200 as okb
+    from openkeonspark_b200 import datagen
+    g = datagen.make_graph(E, R, n_train, 200, 200, seed=E)
+    outs = []
+    for multi in (0, 1):
+        con = okb.Config(private_context=True)
+        con.set_nbatches(nbatches); con.set_ent_neg_rate(k); con.set_rel_neg_rate(kr); con.set_dimension(16)
+        con.set_opt_method("SGD"); con.set_alpha(0.01); con.workThreads = 4
+        with contextlib.redirect_stdout(io.StringIO()):
+            con.init_from_arrays(g.E, g.R, g.train, g.valid, g.test)
+        seeds = np.arange(1, 5, dtype=np.uint64) * np.uint64(2654435761)
+        con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), 4)
+        con.set_model_and_session(okb.TransE)
+        con.ctx.call("okb_set_flag", 9, multi)
+        con.set_parameters(make_params("TransE", con.entTotal, con.relTotal, 16, seed=5))
+        assert con.batch_size * (3 + k + kr) <= 32768
+        losses = []
+        for it in range(3):
+            con.sampling_device()
+            losses.append(float(con.train_step_device(0).item()))
+        outs.append((losses, con.get_parameters()))
+    assert outs[0][0] == outs[1][0]
+    for name in outs[0][1]:
+        assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
