@@ -95,3 +95,17 @@ def test_ctypes_signatures_match_the_header(built):
                 assert ct is ctypes.c_int64, (name, p, ct)
         checked += 1
     assert checked > 50
+
+
+def test_wait_word_host_side(built):
+    """okb_wait_word is host code: a word that already differs from the sentinel returns at once without touching CUDA; a
+    word that never changes ends in an error once the stream query fails (no device here) instead of spinning for ever."""
+    import numpy as np
+    from openkeonspark_b200 import _native
+    c = _native.Ctx()
+    w = np.array([0x3f800000], dtype=np.uint32)
+    c.call("okb_wait_word", ctypes.c_void_p(w.ctypes.data), 0xFFC0DEAD, None)
+    w[0] = 0xFFC0DEAD
+    with pytest.raises(_native.OkbError):
+        c.call("okb_wait_word", ctypes.c_void_p(w.ctypes.data), 0xFFC0DEAD, None)
+    c.close()
