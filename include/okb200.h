@@ -17,6 +17,10 @@
  *
  * No torch / C++ types cross this boundary.  The library never falls back to the CPU for the
  * hot path: without a CUDA device every compute entry point returns OKB_ERR_CUDA.
+ *
+ * Error behaviour of layer (1): like the reference (base/Reader.h:36-39 prints and returns), a failed call prints
+ * "libokb200: <symbol> failed: <why>" to stderr and returns without filling its outputs; the text stays available
+ * through okb_last_error(okb_default_ctx()).  Set OKB200_ABORT_ON_ERROR=1 to abort() instead.
  */
 #ifndef OKB200_H
 #define OKB200_H
@@ -135,6 +139,12 @@ int okb_sample_to_host(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT
 int okb_batch_from_host(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, const INT *h, const INT *t,
                         const INT *r, void *cuda_stream);
 
+/* The ids okb_batch_from_host receives are validated on the device: an id outside [0, E) / [0, R) is replaced by 0 (so
+ * nothing indexes out of bounds), the step that trains on such a batch leaves every table untouched and reports a NaN
+ * loss, and this call (synchronises the stream) returns OKB_ERR_ARG once and clears the flag.  okb_train_step_host
+ * calls it itself when the loss comes back NaN.  (TF's embedding_lookup raises InvalidArgument in the reference.) */
+int okb_batch_check(okb_ctx *c, void *cuda_stream);
+
 /* ---- model parameters: device pointers owned by the caller (row-major fp32). */
 typedef struct {
     int32_t model;        /* OKB_TRANSE .. OKB_TRANSD */
@@ -236,6 +246,15 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
 /* stream-ordered wait until every rank's row updates of all steps issued so far have landed in THIS rank's tables (a
  * rank's last update kernel stores into its peers' arenas).  Not a collective. */
 int okb_dp_quiesce(okb_ctx *c, void *cuda_stream);
+
+/* ---- TransR under data parallelism: RELATION-sharded.  TransR's gradients come out reduced per relation (one CTA owns one
+ *      relation's 40 KB matrix), so ranks split the relations instead of the positives: after okb_transr_set_shard(r_lo,
+ *      r_hi) okb_grad (called with the full positive range) computes only the positives whose relation lies in [r_lo, r_hi)
+ *      — their entity gradient rows, loss terms and the relations' [d rel | d M_r] rows — and okb_update moves only those
+ *      relations' rel_embeddings / transfer_matrix rows (entity tables: all rows, from the gradient rows the ranks have
+ *      summed).  M_r never crosses NVLink during training; the owners' rows are gathered when the tables are read.
+ *      (0, 0) restores "all relations". */
+int okb_transr_set_shard(okb_ctx *c, INT r_lo, INT r_hi);
 
 /* ---- chunk pipeline.  Sampling and planning depend only on the RNG streams, so the next chunk of steps can be produced on
  *      an internal side stream while the current chunk trains.  okb_chunk_begin makes `steps` sampled + planned steps

@@ -314,6 +314,29 @@ class Config(object):
         self._chunk_pos += 1
         return loss
 
+    # ------------------------------------------------------------------ data-parallel hygiene
+    def _owner_mode(self):
+        return self._world is not None and self._world.mode == "owner"
+
+    def _rank(self):
+        return 0 if self._world is None else self._world.rank
+
+    def _settle(self, adam=False):
+        """Owner-sharded data parallelism: before anything READS the tables, wait until every peer's last row updates have
+        landed here (a rank's final update kernel stores into its peers' arenas).  adam=True also completes the Adam
+        slots (a rank only maintains m / v for the rows it owns) — a collective, for checkpoints and snapshots."""
+        if self._owner_mode():
+            self._world.quiesce(self)
+            if adam:
+                self._world.sync_adam_slots(self)
+        elif self._world is not None and self._world.mode == "relation":
+            self._world.gather_relations(self, adam)      # TransR: relation rows live with their owners (a collective)
+
+    def _barrier(self):
+        if self._world is not None:
+            import torch.distributed as dist
+            dist.barrier(group=self._world.group)
+
     # ------------------------------------------------------------------ parameters (Config.py:379-422)
     def get_parameter_lists(self):
         return self.trainModel.parameter_lists
@@ -324,8 +347,7 @@ class Config(object):
         return None
 
     def get_parameters(self, mode="numpy"):
-        if self._world is not None and self._world.mode == "owner":
-            self._world.quiesce(self)                 # peers' last row updates have landed (not a collective)
+        self._settle()                                # peers' last row updates have landed (not a collective)
         res = {}
         for var_name in self.get_parameter_lists():
             v = self.get_parameters_by_name(var_name)
@@ -338,30 +360,57 @@ class Config(object):
         with open(path, "w") as f:
             f.write(json.dumps(self.get_parameters("list")))
 
-    def set_parameters_by_name(self, var_name, tensor):
+    def set_parameters_by_name(self, var_name, tensor, allow_partial_rows=False):
+        """Config.py:414-418 (tf.assign: a shape mismatch raises).  allow_partial_rows=True is the incremental-batch
+        case only: a model trained before new entities arrived lands in the leading rows of the grown table."""
         if var_name in self.trainModel.parameter_lists:
             dst = self.trainModel.parameter_lists[var_name]
             src = torch.as_tensor(np.asarray(tensor, dtype=np.float32))
-            if src.dim() == 2 and src.shape[1] == dst.shape[1] and src.shape[0] < dst.shape[0] and var_name in ("ent_embeddings", "ent_transfer"):
-                # a model trained before new entities arrived: its rows land in the leading rows, the new entities keep
-                # their fresh Xavier-normal rows (main_spark.py:71-75: scatter_update into a tensor of the final shape)
+            partial = (src.dim() == 2 and src.shape[1] == dst.shape[1] and src.shape[0] < dst.shape[0]
+                       and var_name in ("ent_embeddings", "ent_transfer"))
+            if partial and allow_partial_rows:
+                # main_spark.py:71-75: scatter_update of the old rows into a tensor of the final shape; the new entities
+                # keep their fresh Xavier-normal rows
                 dst[:src.shape[0]].copy_(src)
+            elif src.numel() != dst.numel():
+                raise OkbError("set_parameters: %s has shape %s, the table is %s" % (var_name, tuple(src.shape), tuple(dst.shape)))
             else:
                 dst.copy_(src.reshape(dst.shape))
 
-    def set_parameters(self, lists):
+    def set_parameters(self, lists, allow_partial_rows=False):
         for i in lists:
-            self.set_parameters_by_name(i, lists[i])
+            self.set_parameters_by_name(i, lists[i], allow_partial_rows)
 
     def save_tensorflow(self):
-        """Reference: Saver.save (Config.py:350-356).  Here: a torch checkpoint of tables + optimizer state."""
-        state = {"params": {k: v.cpu() for k, v in self.trainModel.parameter_lists.items()}, "step": self._step,
-                 "adam": None if self._adam is None else {k: v.cpu() if torch.is_tensor(v) else float(v) for k, v in self._adam.items()}}
-        torch.save(state, self.exportName)
+        """Reference: Saver.save (Config.py:350-356).  Here: a torch checkpoint of tables + optimizer state.
+        Under data parallelism this is a collective (every rank calls it); rank 0 writes the file."""
+        self._settle(adam=True)
+        if self._rank() == 0:
+            state = {"params": {k: v.cpu() for k, v in self.trainModel.parameter_lists.items()}, "step": self._step,
+                     "adam": None if self._adam is None else {k: v.cpu() if torch.is_tensor(v) else float(v) for k, v in self._adam.items()}}
+            torch.save(state, self.exportName)
+        self._barrier()
+
+    def save_tensorflow_weights(self, export_name=None, write_meta_graph=False):
+        """Config.py:358-364 (Saver.save to an explicit path; the meta graph has no counterpart here)."""
+        keep, self.exportName = self.exportName, (self.exportName if export_name is None else export_name)
+        try:
+            self.save_tensorflow()
+        finally:
+            self.exportName = keep
+
+    def import_model(self, ckpt):
+        """Config.py:366-376 (Saver.restore from an explicit checkpoint path)."""
+        self._ensure_model()
+        keep, self.importName = self.importName, ckpt
+        try:
+            self.restore_tensorflow()
+        finally:
+            self.importName = keep
 
     def restore_tensorflow(self):
         state = torch.load(self.importName, map_location="cpu")
-        self.set_parameters({k: v.numpy() for k, v in state["params"].items()})
+        self.set_parameters({k: v.numpy() for k, v in state["params"].items()}, allow_partial_rows=True)
         self._step = state.get("step", 0)
         if state.get("adam") is not None and self._adam is not None:
             for k, v in state["adam"].items():
@@ -404,6 +453,12 @@ class Config(object):
             return self._model_struct
         P = self.trainModel.parameter_lists
         name = self.trainModel.name
+        # the kernels index the tables with the context's entity / relation ids: shapes must agree (a dataset re-imported
+        # after growing needs grow_entities() first)
+        E, R = self.ctx.total(0), self.ctx.total(1)
+        if E and (P["ent_embeddings"].shape[0] != E or P["rel_embeddings"].shape[0] != R):
+            raise OkbError("tables have %d entity / %d relation rows, the loaded dataset has %d / %d (grow_entities() after a "
+                           "re-import?)" % (P["ent_embeddings"].shape[0], P["rel_embeddings"].shape[0], E, R))
         m = okb_model()
         m.model = MODEL_ID[name]
         m.ent_dim = P["ent_embeddings"].shape[1]
@@ -425,36 +480,48 @@ class Config(object):
         self._model_struct = m
         return m
 
-    def _hyper(self, advance=True):
-        hp = okb_hyper()
-        hp.margin = float(self.margin)
-        hp.beta1, hp.beta2, hp.eps = 0.9, 0.999, 1e-8
+    def _hypers(self, n=1):
+        """Hyper-parameters of the next n steps and the beta powers after them.  The powers are COMMITTED by the caller
+        (_commit_powers) only once the native call has succeeded, so a failed call leaves the Adam state in step."""
+        out = []
+        powers = None
         if self._adam is not None:
-            # tf.train.AdamOptimizer: beta powers are fp32 variables multiplied once per step;
-            # lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), all in fp32.
             b1p, b2p = self._adam["b1p"], self._adam["b2p"]
-            if advance:
+        for _ in range(n):
+            hp = okb_hyper()
+            hp.margin = float(self.margin)
+            hp.beta1, hp.beta2, hp.eps = 0.9, 0.999, 1e-8
+            if self._adam is not None:
+                # tf.train.AdamOptimizer: beta powers are fp32 variables multiplied once per step;
+                # lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), all in fp32.
                 b1p = np.float32(b1p * np.float32(0.9))
                 b2p = np.float32(b2p * np.float32(0.999))
-                self._adam["b1p"], self._adam["b2p"] = b1p, b2p
-            one = np.float32(1.0)
-            hp.lr = float(np.float32(self.alpha) * np.sqrt(one - b2p, dtype=np.float32) / (one - b1p))
-        else:
-            hp.lr = float(self.alpha)
-        return hp
+                one = np.float32(1.0)
+                hp.lr = float(np.float32(self.alpha) * np.sqrt(one - b2p, dtype=np.float32) / (one - b1p))
+                powers = (b1p, b2p)
+            else:
+                hp.lr = float(self.alpha)
+            out.append(hp)
+        return out, powers
+
+    def _commit_powers(self, powers, steps):
+        if powers is not None:
+            self._adam["b1p"], self._adam["b2p"] = powers
+        self._step += steps
 
     # ------------------------------------------------------------------ training
     def train_step_device(self, step=0):
         """loss_def + optimizer on batch `step` of the last sampling_device(); loss stays on the GPU."""
         self._ensure_model()
-        m, hp = self._cmodel(), self._hyper()
+        m = self._cmodel()
+        (hp,), powers = self._hypers(1)
         if self._world is not None and self._world.mode == "owner":
             self.ctx.call("okb_dp_train_steps", ctypes.byref(m), ctypes.byref(hp), step, 1, _vp(self._loss_dev.data_ptr()), _stream())
         elif self._world is not None:
             self._world.train_step(self, m, hp, step)
         else:
             self.ctx.call("okb_train_step", ctypes.byref(m), ctypes.byref(hp), step, _vp(self._loss_dev.data_ptr()), _stream())
-        self._step += 1
+        self._commit_powers(powers, 1)
         return self._loss_dev
 
     def train_chunk_device(self, n=None, n_next=None):
@@ -474,11 +541,12 @@ class Config(object):
         if n_next > 0:                                # sample + plan the next chunk on the side stream while this one trains
             self.ctx.call("okb_chunk_prefetch", *a, n_next, _stream())
         m = self._cmodel()
-        hps = (okb_hyper * n)(*[self._hyper() for _ in range(n)])
+        hl, powers = self._hypers(n)
+        hps = (okb_hyper * n)(*hl)
         if getattr(self, "_loss_chunk", None) is None or self._loss_chunk.numel() < n:
             self._loss_chunk = torch.zeros(n, dtype=torch.float32, device=self.trainModel.device)
         self.ctx.call("okb_train_steps", ctypes.byref(m), hps, 0, n, _vp(self._loss_chunk.data_ptr()), _stream())
-        self._step += n
+        self._commit_powers(powers, n)
         self._chunk_pos = self._chunk_len = 0
         return self._loss_chunk[:n]
 
@@ -492,6 +560,7 @@ class Config(object):
             raise OkbError("batch has %d rows, expected batch_seq_size=%d" % (h.size, self.batch_seq_size))
         if self._world is not None:
             self.ctx.call("okb_batch_from_host", self.batch_size, self.negative_ent, self.negative_rel, _addr(h), _addr(t), _addr(r), _stream())
+            self.ctx.call("okb_batch_check", _stream())       # ids outside the tables raise here, before any rank steps
             self._chunk_pos = self._chunk_len = 0
             return float(self.train_step_device(0).item())
         # one library call; the loss comes back through one page-locked host word the update kernel stores into (no
@@ -499,21 +568,26 @@ class Config(object):
         if getattr(self, "_loss_pin", None) is None:
             self._loss_pin = torch.zeros(1, dtype=torch.float32).pin_memory()
             self._loss_pin_np = self._loss_pin.numpy()
-        m, hp = self._cmodel(), self._hyper()
+        m = self._cmodel()
+        (hp,), powers = self._hypers(1)
         self._chunk_pos = self._chunk_len = 0
         self.ctx.call("okb_train_step_host", ctypes.byref(m), ctypes.byref(hp), self.batch_size, self.negative_ent, self.negative_rel,
                       _addr(h), _addr(t), _addr(r), _vp(self._loss_pin.data_ptr()), _stream())
-        self._step += 1
+        self._commit_powers(powers, 1)
         return float(self._loss_pin_np[0])
 
     def _snapshot(self):
-        """Device-side copy of everything a reference checkpoint holds: tables, Adam slots, beta powers, step."""
+        """Device-side copy of everything a reference checkpoint holds: tables, Adam slots, beta powers, step.
+        (Collective under owner-sharded data parallelism: the Adam slots are completed first.)"""
+        self._settle(adam=True)
         snap = {"params": {k: v.clone() for k, v in self.trainModel.parameter_lists.items()}, "step": self._step, "adam": None}
         if self._adam is not None:
             snap["adam"] = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self._adam.items()}
         return snap
 
     def _restore_snapshot(self, snap):
+        self._settle()                                # no peer may still be storing rows into the tables being overwritten
+        self._barrier()
         for k, v in snap["params"].items():
             self.trainModel.parameter_lists[k].copy_(v)
         if snap["adam"] is not None:
@@ -606,16 +680,19 @@ class Config(object):
             # steps (both are multiples of nbatches), so that is the snapshot taken when the best value was seen
             self._restore_snapshot(best_snap_acc if self.early_stop["reason"] == "accuracy" else best_snap_loss)
             self.early_stop.update(best_acc=best_acc, best_loss=best_loss, checks=checks)
-            if self.out_path is not None:
+            if self.out_path is not None and self._rank() == 0:
                 import os as _os
                 with open(_os.path.join(_os.path.dirname(self.out_path) or ".", "stop.txt"), "w") as f:
                     f.write(str(self.early_stop["best_step"]) + "\n")
         elif es:
             self.early_stop = {"reason": None, "best_step": None, "best_acc": best_acc, "best_loss": best_loss, "checks": checks}
         if self.exportName is not None:
-            self.save_tensorflow()
+            self.save_tensorflow()                    # collective; rank 0 writes
         if self.out_path is not None:
-            self.save_parameters(self.out_path)
+            self._settle()
+            if self._rank() == 0:
+                self.save_parameters(self.out_path)
+            self._barrier()
         return losses
 
     def grow_entities(self, n_new, seed=None):
@@ -651,6 +728,7 @@ class Config(object):
     def test_step(self, test_h, test_t, test_r):
         """predict for arbitrary triples: float32 [n] (TransE) or [n,1] (TransH/R/D)."""
         self._ensure_model()
+        self._settle()
         dev = self.trainModel.device
         h = torch.as_tensor(np.ascontiguousarray(test_h, dtype=np.int64)).to(dev)
         t = torch.as_tensor(np.ascontiguousarray(test_t, dtype=np.int64)).to(dev)

@@ -70,6 +70,7 @@ _SIGS = {
     "okb_batch_to_host": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "okb_sample_to_host": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "okb_batch_from_host": (_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "okb_batch_check": (_int, [_vp, _vp]),
     "okb_grad_sizes": (_int, [_vp, C.POINTER(okb_model), _i64, _i64, _i64] + [C.POINTER(_i64)] * 4),
     "okb_plan": (_int, [_vp, _i64, _vp]),
     "okb_plan_steps": (_int, [_vp, _i64, _i64, _vp]),
@@ -88,6 +89,7 @@ _SIGS = {
     "okb_dp_detach": (_int, [_vp]),
     "okb_dp_train_steps": (_int, [_vp, C.POINTER(okb_model), C.POINTER(okb_hyper), _i64, _i64, _vp, _vp]),
     "okb_dp_quiesce": (_int, [_vp, _vp]),
+    "okb_transr_set_shard": (_int, [_vp, _i64, _i64]),
     "okb_chunk_begin": (_int, [_vp, _i64, _i64, _i64, _i64, _vp]),
     "okb_chunk_prefetch": (_int, [_vp, _i64, _i64, _i64, _i64, _vp]),
     "okb_predict": (_int, [_vp, C.POINTER(okb_model), _vp, _vp, _vp, _i64, _vp, _vp]),

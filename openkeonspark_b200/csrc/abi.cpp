@@ -4,19 +4,27 @@
 // this library unchanged.  Every compute call lands on the CUDA kernels; nothing here falls back
 // to a CPU implementation of the hot path.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+
+#include <algorithm>
 
 #include "okb_internal.h"
 
 
 static okb_ctx *g_ctx = nullptr;
 
+// The reference ABI has void returns and reports problems by printing and returning (Reader.h:36-39: a missing file
+// prints a message, the totals stay 0).  Same here: the message goes to stderr AND stays readable through
+// okb_last_error(okb_default_ctx()); nothing is computed on the CPU instead.  OKB200_ABORT_ON_ERROR=1 turns every
+// failure into abort() for callers that would rather die than continue with unfilled output buffers.
 static void die(okb_ctx *c, const char *where) {
-    // The reference ABI has void returns; a failed GPU call must not pass silently.
     fprintf(stderr, "libokb200: %s failed: %s\n", where, c->err.c_str());
-    abort();
+    const char *e = getenv("OKB200_ABORT_ON_ERROR");
+    if (e && e[0] == '1') abort();
 }
-#define MUST(call, where) do { if ((call) != 0) die(g_ctx_get(), where); } while (0)
+#define MUST(call, where) do { if ((call) != 0) { die(g_ctx_get(), where); return; } } while (0)
+#define MUSTV(call, where, val) do { if ((call) != 0) { die(g_ctx_get(), where); return (val); } } while (0)
 
 static okb_ctx *g_ctx_get() {
     if (!g_ctx) g_ctx = new okb_ctx();
@@ -43,7 +51,8 @@ int okb_destroy(okb_ctx *c) {
         if (L->d_ids) cudaFree(L->d_ids);
     }
     for (DevBuf *b : {&c->batch, &c->keys_ent, &c->keys_rel, &c->perm_ent, &c->perm_rel, &c->sort_tmp, &c->hist, &c->gent, &c->grel,
-                      &c->flags, &c->lossterms, &c->rowseg_e, &c->rowseg_r, &c->rank_ws, &c->host_io, &c->partial})
+                      &c->flags, &c->lossterms, &c->rowseg_e, &c->rowseg_r, &c->rank_ws, &c->host_io, &c->partial, &c->legacy_scores,
+                      &c->legacy_out})
         b->release();
     for (DevBuf *b : {&c->alt.batch, &c->alt.keys_ent, &c->alt.perm_ent, &c->alt.rowseg_e, &c->alt.sort_tmp, &c->alt.hist}) b->release();
     if (c->d_state_saved) cudaFree(c->d_state_saved);
@@ -121,21 +130,30 @@ void sampling(INT *bh, INT *bt, INT *br, REAL *by, INT B, INT k, INT kr) {
     MUST(okb_sample(c, B, k, kr, 1, 0, c->W, nullptr), "sampling");
     MUST(okb_batch_to_host(c, 0, bh, bt, br, by, nullptr), "sampling");
 }
+static bool legacy_index_ok(okb_ctx *c, INT index, const char *where) {
+    if (index >= 0 && index < c->n_test) return true;
+    c->err = "test index out of range (import the test files first)";
+    die(c, where);
+    return false;
+}
 
 void getHeadBatch(INT index, INT *ph, INT *pt, INT *pr) {              // Test.h:11-17 (candidate fill; pure host)
     okb_ctx *c = g_ctx_get();
+    if (!legacy_index_ok(c, index, "getHeadBatch")) return;
     for (INT i = 0; i < c->E; i++) { ph[i] = i; pt[i] = c->test_t[index]; pr[i] = c->test_r[index]; }
 }
 void getTailBatch(INT index, INT *ph, INT *pt, INT *pr) {              // Test.h:20-26
     okb_ctx *c = g_ctx_get();
+    if (!legacy_index_ok(c, index, "getTailBatch")) return;
     for (INT i = 0; i < c->E; i++) { ph[i] = c->test_h[index]; pt[i] = i; pr[i] = c->test_r[index]; }
 }
 static INT *rank_host(INT index, REAL *con, int side) {
     okb_ctx *c = g_ctx_get();
-    static DevBuf dscores, dout;
-    if (dscores.ensure(sizeof(float) * c->E) || dout.ensure(sizeof(i64) * 8)) { c->err = "out of device memory"; die(c, "testHead/testTail"); }
-    if (cudaMemcpy(dscores.p, con, sizeof(float) * c->E, cudaMemcpyHostToDevice) != cudaSuccess) { c->err = "H2D copy failed"; die(c, "testHead/testTail"); }
-    MUST(okb_rank_scores(c, index, side, dscores.as<float>(), dout.as<i64>(), nullptr), "testHead/testTail");
+    DevBuf &dscores = c->legacy_scores, &dout = c->legacy_out;       // per context, not per process
+    for (int i = 0; i < 8; i++) c->res8[i] = 0;
+    if (dscores.ensure(sizeof(float) * std::max<i64>(c->E, 1)) || dout.ensure(sizeof(i64) * 8)) { c->err = "out of device memory"; die(c, "testHead/testTail"); return c->res8; }
+    if (cudaMemcpy(dscores.p, con, sizeof(float) * c->E, cudaMemcpyHostToDevice) != cudaSuccess) { c->err = "H2D copy failed"; die(c, "testHead/testTail"); return c->res8; }
+    MUSTV(okb_rank_scores(c, index, side, dscores.as<float>(), dout.as<i64>(), nullptr), "testHead/testTail", c->res8);
     if (cudaMemcpy(c->res8, dout.p, sizeof(i64) * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { c->err = "D2H copy failed"; die(c, "testHead/testTail"); }
     return c->res8;
 }

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -80,6 +82,7 @@ struct okb_ctx {
     i64 plan_b_lo = 0, plan_b_hi = 0;                          // ... for positives [plan_b_lo, plan_b_hi) of each step
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
+    bool batch_from_host = false;     // the current batch came through okb_batch_from_host: update kernels honour the "bad id" flag
     bool plan_multi = false;          // OKB_FLAG_PLAN_MULTI: one-step plans use the multi-kernel sort too
     bool plan_small_attr = false;     // dynamic shared memory limit of plan_small_kernel raised on this device
     bool grad_single_warp = false;    // OKB_FLAG_GRAD_SINGLE_WARP: never split a positive's negatives over several warps
@@ -87,6 +90,7 @@ struct okb_ctx {
     bool adam_legacy = false;         // OKB_FLAG_ADAM_LEGACY: grid-stride register kernel instead of the tile kernel
     bool adam_tma = false;            // OKB_FLAG_ADAM_TMA: TMA-staged single-wave Adam pass instead of the register-only one
     bool l2_prefetch = false;         // OKB_FLAG_L2_PREFETCH: grad kernel prefetches the Adam state into L2
+    i64 tr_lo = 0, tr_hi = 0;         // TransR relation shard [tr_lo, tr_hi) (okb_transr_set_shard); empty = all relations
     okb_dp dp = {};                   // owner-sharded data parallelism (okb_dp_attach)
     bool dp_on = false;
     unsigned long long dp_epoch = 0;
@@ -106,7 +110,30 @@ struct okb_ctx {
     // legacy result buffers
     i64 res8[8];
     std::vector<i64> tpfp;
+    // ---------------- per-context device facts / function attributes (never process-global: one context per device)
+    int sm_count = 0;                 // multiProcessorCount of the context's device (okb_sms)
+    std::map<const void *, size_t> smem_attr;   // largest dynamic shared memory opted into per kernel on this device
+    DevBuf legacy_scores, legacy_out; // testHead / testTail staging of the reference-compatible layer
 };
+
+// number of SMs of the current device (grids are sized in multiples of it)
+static inline int okb_sms(okb_ctx *c) {
+    if (c->sm_count <= 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            c->sm_count = n;
+        else { cudaGetLastError(); return 148; }
+    }
+    return c->sm_count;
+}
+// opt a kernel into `bytes` of dynamic shared memory once per context (cudaFuncSetAttribute is a per-device setting)
+template <class F> static inline cudaError_t okb_smem_optin(okb_ctx *c, F *fn, size_t bytes) {
+    size_t &have = c->smem_attr[(const void *)fn];
+    if (bytes <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+}
 
 #define OKB_FAIL(c, code, msg) do { (c)->err = (msg); return (code); } while (0)
 #define OKB_CUDA(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
@@ -127,8 +154,8 @@ struct ProfScope {                     // records an event pair around the launc
     ~ProfScope() { prof_mark(c, id, s); }
 };
 
-extern i64 g_launches;                // kernels launched by this library
-#define OKB_LAUNCHED(n) (g_launches += (n))
+extern std::atomic<long long> g_launches;   // kernels launched by this library (all contexts, all threads)
+#define OKB_LAUNCHED(n) (g_launches.fetch_add((n), std::memory_order_relaxed))
 
 // loader.cpp
 int okb_upload_train(okb_ctx *c);
@@ -136,6 +163,11 @@ int okb_upload_test(okb_ctx *c);
 int okb_upload_lists(okb_ctx *c);
 bool okb_host_find(const okb_ctx *c, i64 h, i64 t, i64 r);
 i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(0, h, r) on stream 0
+
+// okb_ctx::flags, in 4-byte words: [0,64) partial loss sums | [64] loss ticket | [68] "bad id" flag of the host-batch path
+#define OKB_FLAGS_BYTES (sizeof(float) * 64 + 32)
+#define OKB_FLAGS_BAD 68
+int okb_ensure_flags(okb_ctx *c, cudaStream_t s);     // train.cu: allocate + zero once
 
 // train.cu: forget a prefetched chunk (restores the RNG streams); every entry point that touches the streams calls it
 int okb_discard_prefetch(okb_ctx *c);

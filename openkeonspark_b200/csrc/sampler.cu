@@ -12,7 +12,7 @@
 
 #include "okb_internal.h"
 
-i64 g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 #define LCG_A 25214903917ULL
 #define LCG_C 11ULL
@@ -123,11 +123,17 @@ __global__ void widen_kernel(const i32 *__restrict__ src, i64 *__restrict__ h, i
     h[i] = src[i]; t[i] = src[S + i]; r[i] = src[2 * S + i];
     y[i] = i < B ? 1.0f : -1.0f;                            // Base.cpp:111,127,137
 }
+// Caller-supplied ids are VALIDATED here (TF's embedding_lookup raises InvalidArgument for an id outside the table): a bad id
+// is replaced by 0 — nothing downstream can index out of bounds — and raises the context's "bad id" flag, which makes
+// the update kernels of the step leave the tables alone and report a NaN loss; the host then returns OKB_ERR_ARG.
 __global__ void narrow_kernel(const i64 *__restrict__ h, const i64 *__restrict__ t, const i64 *__restrict__ r,
-                              i32 *__restrict__ dst, i32 S) {
+                              i32 *__restrict__ dst, i32 S, i64 E, i64 R, unsigned *__restrict__ bad) {
     const i32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= S) return;
-    dst[i] = (i32)h[i]; dst[S + i] = (i32)t[i]; dst[2 * S + i] = (i32)r[i];
+    const i64 vh = h[i], vt = t[i], vr = r[i];
+    const bool ok = vh >= 0 && vh < E && vt >= 0 && vt < E && vr >= 0 && vr < R;
+    dst[i] = ok ? (i32)vh : 0; dst[S + i] = ok ? (i32)vt : 0; dst[2 * S + i] = ok ? (i32)vr : 0;
+    if (!ok) atomicOr(bad, 1u);
 }
 
 static int push_state(okb_ctx *c) {
@@ -205,6 +211,7 @@ static int sample_impl(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_l
     const i64 S = B * (1 + k + kr);
     if (c->batch.ensure(sizeof(i32) * 3 * S * steps)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (batch)");
     c->B = B; c->K = k; c->KR = kr; c->steps = steps;
+    c->batch_from_host = false;
     c->plan_lo = c->plan_hi = 0;                            // new batches: any previous plan is stale
     SampleArgs a;
     a.raw = c->d_raw; a.run = c->d_run; a.run_ht = c->d_run_ht;
@@ -301,11 +308,17 @@ int okb_batch_from_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const IN
     const i64 S = B * (1 + k + kr);
     if (c->batch.ensure(sizeof(i32) * 3 * S)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (batch)");
     if (c->host_io.ensure(sizeof(i64) * 3 * S)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+    if (B < 1 || k < 0 || kr < 0 || !h || !t || !r) OKB_FAIL(c, OKB_ERR_ARG, "bad batch geometry");
+    if (c->E < 1 || c->R < 1) OKB_FAIL(c, OKB_ERR_STATE, "import the training files first");
+    int rcf = okb_ensure_flags(c, s);
+    if (rcf) return rcf;
+    unsigned *bad = c->flags.as<unsigned>() + OKB_FLAGS_BAD;
     c->B = B; c->K = k; c->KR = kr; c->steps = 1;
+    c->batch_from_host = true;
     c->plan_lo = c->plan_hi = 0;
     if (t == h + S && r == t + S) {                        // one pinned block: the narrowing kernel reads it over PCIe itself
         if (const i64 *ph = (const i64 *)pinned_alias(h)) {
-            narrow_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(ph, ph + S, ph + 2 * S, c->batch.as<i32>(), (i32)S);
+            narrow_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(ph, ph + S, ph + 2 * S, c->batch.as<i32>(), (i32)S, c->E, c->R, bad);
             OKB_LAUNCHED(1);
             OKB_CUDA(c, cudaGetLastError());
             return 0;
@@ -319,7 +332,7 @@ int okb_batch_from_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const IN
         OKB_CUDA(c, cudaMemcpyAsync(dt, t, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
         OKB_CUDA(c, cudaMemcpyAsync(dr, r, sizeof(i64) * S, cudaMemcpyHostToDevice, s));
     }
-    narrow_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(dh, dt, dr, c->batch.as<i32>(), (i32)S);
+    narrow_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(dh, dt, dr, c->batch.as<i32>(), (i32)S, c->E, c->R, bad);
     OKB_LAUNCHED(1);
     // no synchronisation needed: the copies are stream-ordered before the kernel; pageable sources are
     // staged by the driver before the call returns, pinned sources must stay untouched until the step ran
@@ -328,6 +341,18 @@ int okb_batch_from_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const IN
     return 0;
 }
 
-INT okb_launch_count(void) { return g_launches; }
+// Stream-ordered check of the ids the last okb_batch_from_host received: synchronises, returns OKB_ERR_ARG if any id was
+// outside [0, E) / [0, R) (the flag is cleared, the batch of such a call must not be trained on).
+int okb_batch_check(okb_ctx *c, void *stream) {
+    if (!c->flags.p) return 0;
+    unsigned bad = 0;
+    OKB_CUDA(c, cudaStreamSynchronize((cudaStream_t)stream));
+    OKB_CUDA(c, cudaMemcpy(&bad, c->flags.as<unsigned>() + OKB_FLAGS_BAD, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    if (!bad) return 0;
+    OKB_CUDA(c, cudaMemset(c->flags.as<unsigned>() + OKB_FLAGS_BAD, 0, sizeof(unsigned)));
+    OKB_FAIL(c, OKB_ERR_ARG, "batch contains an entity or relation id outside the tables (InvalidArgument in the reference's embedding_lookup)");
+}
+
+INT okb_launch_count(void) { return (INT)g_launches.load(); }
 
 }  // extern "C"

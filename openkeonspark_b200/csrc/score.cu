@@ -721,17 +721,12 @@ int okb_rank(okb_ctx *c, const okb_model *m, INT q_lo, INT q_hi, int heads, INT 
     const size_t NQ = (size_t)QGsel * QB;
     const size_t smem_rank = rank_smem(QGsel);
     if (smem_rank > 227 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "embedding dimension too large for the ranking tile");
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(rank_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(rank_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(rank_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(rank_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(rank_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(rank_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(qvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_done = true;
+    {   // per context (= per device), not per process
+        const size_t lim = 227 * 1024;
+        OKB_CUDA(c, okb_smem_optin(c, rank_kernel<true, 2>, lim)); OKB_CUDA(c, okb_smem_optin(c, rank_kernel<false, 2>, lim));
+        OKB_CUDA(c, okb_smem_optin(c, rank_kernel<true, 3>, lim)); OKB_CUDA(c, okb_smem_optin(c, rank_kernel<false, 3>, lim));
+        OKB_CUDA(c, okb_smem_optin(c, rank_kernel<true, 4>, lim)); OKB_CUDA(c, okb_smem_optin(c, rank_kernel<false, 4>, lim));
+        OKB_CUDA(c, okb_smem_optin(c, cand_kernel, lim)); OKB_CUDA(c, okb_smem_optin(c, qvec_kernel, lim));
     }
     const bool second = m->model == OKB_TRANSD || m->model == OKB_TRANSR;
     const size_t s2 = (m->model == OKB_TRANSR ? D : Din) + 1;
@@ -862,7 +857,7 @@ int okb_rank_scores(okb_ctx *c, INT index, int side, const float *scores, int64_
     a.known = side ? c->d_known_t : c->d_known_h;
     a.klo = side ? run.x : run.z; a.khi = side ? run.y : run.w;
     a.counts = cnt + (side ? 4 : 0); a.best = bst + (side ? 4 : 0);
-    rank_scores_kernel<<<148, 256, 0, s>>>(a);
+    rank_scores_kernel<<<okb_sms(c), 256, 0, s>>>(a);
     OKB_LAUNCHED(1);
     if (c->host_io.ensure(sizeof(i64) * 16)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
     int rc = okb_rank_finalize(c, index, index + 1, (const int64_t *)cnt, (const uint64_t *)bst, c->host_io.as<i64>(), stream);

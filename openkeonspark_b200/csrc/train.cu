@@ -977,9 +977,11 @@ struct UpdArgs {
     i32 pcols, hub, by_row, loss_blocks;
     float *loss_part;
     unsigned *loss_ctr;
+    const unsigned *bad;       // "bad id" flag of the host-batch path (narrow_kernel): set -> tables untouched, loss = NaN
     i32 n, n_ent_slots, E, R, ce, cr, B, key_limit, ntab, work_blocks;
     float w;
 };
+__device__ __forceinline__ bool upd_bad(const UpdArgs &a) { return a.bad && *(const volatile unsigned *)a.bad != 0u; }
 
 // mean hinge over B*(k+kr) pairs in a fixed order, by `loss_blocks` extra blocks of the update launch: each
 // sums a fixed contiguous range of the per-positive terms; the block that finishes last adds the partial
@@ -1014,7 +1016,7 @@ __device__ __forceinline__ void loss_block(const UpdArgs &a, i32 lb) {
         __threadfence();
         float tot = 0.f;
         for (i32 q = 0; q < a.loss_blocks; q++) tot += ((volatile float *)a.loss_part)[q];
-        a.loss_out[0] = tot * a.w;
+        a.loss_out[0] = upd_bad(a) ? __int_as_float(0x7fc00000) : tot * a.w;
         *a.loss_ctr = 0u;
         __threadfence_system();                            // loss_out may be page-locked host memory a waiting caller polls
     }
@@ -1093,6 +1095,7 @@ template <int VW, int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
     constexpr int N = VW * NV;
     if ((i32)blockIdx.x >= a.work_blocks) { loss_block(a, (i32)blockIdx.x - a.work_blocks); return; }
+    if (upd_bad(a)) return;
     const int lane = threadIdx.x & 31;
     const i32 w = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     i32 key, i, end;
@@ -1138,6 +1141,7 @@ template <int VW>
 __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
     pdl_launch_dependents();
     if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a, (i32)blockIdx.x - a.work_blocks); return; }
+    if (upd_bad(a)) return;
     typedef typename VecT<VW>::T V;
     const i64 total = a.tab[a.ntab - 1].vec_end;
     const i64 stride = (i64)a.work_blocks * blockDim.x;
@@ -1240,8 +1244,10 @@ __global__ void __launch_bounds__(256, ADAM_TILE_MIN_BLOCKS) adam_tile_kernel(Up
     const size_t e = (size_t)lv * VW;
     float *px = T.x + e, *pm = T.m + e, *pv = T.v + e;
     const int4 seg = __ldg(a.rowhead + T.key_off + row);
+    const unsigned badv = a.bad ? *(const volatile unsigned *)a.bad : 0u;     // host-batch steps only (see narrow_kernel)
     V xv = *reinterpret_cast<const V *>(px), mv = *reinterpret_cast<const V *>(pm), vv = *reinterpret_cast<const V *>(pv);
     pdl_wait();                                            // gradient rows of this step are complete from here on
+    if (badv) return;
     float g[VW];
 #pragma unroll
     for (int q = 0; q < VW; q++) g[q] = 0.f;
@@ -1319,6 +1325,7 @@ __global__ void __launch_bounds__(AP_TILE, 2) adam_pipe_kernel(UpdArgs a, int nt
     unsigned long long *full = reinterpret_cast<unsigned long long *>(st + AP_STAGES);
     const int G = a.work_blocks, tid = threadIdx.x;
     if ((int)blockIdx.x >= G) { pdl_launch_dependents(); pdl_wait(); loss_block(a, (i32)blockIdx.x - G); return; }
+    if (upd_bad(a)) { pdl_launch_dependents(); return; }
     const int my_n = (ntiles - (int)blockIdx.x + G - 1) / G;         // this CTA's tiles: blockIdx.x + j * G
     if (tid == 0) {
         for (int s = 0; s < AP_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_smem(full + s)));
@@ -1498,6 +1505,12 @@ static void group_cols(const okb_model *m, i32 &ce, i32 &cr) {
     if (m->model == OKB_TRANSR) cr = m->rel_dim + m->ent_dim * m->rel_dim;     // [d rel | d M_r], one row per RELATION
 }
 
+int okb_ensure_flags(okb_ctx *c, cudaStream_t s) {
+    if (c->flags.ensure(OKB_FLAGS_BYTES)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+    if (!c->loss_ctr_ready) { OKB_CUDA(c, cudaMemsetAsync(c->flags.p, 0, OKB_FLAGS_BYTES, s)); c->loss_ctr_ready = true; }
+    return 0;
+}
+
 // per-step map table row -> {first, end, slot0, slot1} in the sorted plan, built once per planned chunk
 static int ensure_rowhead(okb_ctx *c, cudaStream_t s) {
     if (c->rowhead_ready) return 0;
@@ -1557,10 +1570,7 @@ static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, 
         q.chunk = (i32)chunk;
         q.magic_e = (unsigned)(((1ull << 32) + NE - 1) / NE); q.magic_r = (unsigned)(((1ull << 32) + NR - 1) / NR);
         const size_t smem = (size_t)(2 * chunk * PS_WARPS + PS_WARPS * (ndig + 1) + 2 * ndig + PS_WARPS) * 4;
-        if (!c->plan_small_attr) {                         // up to 2 x 16 KB of items + 33 KB of counters
-            OKB_CUDA(c, cudaFuncSetAttribute(plan_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-            c->plan_small_attr = true;
-        }
+        OKB_CUDA(c, okb_smem_optin(c, plan_small_kernel, 80 * 1024));     // up to 2 x 16 KB of items + 33 KB of counters
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(PS_CTAS); cfg.blockDim = dim3(PS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
         cudaLaunchAttribute at[1];
@@ -1596,6 +1606,7 @@ int okb_wait_word(okb_ctx *c, const void *host_word, unsigned sentinel, void *st
     }
 }
 int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, float *loss_out, void *stream);
+int okb_batch_check(okb_ctx *c, void *stream);
 // Config.train_step(batch_h, batch_t, batch_r, batch_y) of the reference (Config.py:464-475) as ONE library call: feed the
 // host batch, run the step, return as soon as the loss has arrived in the caller's page-locked word.
 int okb_train_step_host(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT B, INT k, INT kr, const INT *h, const INT *t,
@@ -1606,7 +1617,9 @@ int okb_train_step_host(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT
     if (rc) return rc;
     *(volatile unsigned *)loss_word = sentinel;
     if ((rc = okb_train_step(c, m, hp, 0, loss_word, stream))) return rc;
-    return okb_wait_word(c, loss_word, sentinel, stream);
+    if ((rc = okb_wait_word(c, loss_word, sentinel, stream))) return rc;
+    if (*(volatile float *)loss_word != *(volatile float *)loss_word) return okb_batch_check(c, stream);   // NaN: an id was out of range?
+    return 0;
 }
 int okb_plan(okb_ctx *c, INT step, void *stream) {
     if (planned(c, step, step + 1, 0, c->B)) return 0;          // already planned as part of a chunk
@@ -1686,7 +1699,7 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     // small batches with several negatives: 2..4 warps per positive, as many as fill ~20 warp slots per SM
     int wpp = 1;
     // (a function of the GLOBAL batch, so that a data-parallel rank's slice is computed exactly like the same positives on one GPU)
-    if (!k1 && c->K >= 2 && !c->grad_single_warp) wpp = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(4, c->K), (i64)148 * 20 / std::max<i64>(1, c->B)));
+    if (!k1 && c->K >= 2 && !c->grad_single_warp) wpp = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(4, c->K), (i64)okb_sms(c) * 20 / std::max<i64>(1, c->B)));
     if (wpp > 1) {
         const int N = vw * nv, F = 2 * (m->model == OKB_TRANSD ? 2 : 1) + (m->model == OKB_TRANSE ? 1 : 2);
         cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32 * wpp);
@@ -1730,9 +1743,9 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
     a.hub = (double)c->plan_ne * c->max_ent_share > PCH || (!is_tr && (double)c->plan_nr * c->max_rel_share > PCH);
     a.partial = nullptr; a.by_row = 0;
     a.loss_blocks = (i32)std::max<i64>(1, std::min<i64>(64, c->B / 8192));
-    if (c->flags.ensure(sizeof(float) * 64 + 16)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
-    if (!c->loss_ctr_ready) { OKB_CUDA(c, cudaMemsetAsync(c->flags.p, 0, sizeof(float) * 64 + 16, s)); c->loss_ctr_ready = true; }
+    if ((rc = okb_ensure_flags(c, s))) return rc;
     a.loss_part = c->flags.as<float>(); a.loss_ctr = (unsigned *)(c->flags.as<float>() + 64);
+    a.bad = c->batch_from_host ? c->flags.as<unsigned>() + OKB_FLAGS_BAD : nullptr;
     if (a.hub) {
         const i64 nblocks = n / PCH;
         if (c->partial.ensure(sizeof(float) * (size_t)(nblocks + 1) * a.pcols)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (partial sums)");
@@ -1773,7 +1786,7 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
 #ifdef EXP_ADAM_BLOCKS
         a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)EXP_ADAM_BLOCKS);
 #else
-        a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)148 * 16);
+        a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)okb_sms(c) * 16);
 #endif
         ProfScope ps(c, PROF_UPDATE, s);
         // programmatic dependent launch: the kernel may start while the grad kernel drains (see adam_kernel)
@@ -1784,10 +1797,9 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         at[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
         if (vw == 4 && c->adam_tma) {                      // pipelined TMA ring (see adam_pipe_kernel)
-            static bool attr = false;
             const size_t smem = sizeof(ApStage) * AP_STAGES + 8 * AP_STAGES;
-            if (!attr) { OKB_CUDA(c, cudaFuncSetAttribute(adam_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-            a.work_blocks = std::min<i32>(blk, 148 * 2);
+            OKB_CUDA(c, okb_smem_optin(c, adam_pipe_kernel, smem));
+            a.work_blocks = std::min<i32>(blk, okb_sms(c) * 2);
             cfg.gridDim = dim3((unsigned)(a.work_blocks + a.loss_blocks)); cfg.dynamicSmemBytes = smem;
             OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_pipe_kernel, a, (int)blk));
         } else if (lean) {                                 // one tile per CTA, block-uniform table (adam_tile_kernel)
@@ -2162,7 +2174,7 @@ static void fill_upd_args(okb_ctx *c, const okb_model *m, const okb_hyper *hp, I
     a.pcols = std::max(a.ce, a.cr);
     a.hub = (double)c->plan_ne * c->max_ent_share > PCH || (double)c->plan_nr * c->max_rel_share > PCH;
     a.partial = nullptr; a.by_row = 1; a.loss_blocks = 1;
-    a.loss_part = nullptr; a.loss_ctr = nullptr;
+    a.loss_part = nullptr; a.loss_ctr = nullptr; a.bad = nullptr;
 }
 
 extern "C" {
@@ -2308,7 +2320,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
             if (m->model == OKB_TRANSD) addt(P.off_ent_aux, m->m_ent_aux, m->v_ent_aux, true, 1);
             addt(P.off_rel, m->m_rel, m->v_rel, false, 0);
             if (m->model != OKB_TRANSE) addt(P.off_rel_aux, m->m_rel_aux, m->v_rel_aux, false, 1);
-            o.work_blocks = (i32)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)148 * 8));
+            o.work_blocks = (i32)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)okb_sms(c) * 8));
             cudaLaunchConfig_t oc = {};
             oc.gridDim = dim3((unsigned)o.work_blocks + 1); oc.blockDim = dim3(256); oc.stream = s; oc.attrs = pat; oc.numAttrs = c->pdl ? 1 : 0;
             {
@@ -2365,7 +2377,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
             if (m->model == OKB_TRANSD) add(P.off_ent_aux, m->m_ent_aux, m->v_ent_aux, true, 1);
             add(P.off_rel, m->m_rel, m->v_rel, false, 0);
             if (m->model != OKB_TRANSE) add(P.off_rel_aux, m->m_rel_aux, m->v_rel_aux, false, 1);
-            const unsigned og = (unsigned)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)148 * 8));
+            const unsigned og = (unsigned)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)okb_sms(c) * 8));
             cudaLaunchConfig_t oc = {};
             oc.gridDim = dim3(og); oc.blockDim = dim3(256); oc.stream = s; oc.attrs = pat; oc.numAttrs = c->pdl ? 1 : 0;
             if (vw == 4) cudaLaunchKernelEx(&oc, dp_owner_kernel<4>, o);
@@ -2419,8 +2431,11 @@ static void swap_slot(okb_ctx *c) {
 int okb_discard_prefetch(okb_ctx *c) {
     if (!c->alt_ready) return 0;
     c->alt_ready = false;
+    // the side stream sampled (and advanced the streams) after everything the caller's stream had issued before the
+    // prefetch; restoring on the same side stream orders the copy behind its advance kernel without touching the
+    // legacy default stream (which does not synchronise with non-blocking streams)
+    OKB_CUDA(c, cudaMemcpyAsync(c->d_state, c->d_state_saved, sizeof(u64) * c->state.size(), cudaMemcpyDeviceToDevice, c->side));
     OKB_CUDA(c, cudaStreamSynchronize(c->side));
-    OKB_CUDA(c, cudaMemcpy(c->d_state, c->d_state_saved, sizeof(u64) * c->state.size(), cudaMemcpyDeviceToDevice));
     c->state_dirty = true;
     return 0;
 }

@@ -12,6 +12,9 @@
 //     dM += A^T . G       (gradient of the matrix, accumulated in registers across chunks)
 // so the matrix gradient is produced already reduced per relation (one [De,Dr] row per relation per
 // step instead of one per positive) in a fixed order: deterministic, no atomics.
+// Data parallelism shards RELATIONS (okb_transr_set_shard): a rank computes and updates only the relations
+// [r_lo, r_hi) it owns — M_r, the 40 KB-per-relation operand, never crosses NVLink during training; only the
+// entity gradient rows are summed across ranks (parallel.RelationSharded).
 // The roof that binds at FB15K batch sizes is M_r traffic, not flops.
 #include <algorithm>
 
@@ -31,6 +34,7 @@ struct TrArgs {
     float *gent, *grel, *loss_terms;
     float margin, w;
     i32 B, k, NE, E, R, n, nes, b_lo, b_hi, CH;
+    i32 r_lo;                 // first relation of this context's shard (relation-sharded data parallelism; else 0)
 };
 
 __device__ __forceinline__ float wsum_t(float x) {
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(TR_THREADS) transr_bucket_kernel(TrArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int De = a.m.ent_dim, Dr = a.m.rel_dim, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int De4 = De >> 2, Dr4 = Dr >> 2, per = 2 + a.k;
-    const i32 r = blockIdx.x;
+    const i32 r = a.r_lo + (i32)blockIdx.x;
     const int4 seg = a.rowhead[a.E + r];
     if (seg.x < 0) return;
     float *Msh = sm;                                   // [De][Dr]
@@ -287,13 +291,15 @@ struct TrUpdArgs {
     okb_hyper hp;
     const int4 *rowhead;
     const float *grel;
-    i32 E, R, adam;
+    const unsigned *bad;       // "bad id" flag of the host-batch path: set -> leave the tables alone
+    i32 E, R, adam, r_lo;
 };
 __global__ void __launch_bounds__(256) transr_rel_update_kernel(TrUpdArgs a) {
-    const i32 r = blockIdx.x;
+    const i32 r = a.r_lo + (i32)blockIdx.x;
     const int De = a.m.ent_dim, Dr = a.m.rel_dim;
     const bool touched = a.rowhead[a.E + r].x >= 0;
     if (!touched && !a.adam) return;
+    if (a.bad && *(const volatile unsigned *)a.bad) return;
     const int cols = Dr + De * Dr, c4 = cols >> 2;
     const float4 *g4 = reinterpret_cast<const float4 *>(a.grel + (i64)r * cols);
     for (int v = blockIdx.y * blockDim.x + threadIdx.x; v < c4; v += gridDim.y * blockDim.x) {
@@ -340,7 +346,7 @@ int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, 
                            float *loss_terms, cudaStream_t s) {
     int rc = okb_transr_check(c, m);
     if (rc) return rc;
-    if (b_lo != 0 || b_hi != c->B) OKB_FAIL(c, OKB_ERR_ARG, "TransR gradients are reduced per relation: data-parallel slices are not supported yet");
+    if (b_lo != 0 || b_hi != c->B) OKB_FAIL(c, OKB_ERR_ARG, "TransR gradients are reduced per relation: shard the RELATIONS (okb_transr_set_shard), not the positives");
     const i64 S = c->B * (1 + c->K);
     TrArgs a;
     a.m = *m; a.bh = batch; a.bt = batch + S; a.br = batch + 2 * S;
@@ -350,15 +356,16 @@ int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, 
     a.B = (i32)c->B; a.k = (i32)c->K; a.NE = (i32)(2 + c->K); a.E = (i32)c->E; a.R = (i32)c->R; a.n = (i32)n;
     a.nes = (i32)c->plan_ne; a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi;
     a.CH = (i32)(TR_ROWS / (2 + c->K));
+    const i64 r_lo = c->tr_hi > c->tr_lo ? c->tr_lo : 0, r_hi = c->tr_hi > c->tr_lo ? c->tr_hi : c->R;
+    a.r_lo = (i32)r_lo;
     const int De = m->ent_dim, Dr = m->rel_dim;
     const size_t smem = sizeof(float) * ((size_t)De * Dr + (size_t)TR_ROWS * De + 2 * (size_t)TR_ROWS * Dr + (size_t)a.CH * Dr + 2 * Dr + TR_ROWS) +
                         sizeof(i32) * (2 * TR_ROWS + a.CH + (size_t)a.CH * a.k) + 64;
     if (smem > 226 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "TransR dimensions too large for shared memory");
-    static size_t attr = 0;                                // static + dynamic must stay within 227 KB
-    if (smem > attr) { OKB_CUDA(c, cudaFuncSetAttribute(transr_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    OKB_CUDA(c, okb_smem_optin(c, transr_bucket_kernel, smem));      // static + dynamic must stay within 227 KB
     {
         ProfScope ps(c, PROF_GRAD, s);
-        transr_bucket_kernel<<<(unsigned)c->R, TR_THREADS, smem, s>>>(a);
+        transr_bucket_kernel<<<(unsigned)(r_hi - r_lo), TR_THREADS, smem, s>>>(a);
     }
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
@@ -370,11 +377,21 @@ int okb_transr_launch_rel_update(okb_ctx *c, const okb_model *m, const okb_hyper
     TrUpdArgs a;
     a.m = *m; a.hp = *hp; a.rowhead = rowhead; a.grel = grel; a.E = (i32)c->E; a.R = (i32)c->R;
     a.adam = m->optimizer == OKB_ADAM;
+    a.bad = c->batch_from_host && c->flags.p ? c->flags.as<unsigned>() + OKB_FLAGS_BAD : nullptr;
     if (a.adam && (!m->m_rel_aux || !m->v_rel_aux)) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
     const int cols = m->rel_dim + m->ent_dim * m->rel_dim;
     const unsigned gy = (unsigned)std::max(1, std::min(8, (cols / 4 + 255) / 256));
-    transr_rel_update_kernel<<<dim3((unsigned)c->R, gy), 256, 0, s>>>(a);
+    const i64 r_lo = c->tr_hi > c->tr_lo ? c->tr_lo : 0, r_hi = c->tr_hi > c->tr_lo ? c->tr_hi : c->R;
+    a.r_lo = (i32)r_lo;
+    transr_rel_update_kernel<<<dim3((unsigned)(r_hi - r_lo), gy), 256, 0, s>>>(a);
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int okb_transr_set_shard(okb_ctx *c, INT r_lo, INT r_hi) {
+    if (r_lo == 0 && r_hi == 0) { c->tr_lo = c->tr_hi = 0; return 0; }      // back to "all relations"
+    if (r_lo < 0 || r_hi > c->R || r_lo >= r_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad relation shard");
+    c->tr_lo = r_lo; c->tr_hi = r_hi;
     return 0;
 }

@@ -201,11 +201,10 @@ int okb_transr_project_tc(okb_ctx *c, const okb_model *m, const i32 *d_grp_rel, 
     a.Kp = (m->ent_dim + 7) & ~7; a.Np = (m->rel_dim + 15) & ~15;
     a.j0 = (i32)j0; a.ncol = (i32)ncol;
     const size_t smem = (size_t)(TC_M / 8 + a.Np / 8) * (a.Kp / 4) * 128 * 2;
-    static size_t attr = 0;
-    if (smem > attr) { OKB_CUDA(c, cudaFuncSetAttribute(transr_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+    OKB_CUDA(c, okb_smem_optin(c, transr_project_tc_kernel, smem));
     // each CTA keeps M_r staged and walks every gx-th entity tile of its group; enough CTAs to fill the chip twice over
     const unsigned ntiles = (unsigned)(ncol / TC_M);
-    const unsigned gx = (unsigned)std::max<i64>(1, std::min<i64>(ntiles, (2 * 148 + G - 1) / G));
+    const unsigned gx = (unsigned)std::max<i64>(1, std::min<i64>(ntiles, (2 * okb_sms(c) + G - 1) / G));
     transr_project_tc_kernel<<<dim3(gx, (unsigned)G), TC_THREADS, smem, s>>>(a);
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());

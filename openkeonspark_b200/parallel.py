@@ -124,6 +124,82 @@ class DataParallel:
         return con.link_prediction_records(q_lo, q_hi, lo, hi, reduce_fn)
 
 
+class RelationSharded(DataParallel):
+    """TransR: ranks split the RELATIONS, not the positives (csrc/transr.cu).
+
+    TransR's train kernel owns one relation per CTA and emits that relation's matrix gradient already reduced, so the
+    natural shard is a contiguous range of relations per rank: a rank computes the positives of its relations and is the
+    only one that ever updates (or, during training, reads) those relations' rel_embeddings / transfer_matrix rows — the
+    40 KB-per-relation operand never crosses NVLink.  Per step the ranks exchange only the entity gradient rows and loss
+    terms (each row is written by exactly one rank, so the all-reduce adds zeros: results are bit-identical to one GPU)
+    and apply the same entity update.  The relation tables are gathered from their owners when something reads them
+    (get_parameters, checkpoints, evaluation) — those calls are collectives in this mode."""
+    mode = "relation"
+
+    def __init__(self, con, group=None):
+        super().__init__(con, group)
+        con._ensure_model()
+        if con.trainModel.name != "TransR":
+            raise ValueError("relation-sharded mode is TransR's; use mode='owner' or 'exact'")
+        if con.negative_rel:
+            raise ValueError("TransR data parallelism needs rel_neg_rate == 0 (a relation negative belongs to two shards)")
+        R = con.relTotal
+        self.rel_ranges = owner_rows(R, self.world)
+        lo, hi = self.rel_ranges[self.rank]
+        if hi <= lo:
+            raise ValueError("more ranks than relations")
+        con.ctx.call("okb_transr_set_shard", lo, hi)
+        self._stale = False          # the relation rows of the other shards are out of date
+
+    def train_step(self, con, m, hp, step):
+        from .Config import _stream
+        b = self._buffers(con, m)
+        s = _stream()
+        con.ctx.call("okb_plan", step, s)
+        b["gent"].zero_(); b["loss"].zero_()
+        con.ctx.call("okb_grad", ctypes.byref(m), ctypes.byref(hp), step, 0, con.batch_size, _vp(b["gent"].data_ptr()),
+                     _vp(b["grel"].data_ptr()), _vp(b["loss"].data_ptr()), s)
+        dist.all_reduce(b["gent"], group=self.group)
+        dist.all_reduce(b["loss"], group=self.group)
+        con.ctx.call("okb_update", ctypes.byref(m), ctypes.byref(hp), step, _vp(b["gent"].data_ptr()),
+                     _vp(b["grel"].data_ptr()), _vp(b["loss"].data_ptr()), _vp(con._loss_dev.data_ptr()), s)
+        self._stale = True
+
+    def _buffers(self, con, m):
+        if self._bufs is None:
+            er, ec, rr, rc = (ctypes.c_int64() for _ in range(4))
+            con.ctx.call("okb_grad_sizes", ctypes.byref(m), con.batch_size, con.negative_ent, con.negative_rel,
+                         ctypes.byref(er), ctypes.byref(ec), ctypes.byref(rr), ctypes.byref(rc))
+            dev = con.trainModel.device
+            self._bufs = dict(gent=torch.zeros(er.value, ec.value, dtype=torch.float32, device=dev),
+                              grel=torch.zeros(rr.value, rc.value, dtype=torch.float32, device=dev),       # one row per RELATION
+                              loss=torch.zeros(con.batch_size, dtype=torch.float32, device=dev))
+        return self._bufs
+
+    def gather_relations(self, con, adam=False):
+        """Collective: every rank receives the other shards' relation rows (and, adam=True, their Adam slots)."""
+        if not self._stale and not adam:
+            return
+        R = con.relTotal
+        per = (R + self.world - 1) // self.world
+        names = ["rel_embeddings", "transfer_matrix"]
+        tensors = [con.trainModel.parameter_lists[n] for n in names]
+        if adam and con._adam is not None:
+            tensors += [con._adam[p + n] for n in names for p in ("m_", "v_")]
+        lo, hi = self.rel_ranges[self.rank]
+        for t in tensors:
+            pad = torch.zeros(per * self.world, t.shape[1], dtype=t.dtype, device=t.device)
+            mine = torch.zeros(per, t.shape[1], dtype=t.dtype, device=t.device)
+            mine[:hi - lo].copy_(t[lo:hi])
+            dist.all_gather_into_tensor(pad, mine, group=self.group)
+            t.copy_(pad[:R])
+        self._stale = False
+
+    def link_prediction(self, con, q_lo=0, q_hi=None):
+        self.gather_relations(con)
+        return super().link_prediction(con, q_lo, q_hi)
+
+
 def owner_rows(n_rows, world):
     """Row ranges owned by each rank in owner-sharded mode: blocks of ceil(n_rows / world) (csrc/train.cu okb_dp_*)."""
     per = (n_rows + world - 1) // world
@@ -150,7 +226,8 @@ class OwnerSharded(DataParallel):
         from .Config import _AUX_ENT, _AUX_REL
         con._ensure_model()
         if con.trainModel.name == "TransR":
-            raise ValueError("owner-sharded mode does not cover TransR; use mode='exact'")
+            raise ValueError("owner-sharded mode does not cover TransR (its gradients are reduced per relation): "
+                             "use mode='relation' (parallel.attach picks it for TransR)")
         if self.world > 16:
             raise ValueError("owner-sharded mode supports up to 16 ranks per box")
         m = con._cmodel()
@@ -210,10 +287,11 @@ class OwnerSharded(DataParallel):
         if con._chunk_pos >= con._chunk_len:
             n = con.batch_size * (3 + con.negative_ent + con.negative_rel) // self.world
             self._sample(con, max(1, min(int(con.plan_ahead), (1 << 24) // max(n, 1))))
-        m, hp = con._cmodel(), con._hyper()
+        m = con._cmodel()
+        (hp,), powers = con._hypers(1)
         con.ctx.call("okb_dp_train_steps", ctypes.byref(m), ctypes.byref(hp), con._chunk_pos, 1, _vp(con._loss_dev.data_ptr()), _stream())
         con._chunk_pos += 1
-        con._step += 1
+        con._commit_powers(powers, 1)
         return con._loss_dev
 
     def train_chunk(self, con, n):
@@ -222,11 +300,12 @@ class OwnerSharded(DataParallel):
         from .Config import _stream
         self._sample(con, n)
         m = con._cmodel()
-        hps = (okb_hyper * n)(*[con._hyper() for _ in range(n)])
+        hl, powers = con._hypers(n)
+        hps = (okb_hyper * n)(*hl)
         if getattr(con, "_loss_chunk", None) is None or con._loss_chunk.numel() < n:
             con._loss_chunk = torch.zeros(n, dtype=torch.float32, device=con.trainModel.device)
         con.ctx.call("okb_dp_train_steps", ctypes.byref(m), hps, 0, n, _vp(con._loss_chunk.data_ptr()), _stream())
-        con._step += n
+        con._commit_powers(powers, n)
         con._chunk_pos = con._chunk_len = 0
         return con._loss_chunk[:n]
 
@@ -273,6 +352,14 @@ def attach(con, group=None, mode="auto", pull=None):
     """Enable data-parallel mode on a Config whose init() has run (torch.distributed initialised).
     mode: "owner" (peer-memory owner-sharded update), "exact" (all-gather of gradient rows, bit-identical to one GPU),
     "auto" = owner on NCCL/GPU for TransE/H/D when the batch touches a sizeable share of the rows, else exact."""
+    con._ensure_model()
+    if con.trainModel.name == "TransR":
+        if mode not in ("auto", "relation"):
+            raise ValueError("TransR trains data-parallel in mode='relation' only (its gradients are reduced per relation)")
+        con._world = RelationSharded(con, group)
+        return con._world
+    if mode == "relation":
+        raise ValueError("mode='relation' is TransR's")
     if mode == "auto":
         mode = "exact"
         if dist.get_backend(group) == "nccl" and dist.get_world_size(group) <= 16:      # peer memory needs GPUs

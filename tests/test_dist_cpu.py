@@ -54,6 +54,18 @@ class FakeCtx:
             B, k, kr = args[1], args[2], args[3]
             args[4]._obj.value, args[5]._obj.value = B * (2 + k), con.D
             args[6]._obj.value, args[7]._obj.value = B * (1 + kr), 2 * con.D
+        elif name == "okb_transr_set_shard":
+            con.shard = (args[0], args[1])
+        elif name == "okb_grad" and con.trainModel.name == "TransR":
+            # relation-sharded: the full positive range is passed, only the positives of this rank's relations are written
+            assert (args[3], args[4]) == (0, con.batch_size)
+            b = con._world._bufs
+            for bb in range(con.batch_size):
+                r = bb % con.relTotal
+                if con.shard[0] <= r < con.shard[1]:
+                    b["gent"][bb * 3:(bb + 1) * 3] = float(bb + 1)
+                    b["loss"][bb] = 0.5 * bb
+            b["grel"][con.shard[0]:con.shard[1]] = float(con._world.rank + 1)
         elif name == "okb_grad":
             lo, hi = args[3], args[4]
             b = con._world._bufs
@@ -68,6 +80,8 @@ class FakeCtx:
 
 class FakeModel:
     device = torch.device("cpu")
+    name = "TransE"
+    parameter_lists = {}
 
 
 class FakeCon:
@@ -77,6 +91,10 @@ class FakeCon:
         self.trainModel = FakeModel()
         self._loss_dev = torch.zeros(1)
         self.ctx = FakeCtx(self)
+        self._adam = None
+
+    def _ensure_model(self):
+        pass
 
 
 def _worker(rank, world, port, B, W):
@@ -105,6 +123,55 @@ def _worker(rank, world, port, B, W):
     assert counts.tolist() == [3, 0, 10]
     assert best.tolist() == [-1, (3 << 32) | 7, (1 << 32) | 9]
     dist.destroy_process_group()
+
+
+def _worker_relation(rank, world, port, B, R):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from openkeonspark_b200 import parallel
+    sys.modules["openkeonspark_b200.Config"]._stream = lambda: None
+    con = FakeCon(B, 4, 4, 1, 0)
+    con.trainModel = FakeModel()
+    con.trainModel.name = "TransR"
+    con.relTotal = R
+    # relation tables whose rows identify their owner: the gather must deliver every owner's rows to every rank
+    rel = torch.full((R, 3), -1.0)
+    mat = torch.full((R, 6), -1.0)
+    con.trainModel.parameter_lists = {"rel_embeddings": rel, "transfer_matrix": mat}
+    orig_sizes = FakeCtx.call
+
+    def sizes(self, name, *args):
+        if name == "okb_grad_sizes":
+            args[4]._obj.value, args[5]._obj.value, args[6]._obj.value, args[7]._obj.value = B * 3, 4, R, 4 + 16
+            self.calls.append(name)
+        else:
+            orig_sizes(self, name, *args)
+    FakeCtx.call = sizes
+    dp = parallel.attach(con)
+    assert dp.mode == "relation" and con.shard == parallel.owner_rows(R, world)[rank]
+    with pytest.raises(ValueError):
+        parallel.attach(con, mode="exact")           # TransR has one data-parallel mode
+    from openkeonspark_b200._native import okb_hyper, okb_model
+    dp.train_step(con, okb_model(), okb_hyper(), 0)
+    assert con.ctx.calls == ["okb_transr_set_shard", "okb_grad_sizes", "okb_plan", "okb_grad", "okb_update"]
+    u = con.updated
+    for bb in range(B):                              # every positive's rows arrive exactly once (one writer + zeros)
+        assert torch.all(u["gent"][bb * 3:(bb + 1) * 3] == float(bb + 1)) and u["loss"][bb] == 0.5 * bb
+    lo, hi = con.shard
+    rel[lo:hi] = float(rank + 10)
+    mat[lo:hi] = float(rank + 20)
+    dp._stale = True
+    dp.gather_relations(con)
+    for q, (a, b) in enumerate(parallel.owner_rows(R, world)):
+        assert torch.all(rel[a:b] == float(q + 10)) and torch.all(mat[a:b] == float(q + 20))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("B,R", [(37, 7), (16, 2)])
+def test_relation_sharded_host_logic_gloo_world2(B, R):
+    port = 31500 + (os.getpid() + B) % 2000
+    mp.spawn(_worker_relation, args=(2, port, B, R), nprocs=2, join=True)
 
 
 @pytest.mark.parametrize("B,W", [(37, 4), (40, 8), (3, 8)])
