@@ -409,6 +409,9 @@ class Config(object):
             self.importName = keep
 
     def restore_tensorflow(self):
+        """Saver.restore (Config.py:366-376).  Under data parallelism a collective: every rank loads the same file."""
+        self._settle()                                # no peer may still be storing rows into the tables being overwritten
+        self._barrier()
         state = torch.load(self.importName, map_location="cpu")
         self.set_parameters({k: v.numpy() for k, v in state["params"].items()}, allow_partial_rows=True)
         self._step = state.get("step", 0)
@@ -422,6 +425,9 @@ class Config(object):
                         self._adam[k].copy_(v)
                 else:
                     self._adam[k] = np.float32(v)     # beta powers are fp32 running products (tf.train.AdamOptimizer)
+        if self._world is not None:
+            torch.cuda.synchronize()
+            self._barrier()                           # every rank's tables are in place before anyone steps (and pushes rows)
 
     # ------------------------------------------------------------------ model (Config.py:425-461)
     def set_model(self, model):
@@ -811,7 +817,10 @@ class Config(object):
         nt = self.test_step(self.test_neg_h, self.test_neg_t, self.test_neg_r)
         n_int = int(self.lib.okb_n_interval(self.ctx.h, rel_index, _addr(pv), _addr(nv)))
         self.lib.okb_tpfp.restype = ctypes.POINTER(ctypes.c_int64 * ((n_int + 1) * 2))
-        res = [j for j in self.lib.okb_tpfp(self.ctx.h, rel_index, _addr(pv), _addr(nv), _addr(pt), _addr(nt)).contents]
+        ptr = self.lib.okb_tpfp(self.ctx.h, rel_index, _addr(pv), _addr(nv), _addr(pt), _addr(nt))
+        if not ptr:       # Test.h:417 returns a null pointer for a relation without valid triples (the reference then crashes)
+            raise OkbError("plot_roc: relation %d has no valid triples to fit a threshold grid on" % rel_index)
+        res = [j for j in ptr.contents]
         TPR, FPR = [], []
         if res[0] != 0 or res[0 + n_int + 1] != 0:
             TPR.append(0)

@@ -117,6 +117,27 @@ class COracle:
                 self.L.orc_load_ontology(self.o, _i64(k.size), _p(k), _p(oa), _p(fa), _p(ob), _p(fb))
         return self
 
+    def load_arrays(self, E, R, train, valid=None, test=None, heads=None, tails=None):
+        """Same as load() from [n,3] int64 arrays (columns h, t, r) — full-size synthetic graphs that are never written to
+        text files.  heads / tails: {relation: sorted ids} type constraints (datagen.type_constraints)."""
+        self.E, self.R, self.n_raw = int(E), int(R), int(train.shape[0])
+        h, t, r = (_i64a(train[:, k]) for k in range(3))
+        self.L.orc_load_train(self.o, _i64(self.E), _i64(self.R), _p(h), _p(t), _p(r), _i64(self.n_raw), _i64(0))
+        if test is not None:
+            self.n_test, self.n_valid = int(test.shape[0]), int(valid.shape[0])
+            a = [_i64a(test[:, k]) for k in range(3)] + [_i64a(valid[:, k]) for k in range(3)]
+            self.L.orc_load_test(self.o, _p(a[0]), _p(a[1]), _p(a[2]), _i64(self.n_test),
+                                 _p(a[3]), _p(a[4]), _p(a[5]), _i64(self.n_valid))
+            keys = sorted(heads)
+            offa, offb = np.zeros(len(keys) + 1, np.int64), np.zeros(len(keys) + 1, np.int64)
+            for i, k in enumerate(keys):
+                offa[i + 1] = offa[i] + heads[k].size
+                offb[i + 1] = offb[i] + tails[k].size
+            fa = _i64a(np.concatenate([heads[k] for k in keys])) if keys else np.zeros(0, np.int64)
+            fb = _i64a(np.concatenate([tails[k] for k in keys])) if keys else np.zeros(0, np.int64)
+            self.L.orc_load_types(self.o, _i64(len(keys)), _p(_i64a(keys)), _p(offa), _p(fa), _p(offb), _p(fb))
+        return self
+
     def set_streams(self, seeds, bern=0):
         s = np.ascontiguousarray(np.asarray(seeds, dtype=np.uint64))
         self.W = s.size

@@ -155,6 +155,68 @@ def main():
             assert torch.equal(t, ref), (model, opt, k, "replicas differ")
         if rank == 0:
             print("dp%d owner-sharded pull == push %s/%s: losses and tables bit-identical, replicas bit-identical" % (world, model, opt))
+    # TransR: relation-sharded mode (ranks split the relations; only entity gradient rows cross NVLink) must leave every
+    # rank with tables and link-prediction records bit-identical to a single-GPU run of the same global batch
+    for opt in ("SGD", "Adam"):
+        a = make(d, "TransR", opt, 8, False)
+        a.set_rel_neg_rate(0); a.init()
+        a.set_model_and_session(__import__("openkeonspark_b200").TransR)
+        b = make(d, "TransR", opt, 8, False)
+        b.set_rel_neg_rate(0); b.init()
+        b.set_model_and_session(__import__("openkeonspark_b200").TransR)
+        from conftest import make_params
+        for con in (a, b):
+            con.set_parameters(make_params("TransR", con.entTotal, con.relTotal, 100, seed=4))
+            seeds = np.arange(1, 9, dtype=np.uint64) * np.uint64(7919)
+            con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), 8)
+        from openkeonspark_b200 import parallel
+        parallel.attach(a)
+        assert a._world.mode == "relation"
+        for it in range(4):
+            for con in (a, b):
+                con.sampling_device()
+                con.train_step_device(0)
+            assert float(a._loss_dev.item()) == float(b._loss_dev.item()), (opt, it)
+        pa, pb = a.get_parameters(), b.get_parameters()          # collective in relation mode: owners' rows are gathered
+        for k in pa:
+            assert np.array_equal(pa[k], pb[k]), ("TransR", opt, k, rank)
+        ra = a._world.link_prediction(a).cpu().numpy()
+        rb = b.link_prediction_records().cpu().numpy()
+        assert np.array_equal(ra, rb), ("TransR", opt, rank)
+        if rank == 0:
+            print("dp%d relation-sharded TransR/%s: tables and link-prediction records bit-identical to single GPU" % (world, opt))
+    # owner-sharded checkpoint: save (collective; Adam slots completed from their owners, rank 0 writes) -> a fresh pair of
+    # processes' worth of state restores it and continues -> bit-identical to the run that never stopped
+    obj = [None]
+    if rank == 0:
+        obj = [tempfile.mkdtemp() + "/ckpt.pt"]
+    dist.broadcast_object_list(obj, src=0)
+    ckpt = obj[0]
+    a = make(d, "TransH", "Adam", 8, True, mode="owner")
+    a.plan_ahead = 4
+    for it in range(4):
+        a.next_step_device()
+    a.set_export_files(ckpt)
+    a.save_tensorflow()
+    st = np.zeros(8, np.uint64)
+    a.ctx.call("okb_get_streams", ctypes.c_void_p(st.ctypes.data), 8)
+    a.plan_ahead = 3
+    la = [float(a.next_step_device().item()) for _ in range(3)]
+    pa = a.get_parameters()
+    a._world.close(a)
+    b = make(d, "TransH", "Adam", 8, True, mode="owner")
+    b.set_import_files(ckpt)
+    b.restore_tensorflow()
+    b.ctx.call("okb_set_streams", ctypes.c_void_p(st.ctypes.data), 8)
+    b.plan_ahead = 3
+    lb = [float(b.next_step_device().item()) for _ in range(3)]
+    pb = b.get_parameters()
+    assert la == lb, (la, lb)
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), ("restore", k, rank)
+    b._world.close(b)
+    if rank == 0:
+        print("dp%d owner-sharded save -> restore -> continue: losses and tables bit-identical to the uninterrupted run" % world)
     dist.barrier()
     dist.destroy_process_group()
 

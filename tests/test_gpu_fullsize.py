@@ -147,3 +147,229 @@ def test_fullsize_ranking(built, fb15k):
             checksum_ref += int((sg < sg[tgt]).sum())
             checksum_gpu += int(rec[i, side, 0])
     assert checksum_gpu == checksum_ref
+
+
+# ------------------------------------------------------------------------------------------ BASELINE configs 3, 4, 5
+def _streams(con, W=8, mult=2654435761):
+    seeds = np.arange(1, W + 1, dtype=np.uint64) * np.uint64(mult)
+    con.ctx.call("okb_set_streams", vp(seeds.ctypes.data), W)
+    return seeds
+
+
+def _adam_slots_close(con, ref64):
+    """After ONE step m = 0.1 g and v = 0.001 g^2: the pure gradient check (same bar as tests/test_gpu_train.py)."""
+    for name in ref64.m:
+        m_gpu, v_gpu = con._adam["m_" + name].cpu().numpy(), con._adam["v_" + name].cpu().numpy()
+        m_ref, v_ref = ref64.m[name].numpy(), ref64.v[name].numpy()
+        assert np.quantile(np.abs(m_gpu - m_ref), 0.999) <= 1e-4 * np.abs(m_ref).max() + 1e-9, name
+        assert np.quantile(np.abs(v_gpu - v_ref), 0.999) <= 2e-4 * np.abs(v_ref).max() + 1e-12, name
+
+
+@pytest.fixture(scope="module")
+def wn18(tmp_path_factory):
+    from openkeonspark_b200 import datagen
+    d = str(tmp_path_factory.mktemp("wn18")) + "/"
+    g = datagen.make_shape("wn18", seed=0)
+    datagen.write_dataset(g, d, ontology=False)
+    return d, g
+
+
+def test_config3_wn18_transd_k10(built, wn18):
+    """BASELINE configs[2]: TransD D=100, ent_neg_rate=10, bern, Adam on the WN18-shaped graph (40,943 / 18 / 141,442),
+    B = 1,414: the 2-4-warps-per-positive grad kernel and the 16-bit key space of the one-step plan at real size.
+    Reference: TransD.py:46-98, base/Corrupt.h:7-69, base/Base.cpp:74-143."""
+    import torch
+    import openkeonspark_b200 as okb
+    from oracle import models_ref
+    from oracle.harness import COracle
+    path, g = wn18
+    con = okb.Config(private_context=True)
+    con.set_in_path(path)
+    con.set_nbatches(100); con.set_ent_neg_rate(10); con.set_alpha(0.001); con.set_opt_method("Adam"); con.set_dimension(100)
+    con.set_bern(1); con.set_test_link_prediction(True); con.set_test_head(1)
+    con.workThreads = 8
+    con.init()
+    assert (con.entTotal, con.relTotal, con.trainTotal, con.batch_size) == (40943, 18, 141442, 1414)
+    con.set_model_and_session(okb.TransD)
+    P = make_params("TransD", con.entTotal, con.relTotal, 100, seed=13)
+    con.set_parameters(P)
+    seeds = _streams(con)
+    orc = COracle(path)
+    orc.set_streams(seeds, 1)
+    # sampler: two consecutive calls bit-exact (bern: the per-relation head/tail coin of Base.cpp:116-117)
+    for it in range(2):
+        con.sampling()
+        eh, et, er, ey = orc.sampling(1414, 10, 0)
+        assert np.array_equal(con.batch_h, eh) and np.array_equal(con.batch_t, et) and np.array_equal(con.batch_r, er), it
+        assert np.array_equal(con.batch_y, ey)
+    # one train step on that batch vs the TF-graph restatement (fp64): loss rtol 2e-5, Adam slots = the gradient check
+    h, t, r = con.batch_h.copy(), con.batch_t.copy(), con.batch_r.copy()
+    ref64 = models_ref.Trainer("TransD", P, margin=1.0, lr=0.001, opt="Adam", dtype=torch.float64)
+    l64 = ref64.step(h, t, r, 1414, 10, 0)
+    loss = float(con.train_step_device(0).item())
+    assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6, (loss, l64)
+    _adam_slots_close(con, ref64)
+    # the host-batch API (one-kernel plan, 16-bit keys: E + R + 1 = 40,962) gives the same step as the device path
+    con2 = okb.Config(private_context=True)
+    con2.set_in_path(path)
+    con2.set_nbatches(100); con2.set_ent_neg_rate(10); con2.set_alpha(0.001); con2.set_opt_method("Adam"); con2.set_dimension(100)
+    con2.set_bern(1); con2.workThreads = 8
+    con2.init()
+    con2.set_model_and_session(okb.TransD)
+    con2.set_parameters(P)
+    l2 = con2.train_step(h, t, r, con.batch_y)
+    assert np.float32(l2) == np.float32(loss)
+    a, b = con.get_parameters(), con2.get_parameters()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    # link prediction: a sample of records bit-exact vs testHead/testTail fed the canonical scores
+    Pn = con.get_parameters()
+    n = 256
+    rec = con.link_prediction_records(0, n).cpu().numpy()
+    th, tt, tr = orc.get_list(0)
+    ents = np.arange(orc.E)
+    for i in range(0, n, 37):
+        s = orc.predict("TransD", Pn, np.full(orc.E, th[i]), ents, np.full(orc.E, tr[i]))
+        assert np.array_equal(rec[i, 1], orc.rank(1, i, s)), (i, "tail")
+        s = orc.predict("TransD", Pn, ents, np.full(orc.E, tt[i]), np.full(orc.E, tr[i]))
+        assert np.array_equal(rec[i, 0], orc.rank(0, i, s)), (i, "head")
+
+
+def test_config4_fb15k_transr(built, fb15k):
+    """BASELINE configs[3]: TransR ent = rel dim = 100 on the FB15K-shaped graph (53.8 MB matrix table), B = 4,831.
+    Reference: TransR.py:36-87."""
+    import torch
+    import openkeonspark_b200 as okb
+    from oracle import models_ref
+    from oracle.harness import COracle
+    path, g = fb15k
+    P = make_params("TransR", g.E, g.R, 100, seed=17)
+    runs = {}
+    for opt in ("SGD", "Adam"):
+        con, _ = _con(path, "TransR", 100, opt=opt, k=1, lr=0.01, lp=True)
+        con.set_parameters(P)
+        con.sampling()
+        h, t, r = con.batch_h.copy(), con.batch_t.copy(), con.batch_r.copy()
+        ref64 = models_ref.Trainer("TransR", P, margin=1.0, lr=0.01, opt=opt, dtype=torch.float64)
+        l64 = ref64.step(h, t, r, con.batch_size, 1, 0)
+        loss = float(con.train_step_device(0).item())
+        assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6, (opt, loss, l64)
+        got, exp = con.get_parameters(), ref64.params()
+        if opt == "SGD":
+            for name in exp:
+                delta = np.abs(exp[name] - P[name]).max()
+                assert np.abs(got[name] - exp[name]).max() <= 1e-4 * delta + 2e-6, (name, np.abs(got[name] - exp[name]).max(), delta)
+        else:
+            _adam_slots_close(con, ref64)
+        runs[opt] = con
+    # canonical link prediction: 16 test triples x both sides = 32 queries bit-exact
+    con = runs["SGD"]
+    Pn = con.get_parameters()
+    orc = COracle(path)
+    n = 1024
+    rec = con.link_prediction_records(0, n).cpu().numpy()
+    th, tt, tr = orc.get_list(0)
+    ents = np.arange(orc.E)
+    for i in range(0, n, 64):
+        s = orc.predict("TransR", Pn, np.full(orc.E, th[i]), ents, np.full(orc.E, tr[i]))
+        assert np.array_equal(rec[i, 1], orc.rank(1, i, s)), (i, "tail")
+        s = orc.predict("TransR", Pn, ents, np.full(orc.E, tt[i]), np.full(orc.E, tr[i]))
+        assert np.array_equal(rec[i, 0], orc.rank(0, i, s)), (i, "head")
+    # tcgen05 (3xTF32) candidate projection at E = 14,951: agrees with the canonical records except where two scores are
+    # within fp32 rounding of each other.  Stated tolerance: every count within 4 of the canonical one, >= 95 % of the
+    # 2,048 records identical, and the filtered MRR within 1e-4 relative.
+    con.transr_tensor_cores = True
+    tc = con.link_prediction_records(0, n).cpu().numpy()
+    con.transr_tensor_cores = False
+    diff = np.abs(rec[..., :4] - tc[..., :4])
+    same = (rec == tc).all(axis=-1).mean()
+    mrr = lambda x: (1.0 / (1.0 + x[..., 1].astype(np.float64))).mean()
+    print("tcgen05 projection at E=14951: max |count diff| %d, identical records %.4f, MRR %.6f vs %.6f" % (diff.max(), same, mrr(tc), mrr(rec)))
+    assert diff.max() <= 4 and same >= 0.95, (int(diff.max()), float(same))
+    assert abs(mrr(tc) - mrr(rec)) <= 1e-4 * mrr(rec)
+
+
+def test_config5_dbpedia_scale(built):
+    """BASELINE configs[4]: TransE D=200 at 4,000,000 entities / 600 relations / 20,000,000 train triples (auto batch rule:
+    B = 2,000).  int32 index guards, the multi-kernel fallback of the one-step plan (E + R >= 65,536), the ranking
+    workspace at 4 M candidates.  Reference: base/Reader.h:27-179, base/Corrupt.h:7-69, TransE.py:26-58, base/Test.h:31-249."""
+    import contextlib
+    import io
+    import torch
+    import openkeonspark_b200 as okb
+    from openkeonspark_b200 import datagen
+    from oracle import models_ref
+    from oracle.harness import COracle
+    E, R, N = 4_000_000, 600, 20_000_000
+    rng = np.random.default_rng(0)
+    need = N + 2_000
+    raw = np.stack([rng.integers(0, E, need + need // 50), rng.integers(0, E, need + need // 50), rng.integers(0, R, need + need // 50)], 1)
+    key = (raw[:, 0] * E + raw[:, 1]) * R + raw[:, 2]
+    _, first = np.unique(key, return_index=True)
+    raw = raw[np.sort(first)][:need]
+    train, valid, test = raw[:N], raw[N:N + 1000], raw[N + 1000:]
+    con = okb.Config(private_context=True)
+    con.set_nbatches(0); con.set_dimension(200); con.set_opt_method("SGD"); con.set_alpha(0.01); con.set_ent_neg_rate(1)
+    con.workThreads = 8
+    con.test_head = 1
+    with contextlib.redirect_stdout(io.StringIO()):
+        con.init_from_arrays(E, R, train, valid, test)
+    assert con.batch_size == 2000 and con.nbatches == 10000 and con.entTotal == E and con.trainTotal == N      # Config.py:204-207
+    con.set_model_and_session(okb.TransE)
+    gen = torch.Generator().manual_seed(5)
+    sig = float(np.sqrt(2.0 / (E + 200)))
+    ent = (torch.randn(E, 200, generator=gen) * sig).numpy()
+    rel = datagen.xavier_normal(np.random.default_rng(6), R, 200)
+    con.set_parameters({"ent_embeddings": ent, "rel_embeddings": rel})
+    seeds = _streams(con)
+    heads, tails = datagen.type_constraints(datagen.Graph(E, R, train, valid, test))
+    orc = COracle().load_arrays(E, R, train, valid, test, heads, tails)
+    orc.set_streams(seeds, 0)
+    # one sampled batch, bit-exact (row picks from 20 M rows, filtered corruption over 4 M entities)
+    con.sampling()
+    eh, et, er, ey = orc.sampling(2000, 1, 0)
+    assert np.array_equal(con.batch_h, eh) and np.array_equal(con.batch_t, et) and np.array_equal(con.batch_r, er)
+    assert con.batch_h.max() > 2 ** 21 and con.batch_h.max() < E
+    h, t, r = con.batch_h.copy(), con.batch_t.copy(), con.batch_r.copy()
+    # one SGD step through the multi-kernel one-step plan (E + R + 1 needs 22 key bits; the one-kernel plan stops at 16)
+    # vs the restatement run on the COMPACTED tables (TransE's loss only sees the gathered rows, so remapping ids is exact)
+    ue, inv_e = np.unique(np.concatenate([h, t]), return_inverse=True)
+    ur, inv_r = np.unique(r, return_inverse=True)
+    S = h.size
+    Pc = {"ent_embeddings": ent[ue], "rel_embeddings": rel[ur]}
+    ref64 = models_ref.Trainer("TransE", Pc, margin=1.0, lr=0.01, opt="SGD", dtype=torch.float64)
+    l64 = ref64.step(inv_e[:S], inv_e[S:], inv_r, 2000, 1, 0)
+    loss = float(con.train_step_device(0).item())
+    assert abs(loss - l64) <= 2e-5 * abs(l64) + 1e-6, (loss, l64)
+    Pt = con.trainModel.parameter_lists
+    got_e = Pt["ent_embeddings"][torch.as_tensor(ue, device=Pt["ent_embeddings"].device)].cpu().numpy()
+    got_r = Pt["rel_embeddings"][torch.as_tensor(ur, device=Pt["rel_embeddings"].device)].cpu().numpy()
+    exp = ref64.params()
+    for got, name, base in ((got_e, "ent_embeddings", ent[ue]), (got_r, "rel_embeddings", rel[ur])):
+        delta = np.abs(exp[name] - base).max()
+        assert np.abs(got - exp[name]).max() <= 1e-4 * delta + 2e-6, (name, np.abs(got - exp[name]).max(), delta)
+    # untouched rows stay bit-identical (checksum over a strided sample of the 4 M rows)
+    idx = np.setdiff1d(np.arange(0, E, 997), ue)
+    assert np.array_equal(Pt["ent_embeddings"][torch.as_tensor(idx, device=Pt["ent_embeddings"].device)].cpu().numpy(), ent[idx])
+    # the chunked plan (one sort for several steps) and the one-step plan agree bit for bit at this key width
+    con.plan_ahead = 3
+    l_chunk = con.train_chunk_device(3).cpu().numpy()
+    assert np.isfinite(l_chunk).all()
+    # link prediction over all 4 M candidates, 2 test triples x both sides, bit-exact:
+    #   (i) the predict kernel's 4 M canonical scores == the C oracle on a strided sample of ~48 k candidates (the oracle's
+    #       scalar loop takes ~30 s for all 4 M), and
+    #   (ii) the ranking kernel's 8-int records == the oracle's testHead / testTail fed those 4 M scores
+    Pn = {"ent_embeddings": Pt["ent_embeddings"].cpu().numpy(), "rel_embeddings": Pt["rel_embeddings"].cpu().numpy()}
+    rec = con.link_prediction_records(0, 4).cpu().numpy()
+    th, tt, tr = orc.get_list(0)
+    ents = np.arange(E)
+    for i in (0, 3):
+        for side in (1, 0):
+            hh = np.full(E, th[i]) if side else ents
+            t2 = ents if side else np.full(E, tt[i])
+            sg = con.test_step(hh, t2, np.full(E, tr[i])).reshape(-1)
+            sub = np.arange(i + side, E, 83)
+            so = orc.predict("TransE", Pn, hh[sub], t2[sub], np.full(sub.size, tr[i]))
+            assert np.array_equal(sg[sub].view(np.uint32), so.view(np.uint32)), (i, side)
+            assert np.array_equal(rec[i, side], orc.rank(side, i, sg)), (i, side, rec[i, side])
+    assert rec[..., 0].max() < E and (rec[..., 1] <= rec[..., 0]).all()
