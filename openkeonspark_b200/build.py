@@ -21,7 +21,7 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def _deps():
-    hdrs = [os.path.join(CSRC, "okb_internal.h"), os.path.join(HERE, "..", "include", "okb200.h"), __file__]
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + [os.path.join(HERE, "..", "include", "okb200.h"), __file__]
     return max(os.path.getmtime(h) for h in hdrs)
 
 

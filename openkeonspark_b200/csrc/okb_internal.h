@@ -139,6 +139,18 @@ template <class F> static inline cudaError_t okb_smem_optin(okb_ctx *c, F *fn, s
 #define OKB_CUDA(c, expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { \
     (c)->err = std::string(#expr) + ": " + cudaGetErrorString(e_); return OKB_ERR_CUDA; } } while (0)
 
+#ifdef __CUDACC__
+// One element of the TF1 Adam rule, spelled with explicitly rounded operations so that EVERY kernel that applies it
+// (tile / legacy / TMA-staged / persistent-chunk / data-parallel owner / TransR relation rows) produces the same bits:
+//   m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; x <- x - lr_t m / (sqrt(v) + eps)
+__device__ __forceinline__ void adam_elem(float &x, float &m, float &v, float g, float b1, float b2, float c1, float c2, float lr, float eps) {
+    const float mq = __fmaf_rn(m, b1, __fmul_rn(g, c1));
+    const float vq = __fmaf_rn(v, b2, __fmul_rn(__fmul_rn(g, g), c2));
+    m = mq; v = vq;
+    x = __fsub_rn(x, __fdiv_rn(__fmul_rn(lr, mq), __fadd_rn(__fsqrt_rn(vq), eps)));
+}
+#endif
+
 // kernel ids for okb_prof_*
 enum { PROF_SAMPLE = 0, PROF_PLAN = 1, PROF_GRAD = 2, PROF_UPDATE = 3, PROF_RANK = 4, PROF_RANK_PREP = 5, PROF_DP_PUSH = 6, PROF_DP_OWNER = 7 };
 static inline void prof_mark(okb_ctx *c, int id, cudaStream_t s) {

@@ -316,12 +316,8 @@ __global__ void __launch_bounds__(256) transr_rel_update_kernel(TrUpdArgs a) {
             float4 mv = *reinterpret_cast<float4 *>(mp), vv = *reinterpret_cast<float4 *>(vp);
             float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const float mq = ms[q] * a.hp.beta1 + gs[q] * (1.f - a.hp.beta1);
-                const float vq = vs[q] * a.hp.beta2 + (gs[q] * gs[q]) * (1.f - a.hp.beta2);
-                ms[q] = mq; vs[q] = vq;
-                xs[q] -= a.hp.lr * mq / (sqrtf(vq) + a.hp.eps);
-            }
+            for (int q = 0; q < 4; q++)
+                adam_elem(xs[q], ms[q], vs[q], gs[q], a.hp.beta1, a.hp.beta2, 1.f - a.hp.beta1, 1.f - a.hp.beta2, a.hp.lr, a.hp.eps);
             *reinterpret_cast<float4 *>(mp) = mv; *reinterpret_cast<float4 *>(vp) = vv;
         } else {
 #pragma unroll

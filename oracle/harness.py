@@ -135,7 +135,8 @@ class COracle:
                 offb[i + 1] = offb[i] + tails[k].size
             fa = _i64a(np.concatenate([heads[k] for k in keys])) if keys else np.zeros(0, np.int64)
             fb = _i64a(np.concatenate([tails[k] for k in keys])) if keys else np.zeros(0, np.int64)
-            self.L.orc_load_types(self.o, _i64(len(keys)), _p(_i64a(keys)), _p(offa), _p(fa), _p(offb), _p(fb))
+            ka = _i64a(keys)                     # a named local: _p() of a temporary would hand C a dangling address
+            self.L.orc_load_types(self.o, _i64(len(keys)), _p(ka), _p(offa), _p(fa), _p(offb), _p(fb))
         return self
 
     def set_streams(self, seeds, bern=0):
