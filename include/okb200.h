@@ -325,7 +325,12 @@ enum { OKB_FLAG_TRANSR_TC = 1,
        OKB_FLAG_GRAD_SINGLE_WARP = 8,
        /* OKB_FLAG_PLAN_MULTI = 9 (default off): plan a single step with the general multi-kernel segmented sort instead of the
           one-CTA single-kernel plan (A/B and test switch; results are identical). */
-       OKB_FLAG_PLAN_MULTI = 9 };
+       OKB_FLAG_PLAN_MULTI = 9,
+       /* OKB_FLAG_CHUNK_KERNEL = 10 (default on): okb_train_steps runs a chunk of planned steps as ONE persistent cooperative
+          kernel (grad -> grid barrier -> update per step; csrc/chunk.cu) where the configuration is covered (TransE/H/D,
+          single GPU, one warp per positive, D in the vectorised layouts); 0 = always the per-phase kernels.  Results are
+          bit-identical either way. */
+       OKB_FLAG_CHUNK_KERNEL = 10 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:

@@ -83,6 +83,7 @@ struct okb_ctx {
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
     bool batch_from_host = false;     // the current batch came through okb_batch_from_host: update kernels honour the "bad id" flag
+    bool chunk_kernel = true;         // OKB_FLAG_CHUNK_KERNEL: okb_train_steps runs a chunk as one persistent kernel where covered
     bool plan_multi = false;          // OKB_FLAG_PLAN_MULTI: one-step plans use the multi-kernel sort too
     bool plan_small_attr = false;     // dynamic shared memory limit of plan_small_kernel raised on this device
     bool grad_single_warp = false;    // OKB_FLAG_GRAD_SINGLE_WARP: never split a positive's negatives over several warps
@@ -177,8 +178,10 @@ bool okb_host_find(const okb_ctx *c, i64 h, i64 t, i64 r);
 i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(0, h, r) on stream 0
 
 // okb_ctx::flags, in 4-byte words: [0,64) partial loss sums | [64] loss ticket | [68] "bad id" flag of the host-batch path
-#define OKB_FLAGS_BYTES (sizeof(float) * 64 + 32)
+//   | [72] arrival counter of the persistent chunk kernel's grid barrier
+#define OKB_FLAGS_BYTES (sizeof(float) * 64 + 64)
 #define OKB_FLAGS_BAD 68
+#define OKB_FLAGS_GRIDBAR 72
 int okb_ensure_flags(okb_ctx *c, cudaStream_t s);     // train.cu: allocate + zero once
 
 // train.cu: forget a prefetched chunk (restores the RNG streams); every entry point that touches the streams calls it

@@ -594,6 +594,26 @@ int okb_plan(okb_ctx *c, INT step, void *stream) {
 }
 
 }  // extern "C"
+// The grad kernels' argument block for positives [b_lo, b_hi) of one sampled step (no launch)
+void okb_fill_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, INT slot_base, float *gent,
+                   float *grel, float *loss_terms, GradArgs &a) {
+    const i64 S = c->B * (1 + c->K + c->KR);
+    a.m = *m;
+    const i32 *base = c->batch.as<i32>() + step * 3 * S;
+    a.bh = base; a.bt = base + S; a.br = base + 2 * S;
+    a.gent = gent; a.grel = grel; a.loss_terms = loss_terms;
+    a.margin = hp->margin; a.w = 1.0f / (float)(c->B * (c->K + c->KR));
+    a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)(2 + c->K); a.NR = (i32)(1 + c->KR);
+    a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi; a.slot_base = (i32)slot_base;
+    a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_n = 0; a.npf = 0;
+}
+// warps per positive the generic grad kernel uses for this batch (1 = one warp per positive); a function of the GLOBAL
+// batch, so that a data-parallel rank's slice is computed exactly like the same positives on one GPU
+int okb_grad_wpp(okb_ctx *c) {
+    const bool k1 = c->K == 1 && c->KR == 0 && !c->grad_generic;
+    if (k1 || c->K < 2 || c->grad_single_warp) return 1;
+    return (int)std::max<i64>(1, std::min<i64>(std::min<i64>(4, c->K), (i64)okb_sms(c) * 20 / std::max<i64>(1, c->B)));
+}
 static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, INT slot_base, float *gent,
                        float *grel, float *loss_terms, const unsigned long long *wait_flags, unsigned long long wait_epoch, int wait_n,
                        void *stream) {
@@ -615,13 +635,7 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
                                       b_lo, b_hi, gent, grel, loss_terms, s);
     }
     GradArgs a;
-    a.m = *m;
-    const i32 *base = c->batch.as<i32>() + step * 3 * S;
-    a.bh = base; a.bt = base + S; a.br = base + 2 * S;
-    a.gent = gent; a.grel = grel; a.loss_terms = loss_terms;
-    a.margin = hp->margin; a.w = 1.0f / (float)(c->B * (c->K + c->KR));
-    a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)(2 + c->K); a.NR = (i32)(1 + c->KR);
-    a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi; a.slot_base = (i32)slot_base;
+    okb_fill_grad(c, m, hp, step, b_lo, b_hi, slot_base, gent, grel, loss_terms, a);
     a.wait_flags = wait_flags; a.wait_epoch = wait_epoch; a.wait_n = wait_n;
     if (wait_flags)
         for (int q = 0; q < wait_n; q++)
@@ -664,9 +678,7 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     const bool k1 = c->K == 1 && c->KR == 0 && !c->grad_generic && a.npf == 0;
     if (k1) { cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32); }
     // small batches with several negatives: 2..4 warps per positive, as many as fill ~20 warp slots per SM
-    int wpp = 1;
-    // (a function of the GLOBAL batch, so that a data-parallel rank's slice is computed exactly like the same positives on one GPU)
-    if (!k1 && c->K >= 2 && !c->grad_single_warp) wpp = (int)std::max<i64>(1, std::min<i64>(std::min<i64>(4, c->K), (i64)okb_sms(c) * 20 / std::max<i64>(1, c->B)));
+    const int wpp = k1 ? 1 : okb_grad_wpp(c);
     if (wpp > 1) {
         const int N = vw * nv, F = 2 * (m->model == OKB_TRANSD ? 2 : 1) + (m->model == OKB_TRANSE ? 1 : 2);
         cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32 * wpp);
@@ -684,17 +696,16 @@ int okb_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT 
     return launch_grad(c, m, hp, step, b_lo, b_hi, 0, gent, grel, loss_terms, nullptr, 0, 0, stream);
 }
 
-int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
-               const float *loss_terms, float *loss_out, void *stream) {
-    int vw, nv;
-    int rc = check_model(c, m, vw, nv);
-    if (rc) return rc;
+}  // extern "C"
+// Everything the update kernels of one step need (no launch): plan pointers, gradient buffers, hub decision + its
+// partial-sum buffer, loss reduction scratch and — for Adam — the dense table list.  blk: 256-vector tiles of the Adam pass.
+int okb_fill_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
+                    const float *loss_terms, float *loss_out, int vw, cudaStream_t s, UpdArgs &a, i32 &blk, bool &lean) {
+    int rc;
     const bool is_tr = m->model == OKB_TRANSR;
-    cudaStream_t s = (cudaStream_t)stream;
     const i64 n = c->plan_ne + c->plan_nr;
     if (n == 0 || !planned(c, step, step + 1, 0, c->B)) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
     const i64 total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
-    UpdArgs a;
     a.m = *m; a.hp = *hp;
     a.skeys = c->keys_ent.as<i32>() + total + rel; a.perm = c->perm_ent.as<i32>() + rel;
     a.gent = gent; a.grel = grel; a.loss_terms = loss_terms; a.loss_out = loss_out;
@@ -717,17 +728,13 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         const i64 nblocks = n / PCH;
         if (c->partial.ensure(sizeof(float) * (size_t)(nblocks + 1) * a.pcols)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (partial sums)");
         a.partial = c->partial.as<float>();
-        const unsigned pg = (unsigned)((nblocks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK + 1);
-#define CALL_PRE(VW, NV) prereduce_kernel<VW, NV><<<pg, WARPS_PER_BLOCK * 32, 0, s>>>(a, c->partial.as<float>())
-        DISPATCH_LAYOUT(vw, nv, CALL_PRE);
-        OKB_LAUNCHED(1);
     }
     a.work_blocks = (i32)((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    blk = 0;
+    lean = !c->adam_legacy;
     if (m->optimizer == OKB_ADAM) {
         if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
         i64 acc = 0;
-        i32 blk = 0;
-        bool lean = !c->adam_legacy;
         auto add = [&](float *x, float *mm, float *vv, i64 nrows, int D, bool is_ent, int part) {
             if (!x) return;
             acc += nrows * D / vw;
@@ -755,6 +762,30 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
 #else
         a.work_blocks = (i32)std::min<i64>((acc + 255) / 256, (i64)okb_sms(c) * 16);
 #endif
+    }
+    return 0;
+}
+extern "C" {
+int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
+               const float *loss_terms, float *loss_out, void *stream) {
+    int vw, nv;
+    int rc = check_model(c, m, vw, nv);
+    if (rc) return rc;
+    const bool is_tr = m->model == OKB_TRANSR;
+    cudaStream_t s = (cudaStream_t)stream;
+    const i64 n = c->plan_ne + c->plan_nr;
+    UpdArgs a;
+    i32 blk = 0;
+    bool lean = true;
+    if ((rc = okb_fill_update(c, m, hp, step, gent, grel, loss_terms, loss_out, vw, s, a, blk, lean))) return rc;
+    if (a.hub) {
+        const i64 nblocks = n / PCH;
+        const unsigned pg = (unsigned)((nblocks + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK + 1);
+#define CALL_PRE(VW, NV) prereduce_kernel<VW, NV><<<pg, WARPS_PER_BLOCK * 32, 0, s>>>(a, c->partial.as<float>())
+        DISPATCH_LAYOUT(vw, nv, CALL_PRE);
+        OKB_LAUNCHED(1);
+    }
+    if (m->optimizer == OKB_ADAM) {
         ProfScope ps(c, PROF_UPDATE, s);
         // programmatic dependent launch: the kernel may start while the grad kernel drains (see adam_kernel)
         cudaLaunchConfig_t cfg = {};
@@ -817,6 +848,15 @@ int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT ste
     if (!planned(c, step_lo, step_lo + n, 0, c->B)) {
         int rc = okb_plan_steps(c, step_lo, step_lo + n, stream);
         if (rc) return rc;
+    }
+    {   // the whole chunk as one persistent kernel where covered (chunk.cu); -1 = not covered: per-phase kernels below
+        INT er, ec, rr, rcn;
+        int rc = okb_grad_sizes(c, m, c->B, c->K, c->KR, &er, &ec, &rr, &rcn);
+        if (rc) return rc;
+        if (c->gent.ensure(sizeof(float) * er * ec) || c->grel.ensure(sizeof(float) * rr * rcn) || c->lossterms.ensure(sizeof(float) * c->B))
+            OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (gradient rows)");
+        rc = okb_chunk_kernel_steps(c, m, hp, step_lo, n, loss_out, (cudaStream_t)stream);
+        if (rc >= 0) return rc;
     }
     for (INT i = 0; i < n; i++) {
         int rc = okb_train_step(c, m, hp + i, step_lo + i, loss_out ? loss_out + i : nullptr, stream);

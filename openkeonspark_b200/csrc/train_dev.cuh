@@ -1057,3 +1057,14 @@ __global__ void __launch_bounds__(256, ADAM_TILE_MIN_BLOCKS) adam_tile_kernel(Up
     *reinterpret_cast<V *>(px) = xv; *reinterpret_cast<V *>(pm) = mv; *reinterpret_cast<V *>(pv) = vv;
 }
 
+
+// ------------------------------------------------------------------------------------------ host-side builders (train.cu)
+int okb_fill_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
+                    const float *loss_terms, float *loss_out, int vw, cudaStream_t s, UpdArgs &a, i32 &blk, bool &lean);
+void okb_fill_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, INT b_lo, INT b_hi, INT slot_base, float *gent,
+                   float *grel, float *loss_terms, GradArgs &a);
+int okb_grad_wpp(okb_ctx *c);
+bool okb_pick_layout(int D, int &vw, int &nv);
+// chunk.cu: n consecutive planned steps as ONE persistent cooperative kernel; returns -1 if this configuration is not
+// covered (the caller then runs the per-phase kernels), 0 on success, else an OKB_ERR_* code
+int okb_chunk_kernel_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out, cudaStream_t s);

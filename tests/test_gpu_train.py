@@ -280,3 +280,36 @@ def test_single_kernel_plan_digit_widths(built, E, R, n_train, nbatches, k, kr):
     assert outs[0][0] == outs[1][0]
     for name in outs[0][1]:
         assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
+
+
+@pytest.mark.parametrize("threads", ["512", "640"])
+@pytest.mark.parametrize("model,opt,D,k,kr,ds,single_warp", [
+    ("TransH", "Adam", 100, 1, 0, "small", 0),        # the bench workload's kernel pair: k = 1 grad body + dense Adam; hub rows (23 Zipf relations)
+    ("TransE", "SGD", 50, 1, 0, "small", 0),          # 64-bit row fragments
+    ("TransD", "Adam", 100, 1, 0, "wide", 0),         # two tables per entity, no hub rows
+    ("TransE", "SGD", 200, 1, 0, "wide", 0),          # two 128-bit vectors per lane
+    ("TransE", "Adam", 64, 1, 0, "small", 0),
+    ("TransH", "SGD", 100, 3, 1, "small", 1),         # generic grad body (several negatives, relation negatives), one warp per positive
+    ("TransD", "Adam", 36, 2, 0, "wide", 1)])
+def test_persistent_chunk_kernel_equals_per_phase_kernels(built, small_ds, wide_ds, monkeypatch, model, opt, D, k, kr, ds, single_warp, threads):
+    """okb_train_steps runs a chunk as ONE persistent cooperative kernel (csrc/chunk.cu: grad -> grid barrier -> update per
+    step) where covered; OKB_FLAG_CHUNK_KERNEL = 0 forces the per-phase kernels.  Same bodies, same fp32 order:
+    losses and tables must be bit-identical, for both CTA sizes."""
+    monkeypatch.setenv("OKB200_CHUNK_THREADS", threads)
+    path = {"small": small_ds, "wide": wide_ds}[ds]
+    outs = []
+    for chunk_kernel in (0, 1):
+        con = _config(path, model, D, k, kr, opt, nbatches=5)
+        con.ctx.call("okb_set_flag", 10, chunk_kernel)
+        con.ctx.call("okb_set_flag", 8, single_warp)
+        con.set_parameters(make_params(model, con.entTotal, con.relTotal, D, seed=5))
+        from openkeonspark_b200 import _native
+        l0 = _native.load().okb_launch_count()
+        losses = []
+        for n in (7, 2, 5):
+            losses += [float(x) for x in con.train_chunk_device(n, 0).cpu().numpy()]
+        outs.append((losses, con.get_parameters(), _native.load().okb_launch_count() - l0))
+    assert outs[0][0] == outs[1][0], (outs[0][0], outs[1][0])
+    for name in outs[0][1]:
+        assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
+    assert outs[1][2] < outs[0][2] - 2 * 10, (outs[0][2], outs[1][2])       # 14 steps: >= 28 grad/update launches became 3
