@@ -326,11 +326,16 @@ enum { OKB_FLAG_TRANSR_TC = 1,
        /* OKB_FLAG_PLAN_MULTI = 9 (default off): plan a single step with the general multi-kernel segmented sort instead of the
           one-CTA single-kernel plan (A/B and test switch; results are identical). */
        OKB_FLAG_PLAN_MULTI = 9,
-       /* OKB_FLAG_CHUNK_KERNEL = 10 (default on): okb_train_steps runs a chunk of planned steps as ONE persistent cooperative
+       /* OKB_FLAG_CHUNK_KERNEL = 10 (default off): okb_train_steps runs a chunk of planned steps as ONE persistent cooperative
           kernel (grad -> grid barrier -> update per step; csrc/chunk.cu) where the configuration is covered (TransE/H/D,
-          single GPU, one warp per positive, D in the vectorised layouts); 0 = always the per-phase kernels.  Results are
-          bit-identical either way. */
-       OKB_FLAG_CHUNK_KERNEL = 10 };
+          k = 1 batch, single GPU, D in the vectorised layouts).  Bit-identical results; measured SLOWER than the per-phase
+          kernels chained with programmatic dependent launch (18.0 vs 25.2 us per step on the bench workload), so it is
+          kept for A/B runs only. */
+       OKB_FLAG_CHUNK_KERNEL = 10,
+       /* OKB_FLAG_ADAM_VPT = 11: vectors per thread (1..4) of the dense Adam pass: a CTA owns 256 * value consecutive vectors
+          of one table and every thread has all its row-map entries and x / m / v vectors in flight before the first
+          gradient load.  Bit-identical results for every value. */
+       OKB_FLAG_ADAM_VPT = 11 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:

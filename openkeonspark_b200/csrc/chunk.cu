@@ -15,6 +15,12 @@
 // The grid barrier is a monotonically increasing arrival counter in global memory (release fence + atomic, acquire
 // spin by one thread per CTA); cooperative launch guarantees that all CTAs are resident, the spin is bounded.
 //
+// MEASURED (B200, profiles/README.md r02c): slower than the per-phase kernels chained with programmatic dependent launch —
+// TransH D=100 Adam 25.2-28.0 vs 18.0 us/step, TransE D=50 SGD 19.6-20.8 vs 19.2 — because one resident CTA of 16-20
+// warps per SM (the grad body needs 94-128 registers) halves the occupancy of the Adam pass and nothing overlaps across
+// a grid barrier, while PDL already hides most of the launch/ramp cost this kernel was built to remove.  Kept behind
+// OKB_FLAG_CHUNK_KERNEL (default OFF) as the A/B baseline of that experiment.
+//
 // Replaces the loop body of /root/reference/distribute_training.py:267-283 (sess.run([train_op, loss]) per batch) for a
 // chunk at a time; TransE.py:26-51 / TransH.py:33-69 / TransD.py:46-84 + distribute_training.py:94-101.
 #include <algorithm>
@@ -175,15 +181,16 @@ static int launch_chunk_nt(okb_ctx *c, const ChunkArgs &a, cudaStream_t s) {
 }
 template <int MODEL, int VW, int NV>
 static int launch_chunk(okb_ctx *c, const ChunkArgs &a, int nt, cudaStream_t s) {
-    if (a.k1) return nt == 512 ? launch_chunk_nt<MODEL, VW, NV, 512, true>(c, a, s) : launch_chunk_nt<MODEL, VW, NV, 640, true>(c, a, s);
-    return nt == 512 ? launch_chunk_nt<MODEL, VW, NV, 512, false>(c, a, s) : launch_chunk_nt<MODEL, VW, NV, 640, false>(c, a, s);
+    return nt == 512 ? launch_chunk_nt<MODEL, VW, NV, 512, true>(c, a, s) : launch_chunk_nt<MODEL, VW, NV, 640, true>(c, a, s);
 }
 
 int okb_chunk_kernel_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out, cudaStream_t s) {
     if (!c->chunk_kernel || n < 2 || n > CK_MAX_STEPS) return -1;
     if (m->model != OKB_TRANSE && m->model != OKB_TRANSH && m->model != OKB_TRANSD) return -1;
     if (c->dp_on || c->batch_from_host || c->prof_on || c->l2_prefetch || c->adam_legacy || c->adam_tma) return -1;
-    if (okb_grad_wpp(c) != 1) return -1;                    // the multi-warp-per-positive kernel associates shared rows differently
+    // the k = 1, kr = 0 batch only (the reference's default): the generic grad body inlined into this kernel is contracted
+    // to FMAs differently than in grad_kernel, so its sums differ in the last bit — not acceptable for a drop-in A/B path
+    if (!(c->K == 1 && c->KR == 0 && !c->grad_generic)) return -1;
     int vw, nv;
     if (!okb_pick_layout(m->ent_dim, vw, nv) || m->ent_dim != m->rel_dim) return -1;
     if (!((vw == 4 && (nv == 1 || nv == 2)) || (vw == 2 && nv == 1))) return -1;      // D in (64, 256] with D % 4 == 0; even D in (32, 64]

@@ -83,11 +83,12 @@ struct okb_ctx {
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
     bool batch_from_host = false;     // the current batch came through okb_batch_from_host: update kernels honour the "bad id" flag
-    bool chunk_kernel = true;         // OKB_FLAG_CHUNK_KERNEL: okb_train_steps runs a chunk as one persistent kernel where covered
+    bool chunk_kernel = false;        // OKB_FLAG_CHUNK_KERNEL: okb_train_steps runs a chunk as one persistent kernel where covered (measured slower: off)
     bool plan_multi = false;          // OKB_FLAG_PLAN_MULTI: one-step plans use the multi-kernel sort too
     bool plan_small_attr = false;     // dynamic shared memory limit of plan_small_kernel raised on this device
     bool grad_single_warp = false;    // OKB_FLAG_GRAD_SINGLE_WARP: never split a positive's negatives over several warps
     bool grad_generic = false;        // OKB_FLAG_GRAD_GENERIC: never use the k = 1 specialisation of the grad kernel
+    int adam_vpt = 1;                 // vectors per thread of adam_tile_kernel (1..4; OKB200_ADAM_VPT for A/B runs)
     bool adam_legacy = false;         // OKB_FLAG_ADAM_LEGACY: grid-stride register kernel instead of the tile kernel
     bool adam_tma = false;            // OKB_FLAG_ADAM_TMA: TMA-staged single-wave Adam pass instead of the register-only one
     bool l2_prefetch = false;         // OKB_FLAG_L2_PREFETCH: grad kernel prefetches the Adam state into L2

@@ -382,6 +382,23 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, unsigned
                  : "memory");
 }
 
+// Packed fp32 pairs (sm_100 add/sub.rn.f32x2 -> SASS FADD2): two individually rounded adds per issue slot.  ptxas folds
+// the |.| of the distance and the scalar broadcast of the candidate element into the instruction's source modifiers
+// (FADD2 R, R.F32x2.HI_LO, |R|.F32x2.HI_LO / -R.F32), so the L1 distance loop costs ONE issue slot per (query, candidate,
+// dim) instead of two — the loop is issue-bound (ncu: issue-active 69 %, FMA pipe 38 % with scalar FADDs).  Each half
+// is rounded to nearest like __fadd_rn / __fsub_rn: scores stay bit-identical to the canonical order.
+__device__ __forceinline__ float2 sub2_rn(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 abs2(float2 a) { return make_float2(fabsf(a.x), fabsf(a.y)); }
+
 struct RankArgs {
     const float *cand;         // [ntab][D][ncol]
     const float *rv;           // [G][2][D]
@@ -491,29 +508,32 @@ __global__ void __launch_bounds__(CT * QG, 1024 / (CT * QG)) rank_kernel(RankArg
         if (qg < nb) {
             const i32 q0 = qg * QB;                        // this thread group's queries within the pass
             const float *qas = qa + (size_t)qg * D * QB, *qts = qt + (size_t)qg * D * QB;
-            float accT[QB], accH[QB];
+            float2 accT2[QB / 2], accH2[QB / 2];
 #pragma unroll
-            for (int q = 0; q < QB; q++) { accT[q] = 0.f; accH[q] = 0.f; }
+            for (int q = 0; q < QB / 2; q++) { accT2[q] = make_float2(0.f, 0.f); accH2[q] = make_float2(0.f, 0.f); }
 #pragma unroll 4
             for (int d = 0; d < D; d++) {
                 const float c = tile[d * CT + jl];
                 const float cr = __fadd_rn(c, rhat[d]);
+                const float2 c2 = make_float2(c, c), cr2 = make_float2(cr, cr);
                 const float4 *pa = (const float4 *)(qas + d * QB), *pt = (const float4 *)(qts + d * QB);
 #pragma unroll
                 for (int v = 0; v < QB / 4; v++) {
                     const float4 x = pa[v];
-                    accT[4 * v + 0] = __fadd_rn(accT[4 * v + 0], fabsf(__fsub_rn(x.x, c)));
-                    accT[4 * v + 1] = __fadd_rn(accT[4 * v + 1], fabsf(__fsub_rn(x.y, c)));
-                    accT[4 * v + 2] = __fadd_rn(accT[4 * v + 2], fabsf(__fsub_rn(x.z, c)));
-                    accT[4 * v + 3] = __fadd_rn(accT[4 * v + 3], fabsf(__fsub_rn(x.w, c)));
+                    accT2[2 * v + 0] = add2_rn(accT2[2 * v + 0], abs2(sub2_rn(make_float2(x.x, x.y), c2)));
+                    accT2[2 * v + 1] = add2_rn(accT2[2 * v + 1], abs2(sub2_rn(make_float2(x.z, x.w), c2)));
                     if (HEADS) {
                         const float4 y = pt[v];
-                        accH[4 * v + 0] = __fadd_rn(accH[4 * v + 0], fabsf(__fsub_rn(cr, y.x)));
-                        accH[4 * v + 1] = __fadd_rn(accH[4 * v + 1], fabsf(__fsub_rn(cr, y.y)));
-                        accH[4 * v + 2] = __fadd_rn(accH[4 * v + 2], fabsf(__fsub_rn(cr, y.z)));
-                        accH[4 * v + 3] = __fadd_rn(accH[4 * v + 3], fabsf(__fsub_rn(cr, y.w)));
+                        accH2[2 * v + 0] = add2_rn(accH2[2 * v + 0], abs2(sub2_rn(cr2, make_float2(y.x, y.y))));
+                        accH2[2 * v + 1] = add2_rn(accH2[2 * v + 1], abs2(sub2_rn(cr2, make_float2(y.z, y.w))));
                     }
                 }
+            }
+            float accT[QB], accH[QB];
+#pragma unroll
+            for (int q = 0; q < QB / 2; q++) {
+                accT[2 * q] = accT2[q].x; accT[2 * q + 1] = accT2[q].y;
+                accH[2 * q] = accH2[q].x; accH[2 * q + 1] = accH2[q].y;
             }
             const int lane = tid & 31;
 #pragma unroll

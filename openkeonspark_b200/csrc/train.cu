@@ -735,14 +735,16 @@ int okb_fill_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT ste
     if (m->optimizer == OKB_ADAM) {
         if (!m->m_ent || !m->v_ent || !m->m_rel || !m->v_rel) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");
         i64 acc = 0;
+        i32 sblk = 0;
         auto add = [&](float *x, float *mm, float *vv, i64 nrows, int D, bool is_ent, int part) {
             if (!x) return;
             acc += nrows * D / vw;
             blk += (i32)((nrows * D / vw + ADAM_TILE_V - 1) / ADAM_TILE_V);
+            sblk += (i32)((nrows * D / vw + ADAM_TILE_V * c->adam_vpt - 1) / (ADAM_TILE_V * c->adam_vpt));
             DenseTab T;
             T.x = x; T.m = mm; T.v = vv; T.grad = is_ent ? gent : grel; T.vec_end = acc; T.D = D;
             T.key_off = is_ent ? 0 : (i32)c->E; T.cols = is_ent ? a.ce : a.cr; T.part = part;
-            T.slot_off = is_ent ? 0 : (i32)c->plan_ne; T.blk_end = blk;
+            T.slot_off = is_ent ? 0 : (i32)c->plan_ne; T.blk_end = blk; T.sblk_end = sblk;
             {   // row = vector / vpr for vector < 2^31: multiply-high by ceil(2^(32+s) / vpr), s = floor(log2 vpr)
                 const unsigned vpr = (unsigned)(D / vw);
                 unsigned sh = 0;
@@ -800,12 +802,15 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
             a.work_blocks = std::min<i32>(blk, okb_sms(c) * 2);
             cfg.gridDim = dim3((unsigned)(a.work_blocks + a.loss_blocks)); cfg.dynamicSmemBytes = smem;
             OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_pipe_kernel, a, (int)blk));
-        } else if (lean) {                                 // one tile per CTA, block-uniform table (adam_tile_kernel)
-            a.work_blocks = blk;
+        } else if (lean) {                                 // one super tile per CTA, block-uniform table (adam_tile_kernel)
+            a.work_blocks = a.tab[a.ntab - 1].sblk_end;
             cfg.gridDim = dim3((unsigned)(a.work_blocks + a.loss_blocks));
-            if (vw == 4) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<4>, a));
-            else if (vw == 2) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<2>, a));
-            else OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<1>, a));
+#define CALL_TILE(VW)                                                                                   \
+            if (c->adam_vpt == 1) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<VW, 1>, a));         \
+            else if (c->adam_vpt == 2) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<VW, 2>, a));    \
+            else if (c->adam_vpt == 3) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<VW, 3>, a));    \
+            else OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_tile_kernel<VW, 4>, a))
+            if (vw == 4) { CALL_TILE(4); } else if (vw == 2) { CALL_TILE(2); } else { CALL_TILE(1); }
         } else if (vw == 4) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_kernel<4>, a));
         else if (vw == 2) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_kernel<2>, a));
         else OKB_CUDA(c, cudaLaunchKernelEx(&cfg, adam_kernel<1>, a));
@@ -949,7 +954,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) dp_reduce_push_kernel(Up
             for (int p = 0; p < parts; p++) {
                 Frag<VW, NV> f;
                 f.zero();
-                if (seg.x >= 0) seg_sum<VW, NV>(a, seg.x, seg.y, is_ent, D, p, lane, f.v);
+                if (seg.x >= 0) seg_sum_map<VW, NV>(a, seg, is_ent, D, p, lane, f.v);
                 f.store(dst + p * D, D, lane);
             }
         }
@@ -1003,11 +1008,18 @@ __global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
 #pragma unroll
         for (int q = 0; q < VW; q++) g[q] = 0.f;
         bool any = false;
-        for (int p = 0; p < d.world; p++) {                // partial rows in rank order
-            const V gp = __ldcg(reinterpret_cast<const V *>(st + (i64)p * T.own_max * T.cols));
-            const float *pg = reinterpret_cast<const float *>(&gp);
+        for (int p0 = 0; p0 < d.world; p0 += 4) {          // partial rows in rank order; four loads in flight at a time
+            V gp[4];
 #pragma unroll
-            for (int q = 0; q < VW; q++) { g[q] += pg[q]; any |= pg[q] != 0.f; }
+            for (int u = 0; u < 4; u++)
+                if (p0 + u < d.world) gp[u] = __ldcg(reinterpret_cast<const V *>(st + (i64)(p0 + u) * T.own_max * T.cols));
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (p0 + u >= d.world) break;
+                const float *pg = reinterpret_cast<const float *>(&gp[u]);
+#pragma unroll
+                for (int q = 0; q < VW; q++) { g[q] += pg[q]; any |= pg[q] != 0.f; }
+            }
         }
         float *xs = reinterpret_cast<float *>(&xv);
         if (d.adam) {

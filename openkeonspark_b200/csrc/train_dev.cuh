@@ -724,6 +724,7 @@ __global__ void __launch_bounds__(32, GRAD1_MIN_BLOCKS) grad_k1_kernel(GradArgs 
 // ------------------------------------------------------------------------------------------ update
 // one parameter table for the flat Adam pass; vec_end: cumulative vector count over the table list
 struct DenseTab { float *x, *m, *v; const float *grad; i64 vec_end; i32 D, key_off, cols, part, slot_off, blk_end;
+                  i32 sblk_end;                // cumulative count of (256 * vectors-per-thread)-vector super tiles (adam_tile_kernel)
                   unsigned magic, shift; };    // row = vector / (D / VW) as __umulhi(vector, magic) >> shift (magic 0: shift only)
 struct UpdArgs {
     okb_model m;
@@ -827,6 +828,26 @@ __device__ __forceinline__ void seg_sum(const UpdArgs &a, i32 s, i32 e, bool is_
     }
 }
 
+// Same sum driven by the row-map entry {first, end, slot0, slot1}: the gradient slots of the first two entries are inlined
+// there, so the common short segment needs no perm[] hop at all.  Same ascending order as seg_sum -> same bits.
+template <int VW, int NV, bool COH = false>
+__device__ __forceinline__ void seg_sum_map(const UpdArgs &a, const int4 seg, bool is_ent, int D, int part, int lane, float *acc) {
+    constexpr int N = VW * NV;
+    const i32 cnt = seg.y - seg.x;
+    if (a.hub && cnt > PCH && (seg.x + PCH - 1) / PCH < seg.y / PCH) { seg_sum<VW, NV, COH>(a, seg.x, seg.y, is_ent, D, part, lane, acc); return; }
+    auto row = [&](i32 slot) { return (is_ent ? a.gent + (i64)slot * a.ce : a.grel + (i64)(slot - a.n_ent_slots) * a.cr) + part * D; };
+    Frag<VW, NV> f0, f1;
+    f0.template load<COH>(row(seg.z), D, lane);
+    if (cnt > 1) f1.template load<COH>(row(seg.w), D, lane); else f1.zero();
+#pragma unroll
+    for (int q = 0; q < N; q++) acc[q] += f0.v[q];
+    if (cnt > 1) {
+#pragma unroll
+        for (int q = 0; q < N; q++) acc[q] += f1.v[q];
+    }
+    if (cnt > 2) sum_rows<VW, NV, COH>(a, seg.x + 2, seg.y, is_ent, D, part, lane, acc, false);
+}
+
 // Hub path, level 1: one warp per PCH-aligned block of sorted positions; a block that lies inside ONE
 // segment is summed into partial[block].  Block boundaries depend only on positions: fixed order.
 template <int VW, int NV, bool COH>
@@ -861,19 +882,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) prereduce_kernel(UpdArgs
 template <int VW, int NV, bool COH>
 __device__ __forceinline__ void sgd_body(const UpdArgs &a, i32 w, int lane) {
     constexpr int N = VW * NV;
-    i32 key, i, end;
+    i32 key;
+    int4 seg;
     if (a.by_row) {
         key = w;
         if (key >= a.key_limit) return;
-        const int4 seg = __ldg(a.rowhead + key);
+        seg = __ldg(a.rowhead + key);
         if (seg.x < 0) return;
-        i = seg.x; end = seg.y;
     } else {
-        i = w;
-        if (i >= a.n) return;
-        key = a.skeys[i];
-        if (key >= a.key_limit || (i > 0 && a.skeys[i - 1] == key)) return;
-        end = __ldg(a.rowhead + key).y;
+        if (w >= a.n) return;
+        key = a.skeys[w];
+        if (key >= a.key_limit || (w > 0 && a.skeys[w - 1] == key)) return;
+        seg = __ldg(a.rowhead + key);
     }
     const bool is_ent = key < a.E;
     const int D = is_ent ? a.m.ent_dim : a.m.rel_dim;
@@ -887,7 +907,7 @@ __device__ __forceinline__ void sgd_body(const UpdArgs &a, i32 w, int lane) {
         float g[N];
 #pragma unroll
         for (int q = 0; q < N; q++) g[q] = 0.f;
-        seg_sum<VW, NV, COH>(a, i, end, is_ent, D, p, lane, g);
+        seg_sum_map<VW, NV, COH>(a, seg, is_ent, D, p, lane, g);
 #pragma unroll
         for (int q = 0; q < N; q++) x.v[q] -= a.hp.lr * g[q];
         x.store(tab + off, D, lane);
@@ -1022,8 +1042,11 @@ __device__ __forceinline__ void adam_gsum(const UpdArgs &a, const DenseTab &T, c
         add_raw(b1 * PCH, seg.y);
     }
 }
-template <int VW>
-__global__ void __launch_bounds__(256, ADAM_TILE_MIN_BLOCKS) adam_tile_kernel(UpdArgs a) {
+// VPT vectors per thread: the CTA owns a super tile of 256 * VPT consecutive vectors of one table and every thread has the
+// row-map entries and x / m / v of ALL its vectors in flight before the first dependent gradient load — fewer, fatter
+// waves instead of three thin ones (the pass is latency-, not bandwidth-bound at these table sizes).
+template <int VW, int VPT>
+__global__ void __launch_bounds__(256, VPT == 1 ? ADAM_TILE_MIN_BLOCKS : (VPT == 2 ? 3 : 2)) adam_tile_kernel(UpdArgs a) {
     pdl_launch_dependents();                               // next step's grad kernel may prefetch its batch ids
     // the loss blocks come FIRST in the grid: the step's loss is out a few microseconds after the grad kernel has
     // finished, so a caller waiting for it (okb_wait_word) gets on with the next batch while the tables are updated
@@ -1031,30 +1054,45 @@ __global__ void __launch_bounds__(256, ADAM_TILE_MIN_BLOCKS) adam_tile_kernel(Up
     if (bid < 0) { pdl_wait(); loss_block(a, (i32)blockIdx.x, (i32)blockDim.x); return; }
     typedef typename VecT<VW>::T V;
     int t = 0;
-    while (bid >= a.tab[t].blk_end) t++;                   // block-uniform
+    while (bid >= a.tab[t].sblk_end) t++;                  // block-uniform
     const DenseTab &T = a.tab[t];
     const unsigned nvec = (unsigned)(T.vec_end - (t ? a.tab[t - 1].vec_end : 0));
-    const unsigned lv = ((unsigned)bid - (unsigned)(t ? a.tab[t - 1].blk_end : 0)) * 256u + threadIdx.x;
-    if (lv >= nvec) return;
+    const unsigned lv0 = ((unsigned)bid - (unsigned)(t ? a.tab[t - 1].sblk_end : 0)) * (256u * VPT) + threadIdx.x;
+    if (lv0 >= nvec) return;
     const unsigned vpr = (unsigned)T.D / VW;
-    const unsigned row = T.magic ? (__umulhi(lv, T.magic) >> T.shift) : (lv >> T.shift);
-    const unsigned col = (lv - row * vpr) * VW;
-    const size_t e = (size_t)lv * VW;
-    float *px = T.x + e, *pm = T.m + e, *pv = T.v + e;
-    const int4 seg = __ldg(a.rowhead + T.key_off + row);
+    unsigned col[VPT];
+    int4 seg[VPT];
+    V xv[VPT], mv[VPT], vv[VPT];
+#pragma unroll
+    for (int u = 0; u < VPT; u++) {
+        const unsigned lv = lv0 + 256u * u;
+        seg[u] = make_int4(-1, 0, 0, 0);
+        if (lv < nvec) {
+            const unsigned row = T.magic ? (__umulhi(lv, T.magic) >> T.shift) : (lv >> T.shift);
+            col[u] = (lv - row * vpr) * VW;
+            const size_t e = (size_t)lv * VW;
+            seg[u] = __ldg(a.rowhead + T.key_off + row);
+            xv[u] = *reinterpret_cast<const V *>(T.x + e); mv[u] = *reinterpret_cast<const V *>(T.m + e); vv[u] = *reinterpret_cast<const V *>(T.v + e);
+        }
+    }
     const unsigned badv = a.bad ? *(const volatile unsigned *)a.bad : 0u;     // host-batch steps only (see narrow_kernel)
-    V xv = *reinterpret_cast<const V *>(px), mv = *reinterpret_cast<const V *>(pm), vv = *reinterpret_cast<const V *>(pv);
     pdl_wait();                                            // gradient rows of this step are complete from here on
     if (badv) return;
-    float g[VW];
-#pragma unroll
-    for (int q = 0; q < VW; q++) g[q] = 0.f;
-    adam_gsum<VW, false>(a, T, seg, col, g);
     const float b1 = a.hp.beta1, b2 = a.hp.beta2, lr = a.hp.lr, eps = a.hp.eps, c1 = 1.f - b1, c2 = 1.f - b2;
-    float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
 #pragma unroll
-    for (int q = 0; q < VW; q++) adam_elem(xs[q], ms[q], vs[q], g[q], b1, b2, c1, c2, lr, eps);
-    *reinterpret_cast<V *>(px) = xv; *reinterpret_cast<V *>(pm) = mv; *reinterpret_cast<V *>(pv) = vv;
+    for (int u = 0; u < VPT; u++) {
+        const unsigned lv = lv0 + 256u * u;
+        if (lv >= nvec) break;
+        float g[VW];
+#pragma unroll
+        for (int q = 0; q < VW; q++) g[q] = 0.f;
+        adam_gsum<VW, false>(a, T, seg[u], col[u], g);
+        float *xs = reinterpret_cast<float *>(&xv[u]), *ms = reinterpret_cast<float *>(&mv[u]), *vs = reinterpret_cast<float *>(&vv[u]);
+#pragma unroll
+        for (int q = 0; q < VW; q++) adam_elem(xs[q], ms[q], vs[q], g[q], b1, b2, c1, c2, lr, eps);
+        const size_t e = (size_t)lv * VW;
+        *reinterpret_cast<V *>(T.x + e) = xv[u]; *reinterpret_cast<V *>(T.m + e) = mv[u]; *reinterpret_cast<V *>(T.v + e) = vv[u];
+    }
 }
 
 

@@ -288,13 +288,11 @@ def test_single_kernel_plan_digit_widths(built, E, R, n_train, nbatches, k, kr):
     ("TransE", "SGD", 50, 1, 0, "small", 0),          # 64-bit row fragments
     ("TransD", "Adam", 100, 1, 0, "wide", 0),         # two tables per entity, no hub rows
     ("TransE", "SGD", 200, 1, 0, "wide", 0),          # two 128-bit vectors per lane
-    ("TransE", "Adam", 64, 1, 0, "small", 0),
-    ("TransH", "SGD", 100, 3, 1, "small", 1),         # generic grad body (several negatives, relation negatives), one warp per positive
-    ("TransD", "Adam", 36, 2, 0, "wide", 1)])
+    ("TransE", "Adam", 64, 1, 0, "small", 0)])
 def test_persistent_chunk_kernel_equals_per_phase_kernels(built, small_ds, wide_ds, monkeypatch, model, opt, D, k, kr, ds, single_warp, threads):
-    """okb_train_steps runs a chunk as ONE persistent cooperative kernel (csrc/chunk.cu: grad -> grid barrier -> update per
-    step) where covered; OKB_FLAG_CHUNK_KERNEL = 0 forces the per-phase kernels.  Same bodies, same fp32 order:
-    losses and tables must be bit-identical, for both CTA sizes."""
+    """OKB_FLAG_CHUNK_KERNEL = 1: okb_train_steps runs a chunk as ONE persistent cooperative kernel (csrc/chunk.cu: grad ->
+    grid barrier -> update per step) where covered (the k = 1 batch); the default is the per-phase kernels (measured
+    faster).  Same bodies, same fp32 order: losses and tables must be bit-identical, for both CTA sizes."""
     monkeypatch.setenv("OKB200_CHUNK_THREADS", threads)
     path = {"small": small_ds, "wide": wide_ds}[ds]
     outs = []
@@ -313,3 +311,24 @@ def test_persistent_chunk_kernel_equals_per_phase_kernels(built, small_ds, wide_
     for name in outs[0][1]:
         assert np.array_equal(outs[0][1][name], outs[1][1][name]), name
     assert outs[1][2] < outs[0][2] - 2 * 10, (outs[0][2], outs[1][2])       # 14 steps: >= 28 grad/update launches became 3
+
+
+@pytest.mark.parametrize("model,D,ds", [("TransH", 100, "small"), ("TransD", 50, "wide"), ("TransE", 33, "small")])
+def test_adam_vectors_per_thread_bit_identical(built, small_ds, wide_ds, model, D, ds):
+    """OKB_FLAG_ADAM_VPT: 1..4 vectors per thread in the dense Adam pass (the gradient sums and the Adam rule are the same
+    functions, only the thread -> vector mapping changes): losses, tables and slots bit-identical."""
+    path = {"small": small_ds, "wide": wide_ds}[ds]
+    outs = []
+    for vpt in (1, 2, 3, 4):
+        con = _config(path, model, D, 2, 0, "Adam", nbatches=5)
+        con.ctx.call("okb_set_flag", 11, vpt)
+        con.set_parameters(make_params(model, con.entTotal, con.relTotal, D, seed=5))
+        losses = [float(x) for x in con.train_chunk_device(5, 0).cpu().numpy()]
+        slots = {k: v.cpu().numpy() for k, v in con._adam.items() if hasattr(v, "cpu")}
+        outs.append((losses, con.get_parameters(), slots))
+    for o in outs[1:]:
+        assert o[0] == outs[0][0]
+        for name in outs[0][1]:
+            assert np.array_equal(o[1][name], outs[0][1][name]), name
+        for name in outs[0][2]:
+            assert np.array_equal(o[2][name], outs[0][2][name]), name
