@@ -283,7 +283,8 @@ int okb_rank_finalize(okb_ctx *c, INT q_lo, INT q_hi, const int64_t *counts, con
 /* Reference-shaped single query with caller-provided scores (device float[E]); out device int64[8]. */
 int okb_rank_scores(okb_ctx *c, INT index, int side, const float *scores, int64_t *out, void *cuda_stream);
 
-/* ---- triple classification (Test.h:253-387): host-side, tiny. */
+/* ---- triple classification (Test.h:253-387).  Negatives are drawn on the host (libc rand(), inherently sequential);
+ *      scores, thresholds and counts are computed on the device. */
 int okb_tc_batch(okb_ctx *c, int which /*0 test, 1 valid*/, INT *ph, INT *pt, INT *pr, INT *nh, INT *nt, INT *nr);
 int okb_best_threshold(okb_ctx *c, REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg);
 int okb_tc_eval(okb_ctx *c, const REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg,
@@ -292,6 +293,14 @@ int okb_tc_eval(okb_ctx *c, const REAL *rel_thresh, const REAL *score_pos, const
  * note in csrc/loader.cpp about the reference's use of the test ranges there) */
 int okb_tc_eval_valid(okb_ctx *c, const REAL *rel_thresh, const REAL *score_pos, const REAL *score_neg,
                       INT *tp_tn_fp_fn, REAL *acc);
+/* The same two steps with DEVICE score arrays (index-aligned with the (r,h,t)-sorted valid / test lists, e.g. straight
+ * out of okb_predict) — csrc/tc.cu: one CTA per relation scans the threshold grid min + i * 0.01 (Test.h:303-341), a
+ * second kernel counts TP / TN / FP / FN over the test (on_valid = 0) or valid (on_valid = 1) ranges (Test.h:345-387).
+ * thresh: device float[R], in/out (relations without valid triples keep their entry).  The host-pointer entry points above
+ * stage their arrays and call these; results are bit-identical to the reference library. */
+int okb_tc_thresholds_dev(okb_ctx *c, const float *score_pos, const float *score_neg, float *thresh, void *cuda_stream);
+int okb_tc_counts_dev(okb_ctx *c, const float *thresh, const float *score_pos, const float *score_neg, int on_valid,
+                      INT *tp_tn_fp_fn /*host[4]*/, REAL *acc /*host*/, void *cuda_stream);
 int okb_test_list(okb_ctx *c, int which, INT *h, INT *t, INT *r);
 INT okb_n_interval(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg);            /* Test.h:390-407 */
 INT *okb_tpfp(okb_ctx *c, INT r, const REAL *score_pos, const REAL *score_neg, const REAL *score_pos_test,

@@ -612,10 +612,8 @@ class Config(object):
         if getattr(self, "_valid_batch_ready", False) is False:
             self.ctx.call("okb_tc_batch", 1, *[_vp(getattr(self, "valid_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")])
             self._valid_batch_ready = True
-        res_pos = self.test_step(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
-        res_neg = self.test_step(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
-        self.ctx.call("okb_best_threshold", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg))
-        self.ctx.call("okb_tc_eval_valid", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg), None, _vp(self.acc_addr))
+        th, vp, vn = self._fit_thresholds_device()
+        self.ctx.call("okb_tc_counts_dev", _vp(th.data_ptr()), _vp(vp.data_ptr()), _vp(vn.data_ptr()), 1, None, _vp(self.acc_addr), _stream())
         return float(self.acc[0])
 
     def run(self):
@@ -733,8 +731,8 @@ class Config(object):
     train = run
 
     # ------------------------------------------------------------------ scoring (Config.py:478-488)
-    def test_step(self, test_h, test_t, test_r):
-        """predict for arbitrary triples: float32 [n] (TransE) or [n,1] (TransH/R/D)."""
+    def test_step_device(self, test_h, test_t, test_r):
+        """predict_def for arbitrary triples, scores left on the GPU: float32 device tensor [n]."""
         self._ensure_model()
         self._settle()
         dev = self.trainModel.device
@@ -745,8 +743,23 @@ class Config(object):
         m = self._cmodel()
         self.ctx.call("okb_predict", ctypes.byref(m), _vp(h.data_ptr()), _vp(t.data_ptr()), _vp(r.data_ptr()), h.numel(),
                       _vp(out.data_ptr()), _stream())
-        res = out.cpu().numpy()
+        return out
+
+    def test_step(self, test_h, test_t, test_r):
+        """predict for arbitrary triples: float32 [n] (TransE) or [n,1] (TransH/R/D)."""
+        res = self.test_step_device(test_h, test_t, test_r).cpu().numpy()
         return res.reshape(-1, 1) if self.trainModel.predict_keepdims else res
+
+    def _fit_thresholds_device(self):
+        """getValidBatch + predict + getBestThreshold (Config.py:503-507) with scores, threshold grid search and the result
+        on the GPU; self.relThresh receives the fitted thresholds.  Returns (thresholds, valid pos scores, valid neg scores)
+        as device tensors."""
+        vp = self.test_step_device(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
+        vn = self.test_step_device(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
+        th = torch.as_tensor(self.relThresh).to(vp.device)
+        self.ctx.call("okb_tc_thresholds_dev", _vp(vp.data_ptr()), _vp(vn.data_ptr()), _vp(th.data_ptr()), _stream())
+        self.relThresh[:] = th.cpu().numpy()
+        return th, vp, vn
 
     # ------------------------------------------------------------------ evaluation
     def link_prediction_records(self, q_lo=0, q_hi=None, cand_lo=0, cand_hi=None, reduce_fn=None):
@@ -776,14 +789,12 @@ class Config(object):
         t0 = time.time()
         if self.test_triple_classification:
             self.ctx.call("okb_tc_batch", 1, *[_vp(getattr(self, "valid_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")])
-            res_pos = self.test_step(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
-            res_neg = self.test_step(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
-            self.ctx.call("okb_best_threshold", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg))
+            th, _, _ = self._fit_thresholds_device()          # scores, threshold search and counts stay on the GPU (csrc/tc.cu)
             self.ctx.call("okb_tc_batch", 0, *[_vp(getattr(self, "test_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")])
-            res_pos = self.test_step(self.test_pos_h, self.test_pos_t, self.test_pos_r)
-            res_neg = self.test_step(self.test_neg_h, self.test_neg_t, self.test_neg_r)
+            tp = self.test_step_device(self.test_pos_h, self.test_pos_t, self.test_pos_r)
+            tn = self.test_step_device(self.test_neg_h, self.test_neg_t, self.test_neg_r)
             cnt = np.zeros(4, np.int64)
-            self.ctx.call("okb_tc_eval", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg), _addr(cnt), _vp(self.acc_addr))
+            self.ctx.call("okb_tc_counts_dev", _vp(th.data_ptr()), _vp(tp.data_ptr()), _vp(tn.data_ptr()), 0, _addr(cnt), _vp(self.acc_addr), _stream())
             TP, TN, FP, FN = [float(x) for x in cnt]
             prec, rec = TP / max(TP + FP, 1.0), TP / max(TP + FN, 1.0)
             self.tc_counts = cnt
@@ -888,9 +899,7 @@ class Config(object):
         if thresh is None:
             a = [_vp(getattr(self, "valid_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")]
             self.ctx.call("okb_tc_batch", 1, *a)
-            res_pos = self.test_step(self.valid_pos_h, self.valid_pos_t, self.valid_pos_r)
-            res_neg = self.test_step(self.valid_neg_h, self.valid_neg_t, self.valid_neg_r)
-            self.ctx.call("okb_best_threshold", _vp(self.relThresh_addr), _addr(res_pos), _addr(res_neg))
+            self._fit_thresholds_device()
             thresh = self.relThresh[r]
         ok = bool(res.reshape(-1)[0] < thresh)
         print("triple (%d,%d,%d) is %s" % (h, t, r, "correct" if ok else "wrong"))

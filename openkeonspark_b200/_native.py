@@ -100,6 +100,8 @@ _SIGS = {
     "okb_best_threshold": (_int, [_vp, _vp, _vp, _vp]),
     "okb_tc_eval": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "okb_tc_eval_valid": (_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "okb_tc_thresholds_dev": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "okb_tc_counts_dev": (_int, [_vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "okb_test_list": (_int, [_vp, _int, _vp, _vp, _vp]),
     "okb_n_interval": (_i64, [_vp, _i64, _vp, _vp]),
     "okb_tpfp": (_vp, [_vp, _i64, _vp, _vp, _vp, _vp]),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libokb200.so")
-SOURCES = ["abi.cpp", "loader.cpp", "sampler.cu", "radix.cu", "train.cu", "chunk.cu", "score.cu", "transr.cu", "transr_tc.cu"]
+SOURCES = ["abi.cpp", "loader.cpp", "sampler.cu", "radix.cu", "train.cu", "chunk.cu", "score.cu", "tc.cu", "transr.cu", "transr_tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O2,-fno-fast-math,-ffp-contract=off", "-x", "cu", "-rdc=false"]

@@ -247,6 +247,7 @@ static int build_test(okb_ctx *c, const i64 *th, const i64 *tt, const i64 *tr, i
     sort_rht(pk, vh, vt, vr, n_valid, c->valid_h, c->valid_t, c->valid_r);
     rel_ranges(c->test_r, R, c->test_lef, c->test_rig);
     rel_ranges(c->valid_r, R, c->valid_lef, c->valid_rig);
+    c->tc_ranges_ready = false;                            // tc.cu re-uploads the ranges
     c->all_hrt.resize(c->n_all);
     i64 k = 0;
     for (i64 i = 0; i < n_test; i++) c->all_hrt[k++] = pk.ere(th[i], tr[i], tt[i]);
@@ -494,59 +495,43 @@ static bool score_range(const okb_ctx *c, i64 r, const REAL *pos, const REAL *ne
     return true;
 }
 static const float kInterval = 0.01f;     // Setting.h:118
-int okb_best_threshold(okb_ctx *c, REAL *thresh, const REAL *pos, const REAL *neg) {   // Test.h:304-341
+// Host-pointer entry points (the reference's ctypes calls pass numpy buffers): the scores are staged on the device and
+// the threshold search / counting run in tc.cu's kernels; nothing is computed on the CPU.
+int okb_tc_thresholds_dev(okb_ctx *c, const float *pos, const float *neg, float *thresh, void *stream);
+int okb_tc_counts_dev(okb_ctx *c, const float *thresh, const float *pos, const float *neg, int on_valid, INT *tp_tn_fp_fn, REAL *acc, void *stream);
+static int tc_stage(okb_ctx *c, const REAL *thresh, const REAL *pos, const REAL *neg, i64 n, float *&d_th, float *&d_pos, float *&d_neg) {
     if (c->valid_lef.empty()) OKB_FAIL(c, OKB_ERR_STATE, "import test files first");
-    for (i64 r = 0; r < c->R; r++) {
-        float mn, mx;
-        if (!score_range(c, r, pos, neg, mn, mx)) continue;
-        i64 lo = c->valid_lef[r], hi = c->valid_rig[r], total = (hi - lo + 1) * 2;
-        i64 n_int = (i64)((mx - mn) / kInterval);
-        float best_t = 0, best_a = 0;
-        for (i64 i = 0; i <= n_int; i++) {
-            float th = mn + i * kInterval;
-            i64 ok = 0;
-            for (i64 j = lo; j <= hi; j++) { ok += pos[j] <= th; ok += neg[j] > th; }
-            float acc = 1.0 * ok / total;
-            if (i == 0 || acc > best_a) { best_a = acc; best_t = th; }
-        }
-        thresh[r] = best_t;
-    }
+    if (c->tc_io.ensure(sizeof(float) * (size_t)(c->R + 2 * std::max<i64>(n, 1)))) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+    d_th = c->tc_io.as<float>(); d_pos = d_th + c->R; d_neg = d_pos + n;
+    OKB_CUDA(c, cudaMemcpy(d_th, thresh, sizeof(float) * c->R, cudaMemcpyHostToDevice));
+    OKB_CUDA(c, cudaMemcpy(d_pos, pos, sizeof(float) * n, cudaMemcpyHostToDevice));
+    OKB_CUDA(c, cudaMemcpy(d_neg, neg, sizeof(float) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+int okb_best_threshold(okb_ctx *c, REAL *thresh, const REAL *pos, const REAL *neg) {   // Test.h:304-341
+    float *d_th, *d_pos, *d_neg;
+    int rc = tc_stage(c, thresh, pos, neg, c->n_valid, d_th, d_pos, d_neg);
+    if (rc) return rc;
+    if ((rc = okb_tc_thresholds_dev(c, d_pos, d_neg, d_th, nullptr))) return rc;
+    OKB_CUDA(c, cudaMemcpy(thresh, d_th, sizeof(float) * c->R, cudaMemcpyDeviceToHost));
     return 0;
 }
 int okb_tc_eval(okb_ctx *c, const REAL *thresh, const REAL *pos, const REAL *neg, INT *cnt, REAL *acc) {   // Test.h:347-387
-    if (c->valid_lef.empty()) OKB_FAIL(c, OKB_ERR_STATE, "import test files first");
-    i64 TP = 0, TN = 0, FP = 0, FN = 0;
-    for (i64 r = 0; r < c->R; r++) {
-        if (c->valid_lef[r] == -1 || c->test_lef[r] == -1) continue;
-        for (i64 i = c->test_lef[r]; i <= c->test_rig[r]; i++) {
-            if (pos[i] <= thresh[r]) TP++; else FN++;
-            if (neg[i] > thresh[r]) TN++; else FP++;
-        }
-    }
-    if (cnt) { cnt[0] = TP; cnt[1] = TN; cnt[2] = FP; cnt[3] = FN; }
-    if (acc) acc[0] = 1.0 * (TP + TN) / (TP + TN + FP + FN);
-    return 0;
+    float *d_th, *d_pos, *d_neg;
+    int rc = tc_stage(c, thresh, pos, neg, c->n_test, d_th, d_pos, d_neg);
+    if (rc) return rc;
+    return okb_tc_counts_dev(c, d_th, d_pos, d_neg, 0, cnt, acc, nullptr);
 }
 // Accuracy of the thresholds on the VALID triples (early stopping, distribute_training.py:299-316).  The reference calls
 // test_triple_classification with the valid scores there, i.e. it indexes arrays of validTotal scores with the TEST
 // ranges (Test.h:355-366) — an out-of-bounds read whenever testTotal > validTotal.  The evident intent, accuracy over
 // the valid set with the thresholds just fitted on it, is what this entry point computes.
 int okb_tc_eval_valid(okb_ctx *c, const REAL *thresh, const REAL *pos, const REAL *neg, INT *cnt, REAL *acc) {
-    if (c->valid_lef.empty()) OKB_FAIL(c, OKB_ERR_STATE, "import test files first");
-    i64 TP = 0, TN = 0, FP = 0, FN = 0;
-    for (i64 r = 0; r < c->R; r++) {
-        if (c->valid_lef[r] == -1) continue;
-        for (i64 i = c->valid_lef[r]; i <= c->valid_rig[r]; i++) {
-            if (pos[i] <= thresh[r]) TP++; else FN++;
-            if (neg[i] > thresh[r]) TN++; else FP++;
-        }
-    }
-    if (cnt) { cnt[0] = TP; cnt[1] = TN; cnt[2] = FP; cnt[3] = FN; }
-    if (acc) acc[0] = (TP + TN + FP + FN) ? 1.0 * (TP + TN) / (TP + TN + FP + FN) : 0.f;
-    return 0;
+    float *d_th, *d_pos, *d_neg;
+    int rc = tc_stage(c, thresh, pos, neg, c->n_valid, d_th, d_pos, d_neg);
+    if (rc) return rc;
+    return okb_tc_counts_dev(c, d_th, d_pos, d_neg, 1, cnt, acc, nullptr);
 }
-
-// ---------------------------------------------------------------- ROC helpers (Test.h:391-444)
 INT okb_n_interval(okb_ctx *c, INT r, const REAL *pos, const REAL *neg) {
     float mn, mx;
     if (c->valid_lef.empty() || !score_range(c, r, pos, neg, mn, mx)) return 0;

@@ -116,6 +116,8 @@ struct okb_ctx {
     int sm_count = 0;                 // multiProcessorCount of the context's device (okb_sms)
     std::map<const void *, size_t> smem_attr;   // largest dynamic shared memory opted into per kernel on this device
     DevBuf legacy_scores, legacy_out; // testHead / testTail staging of the reference-compatible layer
+    DevBuf tc_ranges, tc_io;          // triple classification: per-relation valid / test ranges + counters; score staging of the host entry points
+    bool tc_ranges_ready = false;
 };
 
 // number of SMs of the current device (grids are sized in multiples of it)

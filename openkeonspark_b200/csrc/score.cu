@@ -76,19 +76,20 @@ __device__ float pred_one_transr(const okb_model &m, i64 h, i64 t, i64 r, i64 r0
     return s;
 }
 
-__device__ float pred_one(const okb_model &m, i64 h, i64 t, i64 r) {
-    const int D = m.ent_dim;
-    const float *eh = m.ent + h * D, *et = m.ent + t * D, *er = m.rel + r * D;
+// canonical score of one triple from its rows (all unit stride): eh / et entity rows, er relation row,
+// aux = normal vector (TransH) or rel_transfer (TransD), eth / ett = ent_transfer rows (TransD)
+__device__ __forceinline__ float pred_rows(int model, int D, const float *eh, const float *et, const float *er, const float *aux,
+                                           const float *eth, const float *ett) {
     const float inv_r = c_inv_norm(c_dot(er, 1, er, 1, D));
     float s = 0.f;
-    if (m.model == OKB_TRANSE) {
+    if (model == OKB_TRANSE) {
         const float ih = c_inv_norm(c_dot(eh, 1, eh, 1, D)), it = c_inv_norm(c_dot(et, 1, et, 1, D));
         for (int d = 0; d < D; d++) {
             const float a = __fadd_rn(__fmul_rn(eh[d], ih), __fmul_rn(er[d], inv_r));
             s = __fadd_rn(s, fabsf(__fsub_rn(a, __fmul_rn(et[d], it))));
         }
-    } else if (m.model == OKB_TRANSH) {
-        const float *n = m.rel_aux + r * D;
+    } else if (model == OKB_TRANSH) {
+        const float *n = aux;
         const float in = c_inv_norm(c_dot(n, 1, n, 1, D));
         float dh = 0.f, dt = 0.f;
         for (int d = 0; d < D; d++) {
@@ -111,8 +112,8 @@ __device__ float pred_one(const okb_model &m, i64 h, i64 t, i64 r) {
             s = __fadd_rn(s, fabsf(__fsub_rn(a, __fmul_rn(pt, it))));
         }
     } else {  // TransD
-        const float *rt = m.rel_aux + r * D;
-        const float ch = c_dot(eh, 1, m.ent_aux + h * D, 1, D), ct = c_dot(et, 1, m.ent_aux + t * D, 1, D);
+        const float *rt = aux;
+        const float ch = c_dot(eh, 1, eth, 1, D), ct = c_dot(et, 1, ett, 1, D);
         float sh = 0.f, st = 0.f;
         for (int d = 0; d < D; d++) {
             const float ph = __fadd_rn(eh[d], __fmul_rn(ch, rt[d])), pt = __fadd_rn(et[d], __fmul_rn(ct, rt[d]));
@@ -126,7 +127,41 @@ __device__ float pred_one(const okb_model &m, i64 h, i64 t, i64 r) {
             s = __fadd_rn(s, fabsf(__fsub_rn(a, __fmul_rn(pt, it))));
         }
     }
-    return c_finish(m.model, s, D);
+    return c_finish(model, s, D);
+}
+__device__ float pred_one(const okb_model &m, i64 h, i64 t, i64 r) {
+    const int D = m.ent_dim;
+    return pred_rows(m.model, D, m.ent + h * D, m.ent + t * D, m.rel + r * D, m.rel_aux ? m.rel_aux + r * D : nullptr,
+                     m.ent_aux ? m.ent_aux + h * D : nullptr, m.ent_aux ? m.ent_aux + t * D : nullptr);
+}
+
+// Staged form for TransE / TransH / TransD: a warp owns 32 triples, copies their rows into shared memory with coalesced
+// loads (lane = column) and then every lane walks ITS triple's rows in the canonical sequential order (row stride D + 1:
+// conflict-free).  Same arithmetic as pred_one — same bits — without 32 strided global streams per warp.
+__global__ void __launch_bounds__(64) predict_stage_kernel(PredArgs a, int narr) {
+    extern __shared__ float psm[];
+    const int D = a.m.ent_dim, lane = threadIdx.x & 31, w = threadIdx.x >> 5, sd = D + 1;
+    float *base = psm + (size_t)w * narr * 32 * sd;
+    const i64 i0 = ((i64)blockIdx.x * (blockDim.x >> 5) + w) * 32;
+    for (int rr = 0; rr < 32; rr++) {
+        const i64 i = i0 + rr;
+        if (i >= a.n) break;
+        const i64 h = a.h[i], t = a.t[i], r = a.r[i];
+        if (h < 0 || h >= a.E || t < 0 || t >= a.E || r < 0 || r >= a.R) continue;
+        const float *src[6] = {a.m.ent + h * D, a.m.ent + t * D, a.m.rel + r * D, a.m.rel_aux ? a.m.rel_aux + r * D : nullptr,
+                               a.m.ent_aux ? a.m.ent_aux + h * D : nullptr, a.m.ent_aux ? a.m.ent_aux + t * D : nullptr};
+        for (int q = 0; q < narr; q++) {
+            float *dst = base + ((size_t)q * 32 + rr) * sd;
+            for (int d = lane; d < D; d += 32) dst[d] = __ldg(src[q] + d);
+        }
+    }
+    __syncwarp();
+    const i64 i = i0 + lane;
+    if (i >= a.n) return;
+    const i64 h = a.h[i], t = a.t[i], r = a.r[i];
+    if (h < 0 || h >= a.E || t < 0 || t >= a.E || r < 0 || r >= a.R) { a.out[i] = __int_as_float(0x7fc00000); return; }
+    auto row = [&](int q) { return base + ((size_t)q * 32 + lane) * sd; };
+    a.out[i] = pred_rows(a.m.model, D, row(0), row(1), row(2), narr > 3 ? row(3) : nullptr, narr > 4 ? row(4) : nullptr, narr > 5 ? row(5) : nullptr);
 }
 
 __global__ void __launch_bounds__(128) predict_kernel(PredArgs a) {
@@ -694,7 +729,14 @@ int okb_predict(okb_ctx *c, const okb_model *m, const int64_t *h, const int64_t 
     if (n <= 0) return 0;
     PredArgs a;
     a.m = *m; a.h = h; a.t = t; a.r = r; a.out = out; a.n = n; a.E = (i32)c->E; a.R = (i32)c->R;
-    predict_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    // TransE / TransH / TransD with rows that fit the staging buffers: coalesced staged form; else one thread per triple
+    const int narr = m->model == OKB_TRANSE ? 3 : (m->model == OKB_TRANSH ? 4 : 6);
+    const size_t smem = sizeof(float) * 2 * (size_t)narr * 32 * (m->ent_dim + 1);
+    if (m->model != OKB_TRANSR && smem <= 200 * 1024 && n >= 64) {
+        OKB_CUDA(c, okb_smem_optin(c, predict_stage_kernel, smem));
+        predict_stage_kernel<<<(unsigned)((n + 63) / 64), 64, smem, (cudaStream_t)stream>>>(a, narr);
+    } else
+        predict_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
     OKB_LAUNCHED(1);
     OKB_CUDA(c, cudaGetLastError());
     return 0;

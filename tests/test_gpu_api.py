@@ -217,3 +217,68 @@ def test_table_shape_checks(built, tiny_ds):
     con.sampling_device()
     with pytest.raises(okb.OkbError, match="rows"):
         con.train_step_device(0)
+
+
+@pytest.mark.parametrize("model,D", [("TransE", 50), ("TransH", 100), ("TransD", 33), ("TransR", 20)])
+def test_triple_classification_device_kernels_match_reference(built, small_ds, model, D):
+    """csrc/tc.cu (threshold grid search + TP/TN/FP/FN counts on the GPU) and both ways in — Config.test() with device
+    scores, and the reference-shaped host-pointer calls — against the reference's own getBestThreshold /
+    test_triple_classification (oracle/_ref/Base.so) fed the same score arrays.  Thresholds bit-exact, counts equal."""
+    from oracle import harness
+    con = _config(small_ds, model, D)
+    P = make_params(model, con.entTotal, con.relTotal, D, seed=31)
+    con.set_parameters(P)
+    con.relThresh[:] = -7.0                            # relations without valid triples must keep their entry (Test.h:310)
+    con.test()
+    th_gpu, cnt_gpu, acc_gpu = con.relThresh.copy(), con.tc_counts.copy(), float(con.acc[0])
+    # the same score arrays, recomputed through the public predict call
+    vpos = con.test_step(con.valid_pos_h, con.valid_pos_t, con.valid_pos_r)
+    vneg = con.test_step(con.valid_neg_h, con.valid_neg_t, con.valid_neg_r)
+    tpos = con.test_step(con.test_pos_h, con.test_pos_t, con.test_pos_r)
+    tneg = con.test_step(con.test_neg_h, con.test_neg_t, con.test_neg_r)
+    # (a) host-pointer entry points of this library (what the reference's Config.py:503-513 calls)
+    th_host = np.full(con.relTotal, -7.0, np.float32)
+    con.ctx.call("okb_best_threshold", vp(th_host.ctypes.data), vp(vpos.ctypes.data), vp(vneg.ctypes.data))
+    assert np.array_equal(th_host.view(np.uint32), th_gpu.view(np.uint32))
+    cnt = np.zeros(4, np.int64); acc = np.zeros(1, np.float32)
+    con.ctx.call("okb_tc_eval", vp(th_host.ctypes.data), vp(tpos.ctypes.data), vp(tneg.ctypes.data), vp(cnt.ctypes.data), vp(acc.ctypes.data))
+    assert np.array_equal(cnt, cnt_gpu) and float(acc[0]) == acc_gpu
+    # (b) the C oracle and (c) the reference library itself
+    orc = harness.COracle(small_ds)
+    th_o = orc.best_threshold(vpos, vneg, np.full(con.relTotal, -7.0, np.float32))
+    assert np.array_equal(th_o.view(np.uint32), th_gpu.view(np.uint32))
+    acc_o, cnt_o = orc.tc_eval(th_o, tpos, tneg)
+    assert np.array_equal(cnt_o, cnt_gpu) and np.float32(acc_o) == np.float32(acc_gpu)
+    if os.path.exists(harness.REF_SO):
+        ref = harness.RefLib().init(small_ds, bern=0, W=2)
+        th_r = ref.best_threshold(vpos, vneg, np.full(con.relTotal, -7.0, np.float32))
+        assert np.array_equal(th_r.view(np.uint32), th_gpu.view(np.uint32))
+        assert np.float32(ref.tc_eval(th_r, tpos, tneg)) == np.float32(acc_gpu)
+    assert (th_gpu == -7.0).sum() == con.relTotal - len(set(int(x) for x in con.valid_pos_r))
+    # early-stop accuracy on the valid ranges: the device count kernel with on_valid = 1 vs a numpy recount
+    a = con.valid_accuracy()
+    vr = np.asarray(con.valid_pos_r)
+    ok = (vpos.reshape(-1) <= con.relThresh[vr]).sum() + (vneg.reshape(-1) > con.relThresh[vr]).sum()
+    assert np.float32(a) == np.float32(1.0 * ok / (2 * vr.size))
+
+
+def test_threshold_search_wide_score_range(built, small_ds):
+    """Threshold grids with thousands of points per relation and ties between candidates: the FIRST best threshold wins
+    (Test.h:333-339), on the device as in the reference."""
+    from oracle import harness
+    con = _config(small_ds, "TransE", 16)
+    con.set_parameters(make_params("TransE", con.entTotal, con.relTotal, 16, seed=3))
+    con.ctx.call("okb_tc_batch", 1, *[vp(getattr(con, "valid_" + n + "_addr")) for n in ("pos_h", "pos_t", "pos_r", "neg_h", "neg_t", "neg_r")])
+    rng = np.random.default_rng(5)
+    n = con.validTotal
+    orc = harness.COracle(small_ds)
+    for scale, quant in ((40.0, 0.0), (3.0, 0.25), (0.004, 0.0)):
+        pos = (rng.random(n) * scale).astype(np.float32)
+        neg = (rng.random(n) * scale + 0.3 * scale).astype(np.float32)
+        if quant:
+            pos, neg = np.round(pos / quant) * np.float32(quant), np.round(neg / quant) * np.float32(quant)
+        pos, neg = pos.astype(np.float32), neg.astype(np.float32)
+        th = np.zeros(con.relTotal, np.float32)
+        con.ctx.call("okb_best_threshold", vp(th.ctypes.data), vp(pos.ctypes.data), vp(neg.ctypes.data))
+        exp = orc.best_threshold(pos, neg, np.zeros(con.relTotal, np.float32))
+        assert np.array_equal(th.view(np.uint32), exp.view(np.uint32)), (scale, quant)

@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/../openkeonspark_b200"
 mkdir -p variants/obj_$1
-for f in abi.cpp loader.cpp sampler.cu radix.cu train.cu chunk.cu score.cu transr.cu transr_tc.cu; do
+for f in abi.cpp loader.cpp sampler.cu radix.cu train.cu chunk.cu score.cu tc.cu transr.cu transr_tc.cu; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-O2,-fno-fast-math,-ffp-contract=off -x cu -rdc=false $2 -c csrc/$f -o variants/obj_$1/$f.o &
 done
 wait
