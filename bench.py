@@ -554,9 +554,9 @@ def main():
         Dd = cfg["dim"]
         ce = 2 if cfg["model"] == "TransD" else 1
         return {"queries_per_s": qps, "queries": 2 * nq, "ms": ms,
-                "roofline": {"bound": "fp32_alu", "achieved": qps * 2.0 * gg.E * Dd / 1e12, "peak": FP32_ALU_TFADD, "unit": "TFADD/s",
-                             "frac": qps * 2.0 * gg.E * Dd / 1e12 / FP32_ALU_TFADD,
-                             "hbm_canonical_frac": qps * 4.0 * Dd * gg.E * ce / 1e9 / peak,
+                "roofline": {"bound": "fp32_alu", "achieved": qps * 2.0 * gg.E * Dd / 1e12 / world, "peak": FP32_ALU_TFADD, "unit": "TFADD/s per GPU",
+                             "frac": qps * 2.0 * gg.E * Dd / 1e12 / FP32_ALU_TFADD / world,
+                             "hbm_canonical_frac": qps * 4.0 * Dd * gg.E * ce / 1e9 / peak / world,
                              "what": "2 FADD per (query, candidate, dim) against 148 SM x 128 lanes x 1.965 GHz (derived peak); "
                                      "hbm_canonical_frac = queries/s x 4*D*E*c_e bytes (SURVEY 8d: each query re-streams the table) / HBM peak — "
                                      "above 1 because one table pass serves a whole batch of queries"},

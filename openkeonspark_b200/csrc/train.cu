@@ -966,6 +966,8 @@ struct DpTab {
     i64 x_off, stage_off;      // byte offsets in an arena: the table / this table's staging slab
     i64 vec_end;               // cumulative vector count over the OWNED rows of the table list
     i32 D, cols, part, row_lo, own_max;
+    i32 blk_end;               // cumulative count of 256-vector tiles (one CTA each)
+    unsigned magic, shift;     // owned-row index = vector / (D / VW) as a multiply-high (see DenseTab)
 };
 struct DpOwn {
     okb_hyper hp;
@@ -977,10 +979,30 @@ struct DpOwn {
     float *loss_out;
     float w;
 };
+// One 256-vector tile of ONE table's owned rows per CTA (block-uniform table, multiply-high row split — the lean form of
+// adam_tile_kernel): x / m / v of the tile are requested BEFORE the wait for this rank's push kernel and for the peers'
+// "stage ready" flags — none of them is written by anyone but this owner — so their HBM latency runs under the flag wait;
+// the world's partial rows are then loaded four at a time and added in rank order.
 template <int VW>
 __global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
     typedef typename VecT<VW>::T V;
     pdl_launch_dependents();
+    const i32 bid = (i32)blockIdx.x;
+    int t = 0;
+    while (bid >= d.tab[t].blk_end) t++;                   // block-uniform
+    const DpTab &T = d.tab[t];
+    const unsigned nvec = (unsigned)(T.vec_end - (t ? d.tab[t - 1].vec_end : 0));
+    const unsigned lv = ((unsigned)bid - (unsigned)(t ? d.tab[t - 1].blk_end : 0)) * 256u + threadIdx.x;
+    const bool live = lv < nvec;
+    const unsigned vpr = (unsigned)T.D / VW;
+    const unsigned rl = T.magic ? (__umulhi(lv, T.magic) >> T.shift) : (lv >> T.shift), col = (lv - rl * vpr) * VW;
+    const i64 e = ((i64)T.row_lo + rl) * T.D + col;         // element index inside the full table
+    const char *own = d.arena[d.rank];
+    V xv, mv, vv;
+    if (live) {
+        xv = *reinterpret_cast<const V *>(own + T.x_off + e * 4);
+        if (d.adam) { mv = *reinterpret_cast<const V *>(T.m + e); vv = *reinterpret_cast<const V *>(T.v + e); }
+    }
     pdl_wait();                                            // this rank's reduce+push kernel is complete: announce it
     dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, blockIdx.x == 0);
     if (blockIdx.x == 0 && threadIdx.x == 0 && d.loss_out) {   // mean hinge over the GLOBAL batch, rank order
@@ -989,51 +1011,38 @@ __global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
         for (int q = 0; q < d.world; q++) tot += lp[q];
         d.loss_out[0] = tot * d.w;
     }
-    const i64 total = d.tab[d.ntab - 1].vec_end;
+    if (!live) return;
     const float b1 = d.hp.beta1, b2 = d.hp.beta2, lr = d.hp.lr, eps = d.hp.eps;
-    const char *own = d.arena[d.rank];
-    for (i64 v = (i64)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (i64)gridDim.x * blockDim.x) {
-        int t = 0;
-        while (v >= d.tab[t].vec_end) t++;
-        const DpTab &T = d.tab[t];
-        const unsigned lv = (unsigned)(v - (t ? d.tab[t - 1].vec_end : 0));
-        const unsigned vpr = (unsigned)T.D / VW;
-        const unsigned rl = lv / vpr, col = (lv - rl * vpr) * VW;
-        const i64 e = ((i64)T.row_lo + rl) * T.D + col;     // element index inside the full table
-        const float *st = (const float *)(own + T.stage_off) + (i64)rl * T.cols + T.part * T.D + col;
-        V xv = *reinterpret_cast<const V *>(own + T.x_off + e * 4);
-        V mv, vv;
-        if (d.adam) { mv = *reinterpret_cast<const V *>(T.m + e); vv = *reinterpret_cast<const V *>(T.v + e); }
-        float g[VW];
+    const float *st = (const float *)(own + T.stage_off) + (i64)rl * T.cols + T.part * T.D + col;
+    float g[VW];
 #pragma unroll
-        for (int q = 0; q < VW; q++) g[q] = 0.f;
-        bool any = false;
-        for (int p0 = 0; p0 < d.world; p0 += 4) {          // partial rows in rank order; four loads in flight at a time
-            V gp[4];
+    for (int q = 0; q < VW; q++) g[q] = 0.f;
+    bool any = false;
+    for (int p0 = 0; p0 < d.world; p0 += 4) {              // partial rows in rank order; four loads in flight at a time
+        V gp[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (p0 + u < d.world) gp[u] = __ldcg(reinterpret_cast<const V *>(st + (i64)(p0 + u) * T.own_max * T.cols));
+        for (int u = 0; u < 4; u++)
+            if (p0 + u < d.world) gp[u] = __ldcg(reinterpret_cast<const V *>(st + (i64)(p0 + u) * T.own_max * T.cols));
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (p0 + u >= d.world) break;
-                const float *pg = reinterpret_cast<const float *>(&gp[u]);
+        for (int u = 0; u < 4; u++) {
+            if (p0 + u >= d.world) break;
+            const float *pg = reinterpret_cast<const float *>(&gp[u]);
 #pragma unroll
-                for (int q = 0; q < VW; q++) { g[q] += pg[q]; any |= pg[q] != 0.f; }
-            }
+            for (int q = 0; q < VW; q++) { g[q] += pg[q]; any |= pg[q] != 0.f; }
         }
-        float *xs = reinterpret_cast<float *>(&xv);
-        if (d.adam) {
-            float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
-#pragma unroll
-            for (int q = 0; q < VW; q++) adam_elem(xs[q], ms[q], vs[q], g[q], b1, b2, 1.f - b1, 1.f - b2, lr, eps);
-            *reinterpret_cast<V *>(T.m + e) = mv; *reinterpret_cast<V *>(T.v + e) = vv;
-        } else {
-            if (!any) continue;                            // SGD leaves rows without gradient untouched: nothing to publish
-#pragma unroll
-            for (int q = 0; q < VW; q++) xs[q] -= lr * g[q];
-        }
-        for (int p = 0; p < d.world; p++) *reinterpret_cast<V *>(d.arena[p] + T.x_off + e * 4) = xv;
     }
+    float *xs = reinterpret_cast<float *>(&xv);
+    if (d.adam) {
+        float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+        for (int q = 0; q < VW; q++) adam_elem(xs[q], ms[q], vs[q], g[q], b1, b2, 1.f - b1, 1.f - b2, lr, eps);
+        *reinterpret_cast<V *>(T.m + e) = mv; *reinterpret_cast<V *>(T.v + e) = vv;
+    } else {
+        if (!any) return;                                  // SGD leaves rows without gradient untouched: nothing to publish
+#pragma unroll
+        for (int q = 0; q < VW; q++) xs[q] -= lr * g[q];
+    }
+    for (int p = 0; p < d.world; p++) *reinterpret_cast<V *>(d.arena[p] + T.x_off + e * 4) = xv;
 }
 
 // End of a library call: publish "my owner-update kernels up to `epoch` are complete" without waiting for the next step's
@@ -1372,21 +1381,30 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
             o.w = 1.0f / (float)(c->B * (c->K + c->KR));
             o.ntab = 0;
             i64 acc = 0;
+            i32 oblk = 0;
             auto add = [&](i64 x_off, float *mm, float *vv, bool is_ent, int part) {
                 if (x_off < 0) return;
                 const int D = is_ent ? m->ent_dim : m->rel_dim;
                 const i64 lo = is_ent ? d.ent_lo[P.rank] : d.rel_lo[P.rank], hi = is_ent ? d.ent_lo[P.rank + 1] : d.rel_lo[P.rank + 1];
                 acc += (hi - lo) * D / vw;
+                oblk += (i32)(((hi - lo) * D / vw + 255) / 256);
                 DpTab T;
                 T.m = mm; T.v = vv; T.x_off = x_off; T.stage_off = is_ent ? P.off_stage_ent : P.off_stage_rel; T.vec_end = acc;
                 T.D = D; T.cols = is_ent ? a.ce : a.cr; T.part = part; T.row_lo = (i32)lo; T.own_max = (i32)(is_ent ? own_e : own_r);
+                T.blk_end = oblk;
+                const unsigned vpr = (unsigned)(D / vw);
+                unsigned sh = 0;
+                while ((2u << sh) <= vpr) sh++;
+                if ((1u << sh) == vpr) { T.magic = 0; T.shift = sh; }
+                else { T.magic = (unsigned)((((unsigned long long)1 << (32 + sh)) + vpr - 1) / vpr); T.shift = sh; }
                 o.tab[o.ntab++] = T;
             };
             add(P.off_ent, m->m_ent, m->v_ent, true, 0);
             if (m->model == OKB_TRANSD) add(P.off_ent_aux, m->m_ent_aux, m->v_ent_aux, true, 1);
             add(P.off_rel, m->m_rel, m->v_rel, false, 0);
             if (m->model != OKB_TRANSE) add(P.off_rel_aux, m->m_rel_aux, m->v_rel_aux, false, 1);
-            const unsigned og = (unsigned)std::max<i64>(1, std::min<i64>((acc + 255) / 256, (i64)okb_sms(c) * 8));
+            const unsigned og = (unsigned)std::max<i32>(1, oblk);
+            if (oblk == 0) { o.tab[0].blk_end = 1; }          // a rank that owns no rows still takes part in the flag exchange
             cudaLaunchConfig_t oc = {};
             oc.gridDim = dim3(og); oc.blockDim = dim3(256); oc.stream = s; oc.attrs = pat; oc.numAttrs = c->pdl ? 1 : 0;
             if (vw == 4) cudaLaunchKernelEx(&oc, dp_owner_kernel<4>, o);

@@ -256,6 +256,7 @@ def test_triple_classification_device_kernels_match_reference(built, small_ds, m
         assert np.float32(ref.tc_eval(th_r, tpos, tneg)) == np.float32(acc_gpu)
     assert (th_gpu == -7.0).sum() == con.relTotal - len(set(int(x) for x in con.valid_pos_r))
     # early-stop accuracy on the valid ranges: the device count kernel with on_valid = 1 vs a numpy recount
+    con._valid_batch_ready = True                      # keep the valid negatives drawn above (a fresh draw would move the thresholds)
     a = con.valid_accuracy()
     vr = np.asarray(con.valid_pos_r)
     ok = (vpos.reshape(-1) <= con.relThresh[vr]).sum() + (vneg.reshape(-1) > con.relThresh[vr]).sum()
