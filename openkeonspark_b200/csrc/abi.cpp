@@ -77,6 +77,7 @@ int okb_set_flag(okb_ctx *c, int flag, INT value) {
     if (flag == OKB_FLAG_PLAN_MULTI) { c->plan_multi = value != 0; return 0; }
     if (flag == OKB_FLAG_DP_PULL) { c->dp_pull = value != 0; return 0; }
     if (flag == OKB_FLAG_CHUNK_KERNEL) { c->chunk_kernel = value != 0; return 0; }
+    if (flag == OKB_FLAG_TRANSR_FUSED) { c->transr_fused = value != 0; return 0; }
     if (flag == OKB_FLAG_ADAM_VPT) { if (value < 1 || value > 4) OKB_FAIL(c, OKB_ERR_ARG, "vectors per thread: 1..4"); c->adam_vpt = (int)value; return 0; }
     OKB_FAIL(c, OKB_ERR_ARG, "unknown flag");
 }

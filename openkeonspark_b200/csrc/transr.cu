@@ -284,6 +284,346 @@ __global__ void __launch_bounds__(TR_THREADS) transr_bucket_kernel(TrArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ persistent, fused form
+// The per-relation kernel above spends its 119 us (FB15K shape, B = 4,831) waiting: every CTA stages 40 KB of M_r, runs
+// three small contractions and writes 40 KB of dM_r back, all serialised, and a second kernel re-reads dM_r and M_r to
+// apply the update — 260 MB of HBM traffic for 104 MB of algorithmic bytes.  Here ONE CTA per SM stays resident and walks
+// its share of the relations:
+//   * M_r of the NEXT touched relation is already in flight (one 40 KB bulk-async / TMA copy on an mbarrier into the
+//     other half of a double buffer) while the current relation is computed;
+//   * 512 threads per relation (the matrix-gradient tiles stay in registers: 2 x 16 per thread);
+//   * the relation's update is applied on the spot — M_r - lr dM_r (or TF1 Adam) straight from the staged copy and the
+//     register tiles to global memory, rel_embeddings[r] likewise — no dM round trip, no second kernel.  Only this CTA
+//     ever touches relation r during the step (negatives share the positive's relation, TransR.py:57-60), so
+//     overwriting it at the end of the relation's pass is safe.
+// TF1 Adam moves untouched relations too (dense decay): the owning CTA streams those after its touched ones.
+#define TRF_THREADS 512
+#define TRF_MAXT 2             // dM tiles (4x4) per thread: De*Dr <= 16 * 512 * 2
+
+struct TrFuse {
+    okb_hyper hp;
+    const unsigned *bad;      // "bad id" flag of the host-batch path: set -> leave everything alone
+    i32 adam, r_lo, r_hi;
+};
+
+__device__ __forceinline__ unsigned trf_smem(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(TRF_THREADS, 1) transr_fused_kernel(TrArgs a, TrFuse f) {
+    extern __shared__ __align__(128) float sm[];
+    const int De = a.m.ent_dim, Dr = a.m.rel_dim, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int De4 = De >> 2, Dr4 = Dr >> 2, per = 2 + a.k, MS = De * Dr;
+    if (f.bad && *(const volatile unsigned *)f.bad) return;
+    float *Mb0 = sm, *Mb1 = sm + MS;                   // double-buffered M_r
+    float *A = Mb1 + MS;                               // [TR_ROWS][De]
+    float *P = A + TR_ROWS * De;                       // [TR_ROWS][Dr]  projected, then normalised
+    float *G = P + TR_ROWS * Dr;                       // [TR_ROWS][Dr]  gradient w.r.t. the projected rows
+    float *Rg = G + TR_ROWS * Dr;                      // [CH][Dr]       per-positive gradient w.r.t. r_hat
+    float *rhat = Rg + a.CH * Dr;                      // [Dr]
+    float *rsum = rhat + Dr;                           // [Dr]
+    float *inv = rsum + Dr;                            // [TR_ROWS]
+    i32 *proj = (i32 *)(inv + TR_ROWS);                // [TR_ROWS]
+    i32 *rowid = proj + TR_ROWS;                       // [TR_ROWS] entity id of each gathered row
+    i32 *posb = rowid + TR_ROWS;                       // [CH] batch index of each positive in the chunk
+    i32 *side = posb + a.CH;                           // [CH][k]  0: head replaced, 1: tail replaced, 2: same triple
+    __shared__ __align__(8) unsigned long long bar[2];
+    __shared__ float s_invr;
+    __shared__ int s_projr;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(trf_smem(bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(trf_smem(bar + 1)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const i32 stride = (i32)gridDim.x;
+    auto next_touched = [&](i32 r) { while (r < f.r_hi && __ldg(&a.rowhead[a.E + r].x) < 0) r += stride; return r; };
+    auto issue = [&](i32 r, int b) {                   // thread 0: 40 KB of M_r into half b of the double buffer
+        const unsigned bytes = (unsigned)MS * 4u, br = trf_smem(bar + b);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(br), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(trf_smem(b ? Mb1 : Mb0)),
+                     "l"(a.m.rel_aux + (i64)r * MS), "r"(bytes), "r"(br) : "memory");
+    };
+    const float b1 = f.hp.beta1, b2 = f.hp.beta2, lr = f.hp.lr, eps = f.hp.eps, c1 = 1.f - b1, c2 = 1.f - b2;
+    const int ntM = De4 * Dr4;
+    i32 cur = next_touched(f.r_lo + (i32)blockIdx.x);
+    int buf = 0;
+    unsigned phase[2] = {0u, 0u};
+    if (cur < f.r_hi && tid == 0) issue(cur, 0);
+    while (cur < f.r_hi) {
+        const i32 r = cur, nxt = next_touched(cur + stride);
+        if (tid == 0) {
+            if (nxt < f.r_hi) issue(nxt, buf ^ 1);     // the other half was released by the barrier that ended the previous pass
+            if (f.adam) {                              // this relation's Adam slots are needed at the end of the pass: start them towards L2
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.m.m_rel_aux + (i64)r * MS), "r"((unsigned)MS * 4u) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.m.v_rel_aux + (i64)r * MS), "r"((unsigned)MS * 4u) : "memory");
+            }
+        }
+        const int4 seg = a.rowhead[a.E + r];
+        float *Msh = buf ? Mb1 : Mb0;
+        if (warp == 0) {                                   // r_hat = l2n(rel_embeddings[r])
+            float ss = 0.f;
+            for (int k = lane; k < Dr; k += 32) { const float v = a.m.rel[(i64)r * Dr + k]; ss += v * v; }
+            ss = wsum_t(ss);
+            const float iv = rsqrtf(fmaxf(ss, EPS_NORM));
+            for (int k = lane; k < Dr; k += 32) rhat[k] = a.m.rel[(i64)r * Dr + k] * iv;
+            if (lane == 0) { s_invr = iv; s_projr = ss > EPS_NORM; }
+        }
+        float accM[TRF_MAXT][16];
+#pragma unroll
+        for (int q = 0; q < TRF_MAXT; q++)
+#pragma unroll
+            for (int e = 0; e < 16; e++) accM[q][e] = 0.f;
+        float racc = 0.f;                                  // thread k < Dr: sum over positives of d loss / d r_hat[k]
+        {   // M_r has landed?
+            unsigned done = 0;
+            const unsigned br = trf_smem(bar + buf);
+            while (!done)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(br), "r"(phase[buf]) : "memory");
+            phase[buf] ^= 1u;
+        }
+        for (i32 base = seg.x; base < seg.y; base += a.CH) {
+            const int np = min(a.CH, seg.y - base);         // positives in this chunk
+            const int rows = np * per, rows4 = (rows + 3) & ~3;
+            __syncthreads();
+            if (tid < np) {
+                const i32 b = a.perm[base + tid] - a.nes;   // relation slots are numbered nes + b  (NR == 1)
+                posb[tid] = b;
+                const i32 ph = a.bh[b], pt = a.bt[b];
+                rowid[tid * per] = ph; rowid[tid * per + 1] = pt;
+                for (int m = 0; m < a.k; m++) {
+                    const i32 at = b + (m + 1) * a.B;
+                    const i32 nh = a.bh[at], nt = a.bt[at];
+                    const int sd = nh != ph ? 0 : (nt != pt ? 1 : 2);
+                    side[tid * a.k + m] = sd;
+                    rowid[tid * per + 2 + m] = sd == 0 ? nh : (sd == 1 ? nt : ph);
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < rows4 * De4; i += TRF_THREADS) {            // gather the entity rows (128-bit)
+                const int row = i / De4, q = i - row * De4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row < rows) v = __ldg(reinterpret_cast<const float4 *>(a.m.ent + (i64)rowid[row] * De) + q);
+                reinterpret_cast<float4 *>(A)[row * De4 + q] = v;
+            }
+            __syncthreads();
+            // ---- P = A . M   (4x4 register tiles)
+            for (int t = tid; t < (rows4 >> 2) * Dr4; t += TRF_THREADS) {
+                const int tr = t / Dr4, tc = t - tr * Dr4;
+                float acc[4][4] = {};
+                for (int i = 0; i < De; i += 4) {
+                    float4 av[4], mv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        av[q] = reinterpret_cast<const float4 *>(A)[(tr * 4 + q) * De4 + (i >> 2)];
+                        mv[q] = reinterpret_cast<const float4 *>(Msh)[(i + q) * Dr4 + tc];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        acc[q][0] += av[q].x * mv[0].x + av[q].y * mv[1].x + av[q].z * mv[2].x + av[q].w * mv[3].x;
+                        acc[q][1] += av[q].x * mv[0].y + av[q].y * mv[1].y + av[q].z * mv[2].y + av[q].w * mv[3].y;
+                        acc[q][2] += av[q].x * mv[0].z + av[q].y * mv[1].z + av[q].z * mv[2].z + av[q].w * mv[3].z;
+                        acc[q][3] += av[q].x * mv[0].w + av[q].y * mv[1].w + av[q].z * mv[2].w + av[q].w * mv[3].w;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    reinterpret_cast<float4 *>(P)[(tr * 4 + q) * Dr4 + tc] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+            }
+            __syncthreads();
+            // ---- normalise the projected rows (tf.nn.l2_normalize, TransR.py:19-23)
+            for (int row = warp; row < rows; row += TRF_THREADS / 32) {
+                float ss = 0.f;
+                for (int k = lane; k < Dr; k += 32) { const float v = P[row * Dr + k]; ss += v * v; }
+                ss = wsum_t(ss);
+                const float iv = rsqrtf(fmaxf(ss, EPS_NORM));
+                for (int k = lane; k < Dr; k += 32) P[row * Dr + k] *= iv;
+                if (lane == 0) { inv[row] = iv; proj[row] = ss > EPS_NORM; }
+            }
+            __syncthreads();
+            // ---- scores, hinge and the gradient w.r.t. the projected rows: one warp per positive
+            for (int c = warp; c < np; c += TRF_THREADS / 32) {
+                const int r0 = c * per;
+                const float *Ph = P + r0 * Dr, *Pt = P + (r0 + 1) * Dr;
+                float gh[4] = {0.f, 0.f, 0.f, 0.f}, gt[4] = {0.f, 0.f, 0.f, 0.f}, gr[4] = {0.f, 0.f, 0.f, 0.f}, gp[4];
+                float sp = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = lane + 32 * i;
+                    const float u = k < Dr ? (Ph[k] + rhat[k]) - Pt[k] : 0.f;
+                    sp += fabsf(u);
+                    gp[i] = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+                }
+                sp = wsum_t(sp);
+                auto backward = [&](const float *Hrow, const float *Trow, int hrow_i, int trow_i, const float *g, float coef,
+                                    float *dh, float *dt) {
+                    float d1 = 0.f, d2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int k = lane + 32 * i;
+                        if (k < Dr) { d1 += g[i] * Hrow[k]; d2 += g[i] * Trow[k]; }
+                    }
+                    d1 = wsum_t(d1); d2 = wsum_t(d2);
+                    if (!proj[hrow_i]) d1 = 0.f;
+                    if (!proj[trow_i]) d2 = 0.f;
+                    const float ih = inv[hrow_i] * coef, it = inv[trow_i] * coef;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int k = lane + 32 * i;
+                        if (k < Dr) {
+                            dh[i] += ih * (g[i] - Hrow[k] * d1);
+                            dt[i] -= it * (g[i] - Trow[k] * d2);
+                            gr[i] += coef * g[i];
+                        }
+                    }
+                };
+                float hinge = 0.f;
+                int active = 0;
+                for (int m = 0; m < a.k; m++) {
+                    const int sd = side[c * a.k + m], nrow = r0 + 2 + m;
+                    const float *Pn = P + nrow * Dr;
+                    const float *Hrow = sd == 0 ? Pn : Ph, *Trow = sd == 1 ? Pn : Pt;
+                    float gn[4], gnew[4] = {0.f, 0.f, 0.f, 0.f};
+                    float sn = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int k = lane + 32 * i;
+                        const float u = k < Dr ? (Hrow[k] + rhat[k]) - Trow[k] : 0.f;
+                        sn += fabsf(u);
+                        gn[i] = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+                    }
+                    sn = wsum_t(sn);
+                    const float x = sp - sn + a.margin;
+                    if (x >= 0.f) {
+                        hinge += x; active++;
+                        if (sd == 0) backward(Hrow, Trow, nrow, r0 + 1, gn, -a.w, gnew, gt);
+                        else if (sd == 1) backward(Hrow, Trow, r0, nrow, gn, -a.w, gh, gnew);
+                        else backward(Hrow, Trow, r0, r0 + 1, gn, -a.w, gh, gt);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { const int k = lane + 32 * i; if (k < Dr) G[nrow * Dr + k] = gnew[i]; }
+                }
+                if (active) backward(Ph, Pt, r0, r0 + 1, gp, a.w * (float)active, gh, gt);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int k = lane + 32 * i;
+                    if (k < Dr) { G[r0 * Dr + k] = gh[i]; G[(r0 + 1) * Dr + k] = gt[i]; Rg[c * Dr + k] = gr[i]; }
+                }
+                if (lane == 0) a.loss_terms[posb[c]] = hinge;
+            }
+            for (int i = tid + rows * Dr; i < rows4 * Dr; i += TRF_THREADS) G[i] = 0.f;      // padding rows
+            __syncthreads();
+            // ---- dA = G . M^T  -> entity gradient rows of this chunk
+            for (int t = tid; t < (rows4 >> 2) * De4; t += TRF_THREADS) {
+                const int tr = t / De4, ti = t - tr * De4;       // this thread: rows 4tr..4tr+3, columns ti + q*De4
+                float acc[4][4] = {};
+                for (int k = 0; k < Dr4; k++) {
+                    float4 gv[4], mv[4];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        gv[q] = reinterpret_cast<const float4 *>(G)[(tr * 4 + q) * Dr4 + k];
+                        mv[q] = reinterpret_cast<const float4 *>(Msh)[(ti + q * De4) * Dr4 + k];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; q++)
+#pragma unroll
+                        for (int e = 0; e < 4; e++) acc[q][e] += dot4(gv[q], mv[e]);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int row = tr * 4 + q;
+                    if (row < rows) {
+                        const int c = row / per, j = row - c * per;
+                        float *dst = a.gent + ((i64)posb[c] * a.NE + j) * De;
+#pragma unroll
+                        for (int e = 0; e < 4; e++) dst[ti + e * De4] = acc[q][e];
+                    }
+                }
+            }
+            // ---- dM += A^T . G
+#pragma unroll
+            for (int q = 0; q < TRF_MAXT; q++) {
+                const int t = tid + q * TRF_THREADS;
+                if (t < ntM) {
+                    const int ti = t / Dr4, tk = t - ti * Dr4;
+                    for (int row = 0; row < rows; row++) {
+                        const float4 av = reinterpret_cast<const float4 *>(A)[row * De4 + ti];
+                        const float4 gv = reinterpret_cast<const float4 *>(G)[row * Dr4 + tk];
+                        const float as[4] = {av.x, av.y, av.z, av.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++)
+#pragma unroll
+                            for (int f2 = 0; f2 < 4; f2++) accM[q][e * 4 + f2] += as[e] * gs[f2];
+                    }
+                }
+            }
+            if (tid < Dr) for (int c = 0; c < np; c++) racc += Rg[c * Dr + tid];       // fixed order over positives
+        }
+        // ---- this relation's update, in place: rel_embeddings[r] and M_r
+        if (tid < Dr) rsum[tid] = racc;
+        __syncthreads();
+        if (tid < Dr) {
+            float d = 0.f;
+            for (int k = 0; k < Dr; k++) d += rsum[k] * rhat[k];
+            const float g = s_invr * (rsum[tid] - (s_projr ? rhat[tid] * d : 0.f));
+            const i64 off = (i64)r * Dr + tid;
+            float x = a.m.rel[off];
+            if (f.adam) {
+                float mm = a.m.m_rel[off], vv = a.m.v_rel[off];
+                adam_elem(x, mm, vv, g, b1, b2, c1, c2, lr, eps);
+                a.m.m_rel[off] = mm; a.m.v_rel[off] = vv;
+            } else x -= lr * g;
+            a.m.rel[off] = x;
+        }
+        float *Mg = a.m.rel_aux + (i64)r * MS;
+#pragma unroll
+        for (int q = 0; q < TRF_MAXT; q++) {
+            const int t = tid + q * TRF_THREADS;
+            if (t < ntM) {
+                const int ti = t / Dr4, tk = t - ti * Dr4;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int idx = (ti * 4 + e) * Dr + tk * 4;
+                    float4 xv = *reinterpret_cast<const float4 *>(Msh + idx);
+                    float *xs = reinterpret_cast<float *>(&xv);
+                    if (f.adam) {
+                        float4 mv = *reinterpret_cast<const float4 *>(a.m.m_rel_aux + (i64)r * MS + idx), vv = *reinterpret_cast<const float4 *>(a.m.v_rel_aux + (i64)r * MS + idx);
+                        float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+                        for (int f2 = 0; f2 < 4; f2++) adam_elem(xs[f2], ms[f2], vs[f2], accM[q][e * 4 + f2], b1, b2, c1, c2, lr, eps);
+                        *reinterpret_cast<float4 *>(a.m.m_rel_aux + (i64)r * MS + idx) = mv;
+                        *reinterpret_cast<float4 *>(a.m.v_rel_aux + (i64)r * MS + idx) = vv;
+                    } else {
+#pragma unroll
+                        for (int f2 = 0; f2 < 4; f2++) xs[f2] -= lr * accM[q][e * 4 + f2];
+                    }
+                    *reinterpret_cast<float4 *>(Mg + idx) = xv;
+                }
+            }
+        }
+        __syncthreads();                                   // every read of this half of the double buffer is done
+        cur = nxt; buf ^= 1;
+    }
+    // ---- TF1 Adam: the dense decay also moves the relations this batch did not touch (g = 0)
+    if (f.adam) {
+        const int c4 = (Dr + MS) >> 2;
+        for (i32 r = f.r_lo + (i32)blockIdx.x; r < f.r_hi; r += stride) {
+            if (a.rowhead[a.E + r].x >= 0) continue;
+            for (int v = tid; v < c4; v += TRF_THREADS) {
+                const int e = v * 4;
+                const bool is_rel = e < Dr;
+                const i64 off = is_rel ? (i64)r * Dr + e : (i64)r * MS + (e - Dr);
+                float *x = (is_rel ? a.m.rel : a.m.rel_aux) + off;
+                float *mp = (is_rel ? a.m.m_rel : a.m.m_rel_aux) + off, *vp = (is_rel ? a.m.v_rel : a.m.v_rel_aux) + off;
+                float4 xv = *reinterpret_cast<float4 *>(x), mv = *reinterpret_cast<float4 *>(mp), vv = *reinterpret_cast<float4 *>(vp);
+                float *xs = reinterpret_cast<float *>(&xv), *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+                for (int q = 0; q < 4; q++) adam_elem(xs[q], ms[q], vs[q], 0.f, b1, b2, c1, c2, lr, eps);
+                *reinterpret_cast<float4 *>(mp) = mv; *reinterpret_cast<float4 *>(vp) = vv; *reinterpret_cast<float4 *>(x) = xv;
+            }
+        }
+    }
+}
+
 // rel_embeddings and transfer_matrix rows: gradients arrive already reduced per relation.
 //   SGD : touched relations only, x -= lr g.      Adam: every relation (TF1 dense decay), g = 0 if untouched.
 struct TrUpdArgs {
@@ -355,6 +695,28 @@ int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, 
     const i64 r_lo = c->tr_hi > c->tr_lo ? c->tr_lo : 0, r_hi = c->tr_hi > c->tr_lo ? c->tr_hi : c->R;
     a.r_lo = (i32)r_lo;
     const int De = m->ent_dim, Dr = m->rel_dim;
+    if (c->transr_fused && loss_terms) {
+        // persistent form with the relation-side update applied in place (transr_fused_kernel); grel is not used
+        const size_t fsmem = sizeof(float) * (2 * (size_t)De * Dr + (size_t)TR_ROWS * De + 2 * (size_t)TR_ROWS * Dr + (size_t)a.CH * Dr + 2 * Dr + TR_ROWS) +
+                             sizeof(i32) * (2 * TR_ROWS + a.CH + (size_t)a.CH * a.k) + 128;
+        const bool adam = m->optimizer == OKB_ADAM;
+        if (fsmem <= 224 * 1024 && (De / 4) * (Dr / 4) <= TRF_MAXT * TRF_THREADS && (!adam || (m->m_rel && m->v_rel && m->m_rel_aux && m->v_rel_aux))) {
+            TrFuse f;
+            f.hp = *hp; f.adam = adam ? 1 : 0; f.r_lo = (i32)r_lo; f.r_hi = (i32)r_hi;
+            f.bad = c->batch_from_host && c->flags.p ? c->flags.as<unsigned>() + OKB_FLAGS_BAD : nullptr;
+            OKB_CUDA(c, okb_smem_optin(c, transr_fused_kernel, fsmem));
+            const unsigned grid = (unsigned)std::max<i64>(1, std::min<i64>(okb_sms(c), r_hi - r_lo));
+            {
+                ProfScope ps(c, PROF_GRAD, s);
+                transr_fused_kernel<<<grid, TRF_THREADS, fsmem, s>>>(a, f);
+            }
+            OKB_LAUNCHED(1);
+            OKB_CUDA(c, cudaGetLastError());
+            c->transr_rel_done = true;                     // okb_update: the relation rows of this step are already updated
+            return 0;
+        }
+    }
+    c->transr_rel_done = false;
     const size_t smem = sizeof(float) * ((size_t)De * Dr + (size_t)TR_ROWS * De + 2 * (size_t)TR_ROWS * Dr + (size_t)a.CH * Dr + 2 * Dr + TR_ROWS) +
                         sizeof(i32) * (2 * TR_ROWS + a.CH + (size_t)a.CH * a.k) + 64;
     if (smem > 226 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "TransR dimensions too large for shared memory");
@@ -370,6 +732,7 @@ int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, 
 
 int okb_transr_launch_rel_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const int4 *rowhead, const float *grel,
                                  cudaStream_t s) {
+    if (c->transr_rel_done) { c->transr_rel_done = false; return 0; }      // applied in place by transr_fused_kernel
     TrUpdArgs a;
     a.m = *m; a.hp = *hp; a.rowhead = rowhead; a.grel = grel; a.E = (i32)c->E; a.R = (i32)c->R;
     a.adam = m->optimizer == OKB_ADAM;

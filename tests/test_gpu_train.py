@@ -332,3 +332,28 @@ def test_adam_vectors_per_thread_bit_identical(built, small_ds, wide_ds, model, 
             assert np.array_equal(o[1][name], outs[0][1][name]), name
         for name in outs[0][2]:
             assert np.array_equal(o[2][name], outs[0][2][name]), name
+
+
+@pytest.mark.parametrize("opt", ["SGD", "Adam"])
+@pytest.mark.parametrize("D,Dr,k,ds", [(100, 100, 1, "small"), (40, 24, 3, "small"), (64, 128, 2, "wide"), (20, 20, 1, "wide")])
+def test_transr_fused_kernel_equals_two_kernel_form(built, small_ds, wide_ds, opt, D, Dr, k, ds):
+    """OKB_FLAG_TRANSR_FUSED (default): persistent kernel, M_r double-buffered by bulk-async copies, relation-side update
+    applied in place — against the round-1 form (one CTA per relation + a separate relation-update kernel through the
+    per-relation gradient rows).  Same contractions in the same order: losses equal, tables within 1e-7 (the update is the
+    same expression compiled in two kernels)."""
+    path = {"small": small_ds, "wide": wide_ds}[ds]
+    outs = []
+    for fused in (0, 1):
+        con = _config(path, "TransR", D, k, 0, opt, Dr=Dr, nbatches=5)
+        con.ctx.call("okb_set_flag", 12, fused)
+        con.set_parameters(make_params("TransR", con.entTotal, con.relTotal, D, seed=9, Dr=Dr))
+        losses = [float(x) for x in con.train_chunk_device(4, 0).cpu().numpy()]
+        con.sampling_device()
+        losses.append(float(con.train_step_device(0).item()))
+        slots = {} if con._adam is None else {kk: v.cpu().numpy() for kk, v in con._adam.items() if hasattr(v, "cpu")}
+        outs.append((losses, con.get_parameters(), slots))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-6, atol=0), (outs[0][0], outs[1][0])
+    for name in outs[0][1]:
+        assert np.allclose(outs[0][1][name], outs[1][1][name], rtol=0, atol=(1e-7 if opt == "SGD" else 2e-2 * 0 + 1e-6)), name
+    for name in outs[0][2]:
+        assert np.allclose(outs[0][2][name], outs[1][2][name], rtol=1e-5, atol=1e-9), name
