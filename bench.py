@@ -566,8 +566,23 @@ def main():
     lp = None
     try:
         lp = measure_lp(con, HEAD, g, min(args.lp_queries, con.testTotal))
+        if world == 1:      # the same evaluation in the regime of a TRAINED model: few candidates beat the target
+            nq_t = min(args.lp_queries, con.testTotal)
+            g_t = planted_test_set(con, HEAD, g, nq_t)
+            con_t, _ = make_con(HEAD, g_t, 1, 0)
+            r_t = measure_lp(con_t, HEAD, g_t, nq_t)
+            rec = con_t.link_prediction_records(0, min(nq_t, 4096)).cpu().numpy()
+            lp["trained_like"] = {"queries_per_s": r_t["queries_per_s"], "ms": r_t["ms"], "queries": r_t["queries"],
+                                  "roofline_frac_fp32_alu": r_t["roofline"]["frac"],
+                                  "mean_raw_rank_tail": float(rec[:, 1, 0].mean()), "mean_raw_rank_head": float(rec[:, 0, 0].mean()),
+                                  "what": "same tables, test triples re-planted so that the true entity is the best of 64 random candidates "
+                                          "(raw mean rank ~ E/65, the regime of a trained model): the better-than counting epilogue runs for ~1.5 % "
+                                          "of the candidates instead of ~50 % with random tables"}
+            del con_t
+            torch.cuda.empty_cache()
     except Exception as e:  # noqa: BLE001  (the secondary metric must not kill the headline line)
-        lp = {"error": repr(e)}
+        lp = lp or {}
+        lp["error"] = repr(e)
 
     # ---------------- data-parallel correctness in the driver's own record (N > 1)
     dp_check = None
@@ -713,6 +728,43 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def planted_test_set(con, cfg, g, n, n_cand=64):
+    """A test set on which the CURRENT tables rank the true entity well — the regime of a trained model (raw mean rank
+    ~ E / 65, like published TransE numbers on FB15K) instead of random tables, where half of all candidates beat the target
+    and the counting epilogue of the ranking kernel is over-weighted.  For each of the first n test triples the tail is
+    replaced by the best of n_cand random candidates under the model's own score, then the head likewise."""
+    import torch
+    from openkeonspark_b200 import datagen
+    P = con.trainModel.parameter_lists
+    dev = P["ent_embeddings"].device
+    ent, rel = P["ent_embeddings"], P["rel_embeddings"]
+    l2n = lambda x: x * torch.rsqrt(torch.clamp((x * x).sum(-1, keepdim=True), min=1e-12))
+
+    def score(h, t, r):                                     # index tensors of equal shape -> scores of that shape
+        he, te, re = ent[h], ent[t], rel[r]
+        if cfg["model"] == "TransH":
+            nv = l2n(P["normal_vectors"][r])
+            he = he - (he * nv).sum(-1, keepdim=True) * nv
+            te = te - (te * nv).sum(-1, keepdim=True) * nv
+        return (l2n(he) + l2n(re) - l2n(te)).abs().sum(-1)
+
+    test = torch.as_tensor(np.ascontiguousarray(g.test[:n]), device=dev)
+    gen = torch.Generator(device=dev).manual_seed(7)
+    out = []
+    for lo in range(0, n, 4096):
+        blk = test[lo:lo + 4096]
+        h, t, r = blk[:, 0:1], blk[:, 1:2], blk[:, 2:3]
+        cand = torch.randint(0, g.E, (blk.shape[0], n_cand), device=dev, generator=gen)
+        cand[:, 0] = t[:, 0]
+        t2 = cand.gather(1, score(h.expand_as(cand), cand, r.expand_as(cand)).argmin(1, keepdim=True))
+        cand = torch.randint(0, g.E, (blk.shape[0], n_cand), device=dev, generator=gen)
+        cand[:, 0] = h[:, 0]
+        h2 = cand.gather(1, score(cand, t2.expand_as(cand), r.expand_as(cand)).argmin(1, keepdim=True))
+        out.append(torch.cat([h2, t2, r], 1))
+    new_test = torch.cat(out, 0).cpu().numpy().astype(np.int64)
+    return datagen.Graph(g.E, g.R, g.train, g.valid, new_test)
 
 
 def run_dp_check(con, dist, dev, world, rank):

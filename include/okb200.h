@@ -345,11 +345,12 @@ enum { OKB_FLAG_TRANSR_TC = 1,
           of one table and every thread has all its row-map entries and x / m / v vectors in flight before the first
           gradient load.  Bit-identical results for every value. */
        OKB_FLAG_ADAM_VPT = 11,
-       /* OKB_FLAG_TRANSR_FUSED = 12 (default on): TransR's okb_grad runs the persistent kernel (one CTA per SM walks its
+       /* OKB_FLAG_TRANSR_FUSED = 12 (default off): TransR's okb_grad runs a persistent kernel (one CTA per SM walks its
           relations, M_r of the next relation in flight by bulk-async copy while the current one is computed) and applies
           the RELATION-side update — rel_embeddings[r], transfer_matrix[r], their Adam slots — in place with the step's
-          hyper-parameters; okb_update then only moves the entity rows and grad_rel is not written.  0: per-relation
-          kernel + separate relation update through grad_rel (the round-1 form, kept for A/B runs). */
+          hyper-parameters; okb_update then only moves the entity rows and grad_rel is not written.  Measured on B200
+          (FB15K shape, B = 4,831): 161 vs 163 us per step with SGD, 240 vs 195 with Adam — the step is bound by the
+          per-relation chain of small dependent phases, not by M_r traffic — so the two-kernel form stays the default. */
        OKB_FLAG_TRANSR_FUSED = 12 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 

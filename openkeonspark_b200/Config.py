@@ -47,7 +47,7 @@ class Config(object):
         # symbols act on the same process-global context this Config uses.
         self.lib = _native.load(cpp_lib_path)
         self.ctx = _native.Ctx(self.lib, default=not private_context)
-        for env, flag, val in (("OKB200_PDL", 2, 0), ("OKB200_ADAM_TMA", 3, 1), ("OKB200_L2_PREFETCH", 4, 1), ("OKB200_ADAM_LEGACY", 5, 1), ("OKB200_GRAD_GENERIC", 6, 1), ("OKB200_DP_PULL", 7, 1), ("OKB200_GRAD_SINGLE_WARP", 8, 1), ("OKB200_PLAN_MULTI", 9, 1), ("OKB200_CHUNK_KERNEL", 10, 1), ("OKB200_TRANSR_FUSED", 12, 0)):
+        for env, flag, val in (("OKB200_PDL", 2, 0), ("OKB200_ADAM_TMA", 3, 1), ("OKB200_L2_PREFETCH", 4, 1), ("OKB200_ADAM_LEGACY", 5, 1), ("OKB200_GRAD_GENERIC", 6, 1), ("OKB200_DP_PULL", 7, 1), ("OKB200_GRAD_SINGLE_WARP", 8, 1), ("OKB200_PLAN_MULTI", 9, 1), ("OKB200_CHUNK_KERNEL", 10, 1), ("OKB200_TRANSR_FUSED", 12, 1)):
             if os.environ.get(env) == str(val):      # A/B switches for measurements (include/okb200.h OKB_FLAG_*)
                 self.ctx.call("okb_set_flag", flag, val)
         if os.environ.get("OKB200_ADAM_VPT"):

@@ -92,7 +92,7 @@ struct okb_ctx {
     bool adam_legacy = false;         // OKB_FLAG_ADAM_LEGACY: grid-stride register kernel instead of the tile kernel
     bool adam_tma = false;            // OKB_FLAG_ADAM_TMA: TMA-staged single-wave Adam pass instead of the register-only one
     bool l2_prefetch = false;         // OKB_FLAG_L2_PREFETCH: grad kernel prefetches the Adam state into L2
-    bool transr_fused = true;         // OKB_FLAG_TRANSR_FUSED: persistent TransR kernel with the relation update applied in place
+    bool transr_fused = false;        // OKB_FLAG_TRANSR_FUSED: persistent TransR kernel with the relation update applied in place (measured: no faster; off)
     bool transr_rel_done = false;     // the last okb_grad (TransR) already applied the relation-side update
     i64 tr_lo = 0, tr_hi = 0;         // TransR relation shard [tr_lo, tr_hi) (okb_transr_set_shard); empty = all relations
     okb_dp dp = {};                   // owner-sharded data parallelism (okb_dp_attach)

@@ -484,19 +484,22 @@ __global__ void __launch_bounds__(CT * QG, 1024 / (CT * QG)) rank_kernel(RankArg
         tma_load_1d(qa, a.qa + (i64)(blk0 + pb) * D * QB, bytes, bar + 1 + buf);
         if (HEADS) tma_load_1d(qt, a.qt + (i64)(blk0 + pb) * D * QB, bytes, bar + 1 + buf);
     };
-    if (tid == 0) {
-        mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);
-        mbar_expect_tx(bar, (unsigned)(D * CT * sizeof(float)));
+    if (tid < 32) {                                        // warp 0: the D row copies of the tile go out from all 32 lanes at once
+        if (tid == 0) {                                    // (one thread issuing them back to back costs ~1 us per CTA)
+            mbar_init(bar, 1); mbar_init(bar + 1, 1); mbar_init(bar + 2, 1);
+            mbar_expect_tx(bar, (unsigned)(D * CT * sizeof(float)));
+        }
+        __syncwarp();
         const float *src = a.cand + (i64)tab * D * a.ncol + col0;
-        for (int d = 0; d < D; d++) tma_load_1d(tile + (size_t)d * CT, src + (i64)d * a.ncol, CT * sizeof(float), bar);
-        if (nblk > 0) load_queries(0, 0);
+        for (int d = tid; d < D; d += 32) tma_load_1d(tile + (size_t)d * CT, src + (i64)d * a.ncol, CT * sizeof(float), bar);
+        if (tid == 0 && nblk > 0) load_queries(0, 0);
     }
     for (int d = tid; d < D; d += CT * QG) rhat[d] = a.rv[(i64)g * 2 * D + d];
     const i32 j = a.j0 + col0 + jl;
     const bool valid = j >= a.cand_lo && j < a.cand_hi;
     const unsigned tf = valid ? a.tflag[(i64)g * a.ncol + col0 + jl] : 0u;
     __syncthreads();                                       // barrier init visible to all waiters
-    mbar_wait(bar, 0);
+    // (the tile is awaited right before the first distance loop: its copy latency runs under the first pass's set-up)
 
     int pass = 0;
     for (i32 pb = 0; pb < nblk; pb += QG, pass++) {        // a pass = QG consecutive 8-query blocks of the group
@@ -538,6 +541,7 @@ __global__ void __launch_bounds__(CT * QG, 1024 / (CT * QG)) rank_kernel(RankArg
             bst[idx] = (qb + (idx >> 3) < qhi) ? a.best[(i64)(qb + (idx >> 3)) * 8 + (idx & 7)] : ~0ull;
         }
         __syncthreads();
+        if (pass == 0) mbar_wait(bar, 0);
         mbar_wait(bar + 1 + buf, (unsigned)(pass >> 1) & 1u);
 
         if (qg < nb) {
@@ -621,6 +625,7 @@ __global__ void __launch_bounds__(CT * QG, 1024 / (CT * QG)) rank_kernel(RankArg
             }
         }
     }
+    if (pass == 0) mbar_wait(bar, 0);                       // never leave with the tile copy still in flight
 }
 
 // ------------------------------------------------------------------------------------------ finalize

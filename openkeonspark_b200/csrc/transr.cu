@@ -285,18 +285,20 @@ __global__ void __launch_bounds__(TR_THREADS) transr_bucket_kernel(TrArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------ persistent, fused form
-// The per-relation kernel above spends its 119 us (FB15K shape, B = 4,831) waiting: every CTA stages 40 KB of M_r, runs
-// three small contractions and writes 40 KB of dM_r back, all serialised, and a second kernel re-reads dM_r and M_r to
-// apply the update — 260 MB of HBM traffic for 104 MB of algorithmic bytes.  Here ONE CTA per SM stays resident and walks
-// its share of the relations:
-//   * M_r of the NEXT touched relation is already in flight (one 40 KB bulk-async / TMA copy on an mbarrier into the
-//     other half of a double buffer) while the current relation is computed;
+// An experiment, kept behind OKB_FLAG_TRANSR_FUSED (default off).  Hypothesis: the per-relation kernel above (119 us at the
+// FB15K shape, B = 4,831) is bound by staging 40 KB of M_r per CTA, writing 40 KB of dM_r back and a second kernel that
+// re-reads both (260 MB of HBM traffic for 104 MB of algorithmic bytes).  So: ONE CTA per SM stays resident and walks its
+// share of the relations,
+//   * M_r of the NEXT touched relation is in flight (one 40 KB bulk-async / TMA copy on an mbarrier into the other half of a
+//     double buffer) while the current relation is computed;
 //   * 512 threads per relation (the matrix-gradient tiles stay in registers: 2 x 16 per thread);
 //   * the relation's update is applied on the spot — M_r - lr dM_r (or TF1 Adam) straight from the staged copy and the
-//     register tiles to global memory, rel_embeddings[r] likewise — no dM round trip, no second kernel.  Only this CTA
-//     ever touches relation r during the step (negatives share the positive's relation, TransR.py:57-60), so
-//     overwriting it at the end of the relation's pass is safe.
-// TF1 Adam moves untouched relations too (dense decay): the owning CTA streams those after its touched ones.
+//     register tiles, rel_embeddings[r] likewise — no dM round trip, no second kernel.  (Only this CTA ever touches
+//     relation r during the step: negatives share the positive's relation, TransR.py:57-60.)
+// MEASURED (profiles/README.md, r02h): 161.2 vs 163.4 us per step with SGD, 240 vs 195 with Adam.  The traffic was never
+// the limiter: a relation owns ~11 gathered rows, and its pass is a chain of seven small dependent phases (gather, P,
+// normalise, scores, dA, dM, update) of 1-3 us each in which most of the 512 threads idle — ~17 us per relation whether or
+// not M_r is already in shared memory.  TF1 Adam's dense decay of untouched relations is streamed by the owning CTA.
 #define TRF_THREADS 512
 #define TRF_MAXT 2             // dM tiles (4x4) per thread: De*Dr <= 16 * 512 * 2
 

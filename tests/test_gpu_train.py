@@ -337,7 +337,7 @@ def test_adam_vectors_per_thread_bit_identical(built, small_ds, wide_ds, model, 
 @pytest.mark.parametrize("opt", ["SGD", "Adam"])
 @pytest.mark.parametrize("D,Dr,k,ds", [(100, 100, 1, "small"), (40, 24, 3, "small"), (64, 128, 2, "wide"), (20, 20, 1, "wide")])
 def test_transr_fused_kernel_equals_two_kernel_form(built, small_ds, wide_ds, opt, D, Dr, k, ds):
-    """OKB_FLAG_TRANSR_FUSED (default): persistent kernel, M_r double-buffered by bulk-async copies, relation-side update
+    """OKB_FLAG_TRANSR_FUSED (an A/B experiment, default off): persistent kernel, M_r double-buffered by bulk-async copies, relation-side update
     applied in place — against the round-1 form (one CTA per relation + a separate relation-update kernel through the
     per-relation gradient rows).  Same contractions in the same order: losses equal, tables within 1e-7 (the update is the
     same expression compiled in two kernels)."""
