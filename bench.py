@@ -568,7 +568,7 @@ def main():
         lp = measure_lp(con, HEAD, g, min(args.lp_queries, con.testTotal))
         if world == 1:      # the same evaluation in the regime of a TRAINED model: few candidates beat the target
             nq_t = min(args.lp_queries, con.testTotal)
-            g_t = planted_test_set(con, HEAD, g, nq_t)
+            g_t = planted_test_set(dev, HEAD, g, nq_t)
             con_t, _ = make_con(HEAD, g_t, 1, 0)
             r_t = measure_lp(con_t, HEAD, g_t, nq_t)
             rec = con_t.link_prediction_records(0, min(nq_t, 4096)).cpu().numpy()
@@ -730,15 +730,14 @@ def main():
         dist.destroy_process_group()
 
 
-def planted_test_set(con, cfg, g, n, n_cand=64):
+def planted_test_set(dev, cfg, g, n, n_cand=64):
     """A test set on which the CURRENT tables rank the true entity well — the regime of a trained model (raw mean rank
     ~ E / 65, like published TransE numbers on FB15K) instead of random tables, where half of all candidates beat the target
     and the counting epilogue of the ranking kernel is over-weighted.  For each of the first n test triples the tail is
     replaced by the best of n_cand random candidates under the model's own score, then the head likewise."""
     import torch
     from openkeonspark_b200 import datagen
-    P = con.trainModel.parameter_lists
-    dev = P["ent_embeddings"].device
+    P = {k: torch.as_tensor(v, device=dev) for k, v in params_for(cfg, g).items()}      # the tables make_con() starts from
     ent, rel = P["ent_embeddings"], P["rel_embeddings"]
     l2n = lambda x: x * torch.rsqrt(torch.clamp((x * x).sum(-1, keepdim=True), min=1e-12))
 
