@@ -382,6 +382,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    align = torch.zeros(1, device=dev)
+
     def max_over_ranks(x):
         t = torch.tensor([x], dtype=torch.float64, device=dev)
         if world > 1:
@@ -428,6 +430,11 @@ def main():
         for a, b in ev:
             if flush is not None:
                 flush.fill_(1)
+                if world > 1:
+                    # the 256 MiB fills finish at different times on different ranks; a synchronous step would then time
+                    # that skew as flag-wait inside the event pair.  A tiny all-reduce (stream-ordered, outside the
+                    # events) lines the ranks up again, as they are in the real loop, which has no flush.
+                    dist.all_reduce(align)
             a.record()
             one_step()
             b.record()

@@ -819,7 +819,14 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
         a.by_row = a.key_limit < n;                       // fewer table rows than gradient rows: one warp per table row
         a.work_blocks = (i32)(((a.by_row ? (i64)a.key_limit : n) + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         ProfScope ps(c, PROF_UPDATE, s);
-#define CALL_SGD(VW, NV) sgd_kernel<VW, NV><<<a.work_blocks + a.loss_blocks, WARPS_PER_BLOCK * 32, 0, s>>>(a)
+        // programmatic dependent launch, like the Adam pass: row map + table rows are requested while the grad kernel drains
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(a.work_blocks + a.loss_blocks)); cfg.blockDim = dim3(WARPS_PER_BLOCK * 32); cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = (c->pdl && !a.hub) ? 1 : 0;     // after the hub pre-reduction kernel: plain stream order
+#define CALL_SGD(VW, NV) OKB_CUDA(c, cudaLaunchKernelEx(&cfg, sgd_kernel<VW, NV>, a))
         DISPATCH_LAYOUT(vw, nv, CALL_SGD);
         OKB_LAUNCHED(1);
     }

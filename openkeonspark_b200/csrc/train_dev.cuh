@@ -879,7 +879,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) prereduce_kernel(UpdArgs
 // SGD: row -= lr * sum of its gradient rows (GradientDescentOptimizer's sparse apply: duplicates accumulate).
 // One warp per sorted position (only segment heads work), or — when the batch has more gradient rows than the
 // tables have rows — one warp per table row.
-template <int VW, int NV, bool COH>
+// PDL: the kernel was launched with programmatic stream serialization — the row map and the table row (neither written by
+// the grad kernel) are requested first, griddepcontrol.wait then guarantees the gradient rows.
+template <int VW, int NV, bool COH, bool PDL = false>
 __device__ __forceinline__ void sgd_body(const UpdArgs &a, i32 w, int lane) {
     constexpr int N = VW * NV;
     i32 key;
@@ -904,6 +906,7 @@ __device__ __forceinline__ void sgd_body(const UpdArgs &a, i32 w, int lane) {
         const i64 off = (i64)row * D;
         Frag<VW, NV> x;
         x.template load<COH>(tab + off, D, lane);         // independent of the gradient rows: in flight first
+        if (PDL) pdl_wait();
         float g[N];
 #pragma unroll
         for (int q = 0; q < N; q++) g[q] = 0.f;
@@ -915,9 +918,10 @@ __device__ __forceinline__ void sgd_body(const UpdArgs &a, i32 w, int lane) {
 }
 template <int VW, int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
-    if ((i32)blockIdx.x >= a.work_blocks) { loss_block(a, (i32)blockIdx.x - a.work_blocks, (i32)blockDim.x); return; }
+    pdl_launch_dependents();                               // next step's grad kernel may fetch its batch ids
+    if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a, (i32)blockIdx.x - a.work_blocks, (i32)blockDim.x); return; }
     if (upd_bad(a)) return;
-    sgd_body<VW, NV, false>(a, blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5), threadIdx.x & 31);
+    sgd_body<VW, NV, false, true>(a, blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 // TF1 AdamOptimizer._apply_sparse_shared: m and v decay over the WHOLE variable and every row moves
