@@ -283,3 +283,60 @@ def test_threshold_search_wide_score_range(built, small_ds):
         con.ctx.call("okb_best_threshold", vp(th.ctypes.data), vp(pos.ctypes.data), vp(neg.ctypes.data))
         exp = orc.best_threshold(pos, neg, np.zeros(con.relTotal, np.float32))
         assert np.array_equal(th.view(np.uint32), exp.view(np.uint32)), (scale, quant)
+
+
+def test_host_batch_fast_path_and_fallback(built, small_ds):
+    """Config.sampling() leaves the batch resident and planned; Config.train_step(batch_h, ...) with the UNCHANGED arrays only
+    verifies them on the device (no narrowing, no re-plan).  Arrays changed in between — in place or replaced — must give
+    exactly what the general path gives: the step is skipped on the device (tables untouched) and redone from the caller's
+    arrays."""
+    import openkeonspark_b200 as okb
+
+    def fresh():
+        con = okb.Config(private_context=True)
+        con.set_in_path(small_ds)
+        con.set_nbatches(6); con.set_ent_neg_rate(2); con.set_dimension(32); con.set_opt_method("Adam"); con.set_alpha(0.01)
+        con.workThreads = 4
+        con.init()
+        seeds = np.arange(1, 5, dtype=np.uint64) * np.uint64(40503)
+        con.ctx.call("okb_set_streams", vp(seeds.ctypes.data), 4)
+        con.set_model_and_session(okb.TransH)
+        con.set_parameters(make_params("TransH", con.entTotal, con.relTotal, 32, seed=2))
+        return con
+
+    a, b, c = fresh(), fresh(), fresh()
+    la, lb, lc = [], [], []
+    for it in range(4):
+        a.sampling()                                          # fast path: hand the pinned block straight back
+        la.append(a.train_step(a.batch_h, a.batch_t, a.batch_r, a.batch_y))
+        b.sampling()                                          # general path: copies of the arrays (not the pinned block)
+        lb.append(b.train_step(b.batch_h.copy(), b.batch_t.copy(), b.batch_r.copy(), b.batch_y))
+        c.sampling()                                          # changed IN PLACE after sampling(): swap two positives' negatives
+        B = c.batch_size
+        for arr in (c.batch_h, c.batch_t, c.batch_r):
+            arr[[B + 1, B + 2]] = arr[[B + 2, B + 1]]
+        lc.append(c.train_step(c.batch_h, c.batch_t, c.batch_r, c.batch_y))
+        # the same modified batch through the general path on a 4th context built from c's pre-step state is overkill:
+        # the hinge mean does not depend on which positive a negative is paired with ONLY if scores tie, so compare with
+        # the restatement instead
+    assert la == lb
+    pa, pb = a.get_parameters(), b.get_parameters()
+    for k in pa:
+        assert np.array_equal(pa[k], pb[k]), k
+    assert a._step == b._step == c._step == 4
+    # c: every step fell back (its arrays never matched the resident batch) and still trained, on the MODIFIED batches
+    from oracle import models_ref
+    d = fresh()
+    ref = models_ref.Trainer("TransH", make_params("TransH", d.entTotal, d.relTotal, 32, seed=2), margin=1.0, lr=0.01, opt="Adam")
+    for it in range(4):
+        d.sampling()
+        B = d.batch_size
+        h, t, r = d.batch_h.copy(), d.batch_t.copy(), d.batch_r.copy()
+        for arr in (h, t, r):
+            arr[[B + 1, B + 2]] = arr[[B + 2, B + 1]]
+        l = ref.step(h, t, r, B, 2, 0)
+        assert abs(lc[it] - l) <= (2e-5 if it == 0 else 1e-3) * abs(l) + 1e-6, (it, lc[it], l)
+        d.train_step(h, t, r, d.batch_y)                      # keeps d's sampler in step with c's
+    pc, pd = c.get_parameters(), d.get_parameters()
+    for k in pc:
+        assert np.array_equal(pc[k], pd[k]), k               # fallback == general path, bit for bit
