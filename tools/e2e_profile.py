@@ -27,7 +27,7 @@ print("  label fill          %.1f us" % timeit(_y))
 print("  okb_sample_to_host  %.1f us (sync)" % timeit(lambda: con.ctx.call("okb_sample_to_host", con.batch_size, con.negative_ent, con.negative_rel, 0, con.workThreads, _vp(con.batch_h_addr), _vp(con.batch_t_addr), _vp(con.batch_r_addr), _stream())))
 print("  okb_sample + okb_batch_to_host %.1f us (sync)" % timeit(lambda: (con.sampling_device(), con.ctx.call("okb_batch_to_host", 0, _vp(con.batch_h_addr), _vp(con.batch_t_addr), _vp(con.batch_r_addr), None, _stream()))))
 print("train_step()          %.1f us" % timeit(lambda: con.train_step(con.batch_h, con.batch_t, con.batch_r, con.batch_y)))
-print("  _hyper()            %.1f us" % timeit(lambda: con._hyper(False)))
+print("  _hyper()            %.1f us" % timeit(lambda: con._hypers(1)))
 print("  train_step_device   %.1f us (async, incl. 1-step plan)" % timeit(lambda: con.train_step_device(0)))
 print("  loss .item()        %.1f us" % timeit(lambda: con._loss_dev.item()))
 both = timeit(lambda: (con.sampling(), con.train_step(con.batch_h, con.batch_t, con.batch_r, con.batch_y)))
