@@ -60,8 +60,6 @@ int okb_destroy(okb_ctx *c) {
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->ev_sampled) cudaEventDestroy(c->ev_sampled);
-    if (c->ev_adv) cudaEventDestroy(c->ev_adv);
-    if (c->ev_grad) cudaEventDestroy(c->ev_grad);
     if (c == g_ctx) g_ctx = nullptr;
     delete c;
     return 0;

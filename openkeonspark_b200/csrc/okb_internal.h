@@ -104,8 +104,6 @@ struct okb_ctx {
     bool alt_ready = false, in_prefetch = false;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_main = nullptr, ev_side = nullptr, ev_sampled = nullptr;
-    cudaEvent_t ev_adv = nullptr, ev_grad = nullptr;   // host-batch loop: stream advance on the side stream / last reader of the resident batch
-    bool adv_pending = false, grad_recorded = false, want_grad_event = false;
     size_t saved_n = 0;
     u64 *d_state_saved = nullptr;     // RNG streams as they were before the prefetched chunk was sampled
     bool pdl = true;                  // programmatic dependent launch between the grad and update kernels

@@ -208,10 +208,6 @@ static int sample_impl(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_l
     if (B * (1 + k + kr) * steps > 0x7fffffffLL / 4) OKB_FAIL(c, OKB_ERR_ARG, "batch too large for int32 indexing");
     if (!c->in_prefetch) okb_discard_prefetch(c);          // a chunk sampled ahead is no longer the continuation of the streams
     cudaStream_t s = (cudaStream_t)stream;
-    if (c->adv_pending && s != c->side) {                  // the last okb_sample_to_host advanced the streams on the side stream
-        OKB_CUDA(c, cudaStreamWaitEvent(s, c->ev_adv, 0));
-        c->adv_pending = false;
-    }
     const i64 S = B * (1 + k + kr);
     if (c->batch.ensure(sizeof(i32) * 3 * S * steps)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (batch)");
     c->B = B; c->K = k; c->KR = kr; c->steps = steps;
@@ -302,34 +298,8 @@ int okb_sample_to_host(okb_ctx *c, INT B, INT k, INT kr, INT stream_lo, INT stre
         return rc ? rc : okb_batch_to_host(c, 0, h, t, r, nullptr, stream);
     }
     if (!c->ev_sampled) OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_sampled, cudaEventDisableTiming));
-    // The sample kernel does not touch the model, so it need not queue behind the previous step's table update: it runs on
-    // the library's side stream, ordered only behind the last kernel that READ the resident batch (the previous step's grad
-    // kernel, okb_train_step_host records ev_grad there).  The ~12 us tail of the dense Adam pass and the 20 us of posted
-    // PCIe stores of the next batch then overlap.  Everything that consumes the batch waits for ev_sampled.
-    cudaStream_t s_main = (cudaStream_t)stream, s_samp = s_main;
-    if (!c->dp_on && !c->prof_on && stream_lo == 0 && stream_hi >= c->W) {
-        if (!c->side) {
-            OKB_CUDA(c, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-            OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
-            OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
-        }
-        if (!c->ev_adv) {
-            OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_adv, cudaEventDisableTiming));
-            OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_grad, cudaEventDisableTiming));
-        }
-        if (c->grad_recorded) {                            // readers of the resident batch issued so far
-            OKB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_grad, 0));
-            s_samp = c->side;
-        }
-    }
-    int rc = sample_impl(c, B, k, kr, 1, stream_lo, stream_hi, dh, c->ev_sampled, s_samp);
+    int rc = sample_impl(c, B, k, kr, 1, stream_lo, stream_hi, dh, c->ev_sampled, stream);
     if (rc) return rc;
-    if (s_samp != s_main) {
-        OKB_CUDA(c, cudaEventRecord(c->ev_adv, s_samp));   // the stream advance behind the sample kernel
-        c->adv_pending = true;
-        OKB_CUDA(c, cudaStreamWaitEvent(s_main, c->ev_sampled, 0));
-        c->grad_recorded = false;
-    }
     // The batch also stays resident on the device, and the reference's loop hands exactly these arrays straight back to
     // train_step (distribute_training.py:274-282).  Plan that step NOW, behind the event the call waits on: the one-step
     // plan then runs while the host is between the two calls, and okb_train_step_host only has to VERIFY that the

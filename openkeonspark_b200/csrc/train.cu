@@ -585,8 +585,6 @@ int okb_train_step_host(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT
     // that).  The batch is still resident and already planned, so the step starts at once and a small kernel only VERIFIES
     // that the arrays were not changed in between; a difference makes the update kernels skip the step (NaN loss) and
     // the call falls through to the general path below with the tables untouched.
-    c->want_grad_event = true;
-    struct Reset { okb_ctx *c; ~Reset() { c->want_grad_event = false; } } reset_flag{c};
     if (okb_batch_verify_host(c, B, k, kr, h, t, r, stream) == 0) {
         *(volatile unsigned *)loss_word = sentinel;
         if ((rc = okb_train_step(c, m, hp, 0, loss_word, stream))) return rc;
@@ -862,10 +860,6 @@ int okb_train_step(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
         OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory (gradient rows)");
     if (!planned(c, step, step + 1, 0, c->B)) { if ((rc = okb_plan(c, step, stream))) return rc; }
     if ((rc = okb_grad(c, m, hp, step, 0, c->B, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), stream))) return rc;
-    if (c->want_grad_event && c->ev_grad) {                // host-batch loop: the next sampling() may overwrite the batch from here on
-        OKB_CUDA(c, cudaEventRecord(c->ev_grad, (cudaStream_t)stream));
-        c->grad_recorded = true;
-    }
     return okb_update(c, m, hp, step, c->gent.as<float>(), c->grel.as<float>(), c->lossterms.as<float>(), loss_out, stream);
 }
 
