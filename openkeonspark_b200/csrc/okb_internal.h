@@ -82,6 +82,8 @@ struct okb_ctx {
     i64 plan_b_lo = 0, plan_b_hi = 0;                          // ... for positives [plan_b_lo, plan_b_hi) of each step
     bool transr_tc = false;           // OKB_FLAG_TRANSR_TC: tensor-core candidate projection for TransR ranking
     bool loss_ctr_ready = false;
+    const void *verify_h = nullptr;   // pending comparison of the caller's block (device alias) with the resident batch: rides in the next grad launch
+    i64 verify_S = 0;
     const void *spec_mirror = nullptr;// host block the last okb_sample_to_host filled while its batch is still resident and planned
     bool batch_from_host = false;     // the current batch came through okb_batch_from_host: update kernels honour the "bad id" flag
     bool chunk_kernel = false;        // OKB_FLAG_CHUNK_KERNEL: okb_train_steps runs a chunk as one persistent kernel where covered (measured slower: off)
@@ -190,6 +192,7 @@ i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(
 #define OKB_FLAGS_GRIDBAR 72
 int okb_ensure_flags(okb_ctx *c, cudaStream_t s);     // train.cu: allocate + zero once
 
+extern "C" int okb_verify_flush(okb_ctx *c, void *stream);       // sampler.cu: launch a pending comparison stand-alone
 extern "C" int okb_batch_verify_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const INT *t, const INT *r, void *stream);   // sampler.cu
 
 // train.cu: forget a prefetched chunk (restores the RNG streams); every entry point that touches the streams calls it

@@ -328,10 +328,20 @@ int okb_batch_verify_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const 
     if (!ph) return -1;
     cudaStream_t s = (cudaStream_t)stream;
     if (okb_ensure_flags(c, s)) return -1;
-    verify_kernel<<<(unsigned)((S + 255) / 256), 256, 0, s>>>(ph, ph + S, ph + 2 * S, c->batch.as<i32>(), (i32)S, c->flags.as<unsigned>() + OKB_FLAGS_BAD);
-    OKB_LAUNCHED(1);
-    if (cudaGetLastError() != cudaSuccess) return -1;
+    // the comparison itself rides in the grad launch (extra blocks at the end of its grid read the caller's block over PCIe
+    // while the positives are processed): launch_grad picks it up; okb_verify_flush launches it stand-alone otherwise
+    c->verify_h = ph; c->verify_S = S;
     c->batch_from_host = true;                             // the update kernels honour the flag word
+    return 0;
+}
+int okb_verify_flush(okb_ctx *c, void *stream) {
+    if (!c->verify_h) return 0;
+    const i64 *ph = (const i64 *)c->verify_h;
+    const i64 S = c->verify_S;
+    c->verify_h = nullptr;
+    verify_kernel<<<(unsigned)((S + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ph, ph + S, ph + 2 * S, c->batch.as<i32>(), (i32)S, c->flags.as<unsigned>() + OKB_FLAGS_BAD);
+    OKB_LAUNCHED(1);
+    OKB_CUDA(c, cudaGetLastError());
     return 0;
 }
 

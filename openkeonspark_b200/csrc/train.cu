@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(AP_TILE, 2) adam_pipe_kernel(UpdArgs a, int nt
     unsigned long long *full = reinterpret_cast<unsigned long long *>(st + AP_STAGES);
     const int G = a.work_blocks, tid = threadIdx.x;
     if ((int)blockIdx.x >= G) { pdl_launch_dependents(); pdl_wait(); loss_block(a, (i32)blockIdx.x - G, (i32)blockDim.x); return; }
-    if (upd_bad(a)) { pdl_launch_dependents(); return; }
+    if (a.bad) { pdl_launch_dependents(); pdl_wait(); if (upd_bad(a)) return; }
     const int my_n = (ntiles - (int)blockIdx.x + G - 1) / G;         // this CTA's tiles: blockIdx.x + j * G
     if (tid == 0) {
         for (int s = 0; s < AP_STAGES; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(a_smem(full + s)));
@@ -619,6 +619,7 @@ void okb_fill_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
     a.B = (i32)c->B; a.k = (i32)c->K; a.kr = (i32)c->KR; a.NE = (i32)(2 + c->K); a.NR = (i32)(1 + c->KR);
     a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi; a.slot_base = (i32)slot_base;
     a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_n = 0; a.npf = 0;
+    a.vh = nullptr; a.vflag = nullptr; a.vS = 0; a.vblocks = 0;
 }
 // warps per positive the generic grad kernel uses for this batch (1 = one warp per positive); a function of the GLOBAL
 // batch, so that a data-parallel rank's slice is computed exactly like the same positives on one GPU
@@ -639,6 +640,7 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     cudaStream_t s = (cudaStream_t)stream;
     const i64 S = c->B * (1 + c->K + c->KR);
     if (m->model == OKB_TRANSR) {                          // relation-bucketed kernel; needs the plan's relation segments
+        if ((rc = okb_verify_flush(c, stream))) return rc;
         if (slot_base || wait_flags) OKB_FAIL(c, OKB_ERR_ARG, "TransR is not supported by the owner-sharded data-parallel path");
         if (!planned(c, step, step + 1, 0, c->B)) OKB_FAIL(c, OKB_ERR_STATE, "step has not been planned (okb_plan / okb_plan_steps)");
         if ((rc = ensure_rowhead(c, s))) return rc;
@@ -697,6 +699,13 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32 * wpp);
         cfg.dynamicSmemBytes = sizeof(float) * (size_t)(wpp - 1) * (F * 32 * N + 64);
     }
+    if (c->verify_h && step == 0 && b_lo == 0 && b_hi == c->B && !wait_flags) {
+        // host-batch fast path: compare the caller's block with the resident batch in extra blocks of this launch
+        a.vh = (const long long *)c->verify_h; a.vS = (i32)c->verify_S; a.vflag = c->flags.as<unsigned>() + OKB_FLAGS_BAD;
+        a.vblocks = (i32)std::min<i64>(64, (c->verify_S + 255) / 256);
+        cfg.gridDim = dim3(cfg.gridDim.x + (unsigned)a.vblocks);
+        c->verify_h = nullptr;
+    } else if ((rc = okb_verify_flush(c, stream))) return rc;
     { ProfScope ps(c, PROF_GRAD, s);
       if (k1) { DISPATCH_LAYOUT(vw, nv, CALL_GRAD1); } else if (wpp > 1) { DISPATCH_LAYOUT(vw, nv, CALL_GRADW); } else { DISPATCH_LAYOUT(vw, nv, CALL_GRAD); } }
     OKB_LAUNCHED(1);

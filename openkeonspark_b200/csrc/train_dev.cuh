@@ -338,7 +338,21 @@ struct GradArgs {
     unsigned long long *announce[OKB_DP_MAX];              // this rank's x_ready word in every rank's flag block
     unsigned long long wait_epoch;
     i32 wait_n;
+    // host-batch fast path: the caller's int64 block [3][S] (page-locked, device alias) is compared with the resident batch
+    // by `vblocks` extra blocks at the END of the grid; a difference raises bit 1 of *vflag (the update kernels then skip)
+    const long long *vh;
+    unsigned *vflag;
+    i32 vS, vblocks;
 };
+__device__ __forceinline__ void grad_verify_block(const GradArgs &a, i32 vb) {
+    const i32 S = a.vS, T = (i32)blockDim.x, per = (S + a.vblocks - 1) / a.vblocks;
+    const i32 lo = vb * per, hi = min(S, lo + per);
+    const i32 *dev = a.bh;                                  // [3][S]: bh, bt = bh + S, br = bh + 2S
+    bool bad = false;
+    for (i32 i = lo + (i32)threadIdx.x; i < hi; i += T)
+        bad |= a.vh[i] != (long long)dev[i] || a.vh[S + i] != (long long)dev[S + i] || a.vh[2 * (i64)S + i] != (long long)dev[2 * (i64)S + i];
+    if (bad) atomicOr(a.vflag, 2u);
+}
 
 // ------------------------------------------------------------------------------------------ grad
 // Everything of one positive group after its batch ids are known (ph, pt, pr and the first negative's nh, nt): gathers,
@@ -471,6 +485,7 @@ __global__ void __launch_bounds__(WPPMAX == 1 ? GRAD_WARPS * 32 : WPPMAX * 32, W
     const int lane = threadIdx.x & 31;
     const int wpp = WPPMAX == 1 ? 1 : (int)(blockDim.x >> 5), wid = WPPMAX == 1 ? 0 : (int)(threadIdx.x >> 5);
     const i32 b = WPPMAX == 1 ? a.b_lo + blockIdx.x * GRAD_WARPS + (threadIdx.x >> 5) : a.b_lo + (i32)blockIdx.x;
+    if (a.vblocks && (i32)blockIdx.x >= (i32)gridDim.x - a.vblocks) { grad_verify_block(a, (i32)blockIdx.x - ((i32)gridDim.x - a.vblocks)); return; }
     if (b >= a.b_hi) return;
     const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
     // entity that replaces a side in negative m (Base.cpp:118-126): the new head if the head changed, else the tail
@@ -705,6 +720,7 @@ template <int MODEL, int VW, int NV>
 __global__ void __launch_bounds__(32, GRAD1_MIN_BLOCKS) grad_k1_kernel(GradArgs a) {
     const int lane = threadIdx.x & 31;
     const i32 b = a.b_lo + blockIdx.x;
+    if (a.vblocks && (i32)blockIdx.x >= (i32)gridDim.x - a.vblocks) { grad_verify_block(a, (i32)blockIdx.x - ((i32)gridDim.x - a.vblocks)); return; }
     if (b >= a.b_hi) return;
     const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
     const i32 nh = a.bh[b + a.B], nt = a.bt[b + a.B];
@@ -920,7 +936,7 @@ template <int VW, int NV>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) sgd_kernel(UpdArgs a) {
     pdl_launch_dependents();                               // next step's grad kernel may fetch its batch ids
     if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a, (i32)blockIdx.x - a.work_blocks, (i32)blockDim.x); return; }
-    if (upd_bad(a)) return;
+    if (a.bad) { pdl_wait(); if (upd_bad(a)) return; }     // host-batch steps: the flag is final once the grad launch has completed
     sgd_body<VW, NV, false, true>(a, blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
@@ -934,7 +950,7 @@ template <int VW>
 __global__ void __launch_bounds__(256, 6) adam_kernel(UpdArgs a) {
     pdl_launch_dependents();
     if ((i32)blockIdx.x >= a.work_blocks) { pdl_wait(); loss_block(a, (i32)blockIdx.x - a.work_blocks, (i32)blockDim.x); return; }
-    if (upd_bad(a)) return;
+    if (a.bad) { pdl_wait(); if (upd_bad(a)) return; }
     typedef typename VecT<VW>::T V;
     const i64 total = a.tab[a.ntab - 1].vec_end;
     const i64 stride = (i64)a.work_blocks * blockDim.x;
@@ -1079,9 +1095,10 @@ __global__ void __launch_bounds__(256, VPT == 1 ? ADAM_TILE_MIN_BLOCKS : (VPT ==
             xv[u] = *reinterpret_cast<const V *>(T.x + e); mv[u] = *reinterpret_cast<const V *>(T.m + e); vv[u] = *reinterpret_cast<const V *>(T.v + e);
         }
     }
-    const unsigned badv = a.bad ? *(const volatile unsigned *)a.bad : 0u;     // host-batch steps only (see narrow_kernel)
     pdl_wait();                                            // gradient rows of this step are complete from here on
-    if (badv) return;
+    // host-batch steps only: the flag may be raised by the verification blocks of THIS step's grad launch, so it is read
+    // after the wait (narrow_kernel / grad_verify_block)
+    if (upd_bad(a)) return;
     const float b1 = a.hp.beta1, b2 = a.hp.beta2, lr = a.hp.lr, eps = a.hp.eps, c1 = 1.f - b1, c2 = 1.f - b2;
 #pragma unroll
     for (int u = 0; u < VPT; u++) {
