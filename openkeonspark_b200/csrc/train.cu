@@ -702,7 +702,7 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     if (c->verify_h && step == 0 && b_lo == 0 && b_hi == c->B && !wait_flags) {
         // host-batch fast path: compare the caller's block with the resident batch in extra blocks of this launch
         a.vh = (const long long *)c->verify_h; a.vS = (i32)c->verify_S; a.vflag = c->flags.as<unsigned>() + OKB_FLAGS_BAD;
-        a.vblocks = (i32)std::min<i64>(64, (c->verify_S + 255) / 256);
+        a.vblocks = (i32)((c->verify_S + cfg.blockDim.x - 1) / cfg.blockDim.x);      // one batch row per thread
         cfg.gridDim = dim3(cfg.gridDim.x + (unsigned)a.vblocks);
         c->verify_h = nullptr;
     } else if ((rc = okb_verify_flush(c, stream))) return rc;

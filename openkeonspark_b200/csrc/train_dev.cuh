@@ -345,16 +345,15 @@ struct GradArgs {
     i32 vS, vblocks;
 };
 __device__ __forceinline__ void grad_verify_block(const GradArgs &a, i32 vb) {
-    const i32 S = a.vS, T = (i32)blockDim.x, per = (S + a.vblocks - 1) / a.vblocks;
-    const i32 lo = vb * per, hi = min(S, lo + per);
+    // one element per thread: every PCIe read of the launch is in flight at once (a loop per thread would serialise
+    // round trips of ~2 us each)
+    const i32 S = a.vS, i = vb * (i32)blockDim.x + (i32)threadIdx.x;
+    if (i >= S) return;
     const i32 *dev = a.bh;                                  // [3][S]: bh, bt = bh + S, br = bh + 2S
-    bool bad = false;
-    for (i32 i = lo + (i32)threadIdx.x; i < hi; i += T)
-        bad |= a.vh[i] != (long long)dev[i] || a.vh[S + i] != (long long)dev[S + i] || a.vh[2 * (i64)S + i] != (long long)dev[2 * (i64)S + i];
-    if (bad) atomicOr(a.vflag, 2u);
+    const long long vh = a.vh[i], vt = a.vh[S + i], vr = a.vh[2 * (i64)S + i];
+    if (vh != (long long)dev[i] || vt != (long long)dev[S + i] || vr != (long long)dev[2 * (i64)S + i]) atomicOr(a.vflag, 2u);
 }
 
-// ------------------------------------------------------------------------------------------ grad
 // Everything of one positive group after its batch ids are known (ph, pt, pr and the first negative's nh, nt): gathers,
 // forward, hinge, backward, gradient rows.  COH: coherent (L2) gathers, for the persistent chunk kernel.
 template <int MODEL, int VW, int NV, int WPPMAX, bool COH>
