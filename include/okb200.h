@@ -233,6 +233,13 @@ typedef struct {
     INT max_local;                  /* positives per rank at most */
     INT neg_ent, neg_rel;
     INT off_rowhead, off_perm, off_gent, off_grel, off_loss, off_partial;   /* -1 = not reserved */
+    /* "scatter" form (set scatter = 1, global_batch, neg_ent, neg_rel before okb_dp_layout): every rank samples and plans the
+     * GLOBAL batch; the grad kernel stores each gradient row of this rank's positives straight into the arena of the rank
+     * that owns its table row (off_gent / off_grel: receive buffers with one slot per gradient row of the global batch;
+     * off_loss: hinge terms, stored to every rank); the owner runs the single-GPU update over its rows and stores the new
+     * rows into every rank's tables.  Two kernels and two flag exchanges per step, no staging slabs, and tables + loss
+     * bit-identical to ONE GPU training the global batch. */
+    INT scatter, global_batch;
 } okb_dp;
 int okb_peer_alloc(okb_ctx *c, INT bytes, void **dev_ptr, unsigned char *handle64);
 int okb_peer_open(okb_ctx *c, const unsigned char *handle64, void **dev_ptr);
@@ -351,7 +358,16 @@ enum { OKB_FLAG_TRANSR_TC = 1,
           hyper-parameters; okb_update then only moves the entity rows and grad_rel is not written.  Measured on B200
           (FB15K shape, B = 4,831): 161 vs 163 us per step with SGD, 240 vs 195 with Adam — the step is bound by the
           per-relation chain of small dependent phases, not by M_r traffic — so the two-kernel form stays the default. */
-       OKB_FLAG_TRANSR_FUSED = 12 };
+       OKB_FLAG_TRANSR_FUSED = 12,
+       /* OKB_FLAG_DP_TRACE = 13 (default off, debugging aid): the data-parallel grad / owner-update kernels stamp
+          %globaltimer at their phase boundaries (first block in, grid dependency resolved, flags seen, hub blocks done,
+          last block out) into a 64-step ring read by okb_debug_dp_trace. */
+       OKB_FLAG_DP_TRACE = 13,
+       /* OKB_FLAG_DP_HANDSHAKE = 14: how the data-parallel kernels exchange their epoch flags.  bit 0: waiters poll with
+          relaxed loads and issue ONE acquire fence when the value has arrived (instead of an acquire per poll); bit 1: the
+          announcing store is relaxed — the data it publishes was written by the PREVIOUS grid, whose completion
+          (griddepcontrol.wait) has already made it visible. */
+       OKB_FLAG_DP_HANDSHAKE = 14 };
 int okb_set_flag(okb_ctx *c, int flag, INT value);
 
 /* Optional per-kernel timing with CUDA events recorded on the launching stream, around:
@@ -361,6 +377,9 @@ int okb_set_flag(okb_ctx *c, int flag, INT value);
 int okb_prof_enable(okb_ctx *c, int on);
 int okb_prof_read(okb_ctx *c, int id, double *total_ms, INT *count);
 const char *okb_debug_cuda_error(void);
+/* OKB_FLAG_DP_TRACE stamps: out = unsigned long long[64 * 16], row = epoch % 64 (all-ones = not stamped; slots 3, 4, 8, 9
+ * hold the complement of the stamp); clears the ring. */
+int okb_debug_dp_trace(okb_ctx *c, unsigned long long *out);
 
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 INT okb_launch_count(void);

@@ -38,7 +38,7 @@ class okb_dp(C.Structure):
                 ("off_stage_ent", _i64), ("off_stage_rel", _i64), ("off_flags", _i64), ("arena_bytes", _i64),
                 ("plan_steps", _i64), ("max_local", _i64), ("neg_ent", _i64), ("neg_rel", _i64),
                 ("off_rowhead", _i64), ("off_perm", _i64), ("off_gent", _i64), ("off_grel", _i64), ("off_loss", _i64),
-                ("off_partial", _i64)]
+                ("off_partial", _i64), ("scatter", _i64), ("global_batch", _i64)]
 
 
 MODEL_ID = {"TransE": 0, "TransH": 1, "TransR": 2, "TransD": 3}
@@ -109,6 +109,7 @@ _SIGS = {
     "okb_prof_enable": (_int, [_vp, _int]),
     "okb_prof_read": (_int, [_vp, _int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "okb_debug_cuda_error": (C.c_char_p, []),
+    "okb_debug_dp_trace": (_int, [_vp, _vp]),
     "okb_launch_count": (_i64, []),
 }
 

@@ -78,6 +78,15 @@ int okb_set_flag(okb_ctx *c, int flag, INT value) {
     if (flag == OKB_FLAG_DP_PULL) { c->dp_pull = value != 0; return 0; }
     if (flag == OKB_FLAG_CHUNK_KERNEL) { c->chunk_kernel = value != 0; return 0; }
     if (flag == OKB_FLAG_TRANSR_FUSED) { c->transr_fused = value != 0; return 0; }
+    if (flag == OKB_FLAG_DP_HANDSHAKE) { c->dp_hs_mode = (int)value & 3; return 0; }
+    if (flag == OKB_FLAG_DP_TRACE) {
+        c->dp_trace_on = value != 0;
+        if (c->dp_trace_on) {
+            if (c->dp_trace.ensure(64 * 16 * 8)) OKB_FAIL(c, OKB_ERR_CUDA, "out of device memory");
+            OKB_CUDA(c, cudaMemset(c->dp_trace.p, 0xff, 64 * 16 * 8));
+        }
+        return 0;
+    }
     if (flag == OKB_FLAG_ADAM_VPT) { if (value < 1 || value > 4) OKB_FAIL(c, OKB_ERR_ARG, "vectors per thread: 1..4"); c->adam_vpt = (int)value; return 0; }
     OKB_FAIL(c, OKB_ERR_ARG, "unknown flag");
 }
@@ -97,6 +106,14 @@ int okb_prof_read(okb_ctx *c, int id, double *total_ms, INT *count) {
     v.clear();
     if (total_ms) *total_ms = tot;
     if (count) *count = n;
+    return 0;
+}
+// debugging aid: the stamps of OKB_FLAG_DP_TRACE (64 steps x 16 u64, indexed by epoch % 64), then cleared
+int okb_debug_dp_trace(okb_ctx *c, unsigned long long *out) {
+    if (!c->dp_trace.p) OKB_FAIL(c, OKB_ERR_STATE, "set OKB_FLAG_DP_TRACE first");
+    OKB_CUDA(c, cudaDeviceSynchronize());
+    OKB_CUDA(c, cudaMemcpy(out, c->dp_trace.p, 64 * 16 * 8, cudaMemcpyDeviceToHost));
+    OKB_CUDA(c, cudaMemset(c->dp_trace.p, 0xff, 64 * 16 * 8));
     return 0;
 }
 // debugging aid: returns (and clears) the CUDA runtime's last error of this library's runtime instance

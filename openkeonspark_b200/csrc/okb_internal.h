@@ -101,6 +101,10 @@ struct okb_ctx {
     okb_dp dp = {};                   // owner-sharded data parallelism (okb_dp_attach)
     bool dp_on = false;
     unsigned long long dp_epoch = 0;
+    DevBuf dp_trace;                  // OKB_FLAG_DP_TRACE: [64 steps][16] globaltimer stamps of the data-parallel kernels (debugging aid)
+    bool dp_trace_on = false;
+    int dp_hs_mode = 2;               // OKB_FLAG_DP_HANDSHAKE: see GradArgs::hs_mode (2 measured fastest: 42.4 -> 39.2 us per step at 2 GPUs)
+    unsigned long long hub_done = 0;  // value OKB_FLAGS_HUBCTR will have reached when every launch issued so far has finished
     bool dp_pull = false;             // OKB_FLAG_DP_PULL: row owners pull partial rows from their peers instead of the reduce+push kernel
     PlanSlot alt;                     // prefetched chunk (okb_chunk_prefetch)
     bool alt_ready = false, in_prefetch = false;
@@ -187,9 +191,10 @@ i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(
 
 // okb_ctx::flags, in 4-byte words: [0,64) partial loss sums | [64] loss ticket | [68] "bad id" flag of the host-batch path
 //   | [72] arrival counter of the persistent chunk kernel's grid barrier
-#define OKB_FLAGS_BYTES (sizeof(float) * 64 + 64)
+#define OKB_FLAGS_BYTES (sizeof(float) * 64 + 128)
 #define OKB_FLAGS_BAD 68
 #define OKB_FLAGS_GRIDBAR 72
+#define OKB_FLAGS_HUBCTR 76    // u64 (byte 304): hub blocks finished since the context was created (scatter-form owner update)
 int okb_ensure_flags(okb_ctx *c, cudaStream_t s);     // train.cu: allocate + zero once
 
 extern "C" int okb_verify_flush(okb_ctx *c, void *stream);       // sampler.cu: launch a pending comparison stand-alone

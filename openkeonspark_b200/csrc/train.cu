@@ -620,6 +620,7 @@ void okb_fill_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
     a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi; a.slot_base = (i32)slot_base;
     a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_n = 0; a.npf = 0;
     a.vh = nullptr; a.vflag = nullptr; a.vS = 0; a.vblocks = 0;
+    a.sc_world = 0; a.trace = nullptr; a.hs_mode = c->dp_hs_mode;
 }
 // warps per positive the generic grad kernel uses for this batch (1 = one warp per positive); a function of the GLOBAL
 // batch, so that a data-parallel rank's slice is computed exactly like the same positives on one GPU
@@ -655,6 +656,15 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     if (wait_flags)
         for (int q = 0; q < wait_n; q++)
             a.announce[q] = (unsigned long long *)((char *)c->dp.arena[q] + c->dp.off_flags) + DP_FLAG_X + c->dp.rank;
+    if (wait_flags && c->dp.scatter) {                     // gradient rows go to their table rows' owners (global slots)
+        const okb_dp &P = c->dp;
+        const i64 own_e = (c->E + P.world - 1) / P.world, own_r = (c->R + P.world - 1) / P.world;
+        a.sc_world = P.world;
+        for (int q = 0; q < P.world; q++) a.sc_arena[q] = (char *)P.arena[q];
+        for (int q = 0; q <= P.world; q++) { a.sc_ent_lo[q] = (i32)std::min<i64>(c->E, q * own_e); a.sc_rel_lo[q] = (i32)std::min<i64>(c->R, q * own_r); }
+        a.sc_gent = P.off_gent; a.sc_grel = P.off_grel; a.sc_loss = P.off_loss;
+    }
+    if (wait_flags && c->dp_trace_on) a.trace = c->dp_trace.as<unsigned long long>() + ((wait_epoch + 1) % 64) * 16;
     const unsigned grid = (unsigned)((b_hi - b_lo + GRAD_WARPS - 1) / GRAD_WARPS);
     a.npf = 0;
     if (m->optimizer == OKB_ADAM && c->l2_prefetch && m->m_ent) {
@@ -924,6 +934,8 @@ struct DpPush {
     i32 ent_lo[OKB_DP_MAX + 1], rel_lo[OKB_DP_MAX + 1];
     i32 own_max_ent, own_max_rel, world, rank, Bl;
     unsigned long long epoch;
+    unsigned long long *trace;
+    i32 hs_mode;
 };
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -938,10 +950,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 // every peer's flag word, then every block waits (acquire) until all ranks have announced the same epoch.  No fences
 // or tickets inside the producing kernels.
 __device__ __forceinline__ void dp_announce_and_wait(char *const *arena, i64 off_flags, int world, int rank, int which,
-                                                     unsigned long long epoch, bool announce) {
+                                                     unsigned long long epoch, bool announce, int hs_mode = 0) {
     if ((int)threadIdx.x < world) {
-        if (announce) st_release_sys((unsigned long long *)(arena[threadIdx.x] + off_flags) + which + rank, epoch);
-        spin_until((const unsigned long long *)(arena[rank] + off_flags) + which + threadIdx.x, epoch);
+        if (announce) st_flag_sys((unsigned long long *)(arena[threadIdx.x] + off_flags) + which + rank, epoch, hs_mode & 2);
+        spin_until((const unsigned long long *)(arena[rank] + off_flags) + which + threadIdx.x, epoch, hs_mode & 1);
     }
     __syncthreads();
 }
@@ -951,6 +963,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) dp_reduce_push_kernel(Up
     constexpr int N = VW * NV;
     const int lane = threadIdx.x & 31;
     pdl_launch_dependents();
+    if (threadIdx.x == 0) trace_min(d.trace, 10);
     if ((i32)blockIdx.x >= a.work_blocks) {                // the extra block: this rank's hinge sum, in a fixed order
         __shared__ float sh[WARPS_PER_BLOCK];
         pdl_wait();
@@ -980,6 +993,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) dp_reduce_push_kernel(Up
             const int4 seg = __ldg(a.rowhead + key);
             const int parts = cols / D;
             pdl_wait();                                    // the grad kernel's rows are complete from here on
+            if (threadIdx.x == 0) trace_min(d.trace, 11);
             for (int p = 0; p < parts; p++) {
                 Frag<VW, NV> f;
                 f.zero();
@@ -987,6 +1001,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) dp_reduce_push_kernel(Up
                 f.store(dst + p * D, D, lane);
             }
         }
+        if (threadIdx.x == 0) trace_max(d.trace, 12);
     }
 }
 
@@ -1007,6 +1022,8 @@ struct DpOwn {
     unsigned long long epoch;
     float *loss_out;
     float w;
+    unsigned long long *trace;
+    i32 hs_mode;
 };
 // One 256-vector tile of ONE table's owned rows per CTA (block-uniform table, multiply-high row split — the lean form of
 // adam_tile_kernel): x / m / v of the tile are requested BEFORE the wait for this rank's push kernel and for the peers'
@@ -1032,8 +1049,11 @@ __global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
         xv = *reinterpret_cast<const V *>(own + T.x_off + e * 4);
         if (d.adam) { mv = *reinterpret_cast<const V *>(T.m + e); vv = *reinterpret_cast<const V *>(T.v + e); }
     }
+    if (threadIdx.x == 0) trace_min(d.trace, 5);
     pdl_wait();                                            // this rank's reduce+push kernel is complete: announce it
-    dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, blockIdx.x == 0);
+    if (threadIdx.x == 0) trace_min(d.trace, 6);
+    dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, blockIdx.x == 0, d.hs_mode);
+    if (threadIdx.x == 0) trace_min(d.trace, 7);
     if (blockIdx.x == 0 && threadIdx.x == 0 && d.loss_out) {   // mean hinge over the GLOBAL batch, rank order
         const volatile float *lp = (const volatile float *)((unsigned long long *)(d.arena[d.rank] + d.off_flags) + DP_FLAG_LOSS);
         float tot = 0.f;
@@ -1072,6 +1092,7 @@ __global__ void __launch_bounds__(256) dp_owner_kernel(DpOwn d) {
         for (int q = 0; q < VW; q++) xs[q] -= lr * g[q];
     }
     for (int p = 0; p < d.world; p++) *reinterpret_cast<V *>(d.arena[p] + T.x_off + e * 4) = xv;
+    if (threadIdx.x == 0) trace_max(d.trace, 9);
 }
 
 // End of a library call: publish "my owner-update kernels up to `epoch` are complete" without waiting for the next step's
@@ -1206,6 +1227,128 @@ __global__ void __launch_bounds__(256) dp_pull_kernel(DpPull d) {
     }
 }
 
+// ---- "scatter" form: the step is the single-GPU pair of kernels.  Every rank samples and plans the GLOBAL batch (integer
+// work, identical everywhere), computes the positives of its own streams and its grad kernel stores each gradient row
+// straight into the arena of the rank that owns the row's table row, at the row's slot of the global batch (grad_dst_ent /
+// grad_dst_rel in train_dev.cuh) — the reduce-scatter is those peer stores, there is no reduce+push kernel and no staging
+// slab.  The owner then runs the single-GPU update over ITS rows: same row map, same slots, same ascending-slot fp32 order,
+// so the tables are bit-identical to one GPU training the global batch; the new row goes to every rank's table (peer
+// stores: the all-gather).  Hinge terms are stored into every rank's loss buffer, so each rank reduces the global loss in
+// the single-GPU order too.
+struct DpSc {
+    char *arena[OKB_DP_MAX];
+    i64 delta[OKB_DP_MAX];     // arena[p] - arena[rank]: rank p's copy of a local table element
+    i64 off_flags;
+    i32 world, rank, adam;
+    i32 ent_lo, ent_hi, rel_lo, rel_hi;                    // owned rows
+    unsigned long long epoch;
+    // hub rows: `hub_blocks` CTAs in front of the tiles pre-reduce the PCH-blocks of this rank's long segments (what
+    // prereduce_kernel does on one GPU) and count themselves off in *hub_ctr; a tile thread whose row has a long segment
+    // waits until the counter has reached hub_target before it reads the block sums
+    unsigned long long *hub_ctr, hub_target;
+    i32 hub_blocks;
+    unsigned long long *trace;
+    i32 hs_mode;
+};
+__device__ __forceinline__ bool dp_owns_key(const UpdArgs &a, const DpSc &d, i32 key) {
+    return key < a.E ? (key >= d.ent_lo && key < d.ent_hi) : (key - a.E >= d.rel_lo && key - a.E < d.rel_hi);
+}
+// One 256-vector tile of ONE table's owned rows per CTA (a.tab[] describes the owned ranges); the loss blocks come first.
+// Row map, x / m / v are requested before the waits (nobody but this owner writes them).
+template <int VW>
+__global__ void __launch_bounds__(256, 4) dp_scatter_update_kernel(UpdArgs a, DpSc d) {
+    typedef typename VecT<VW>::T V;
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) trace_min(d.trace, 5);
+    const i32 hid = (i32)blockIdx.x - a.loss_blocks;       // loss blocks, then hub blocks, then the tiles
+    if (hid >= 0 && hid < d.hub_blocks) {
+        pdl_wait();
+        dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, false, d.hs_mode);
+        // one warp per PCH-block of sorted positions; same additions in the same order as prereduce_body
+        const i32 w = hid * 8 + (i32)(threadIdx.x >> 5), lo = w * PCH, lane = threadIdx.x & 31;
+        if (lo + PCH <= a.n) {
+            const i32 key = a.skeys[lo];
+            if (key < a.key_limit && dp_owns_key(a, d, key) && a.skeys[lo + PCH - 1] == key) {
+                const bool is_ent = key < a.E;
+                const i32 cols = is_ent ? a.ce : a.cr;
+                const float *gb = is_ent ? a.gent : a.grel - (i64)a.n_ent_slots * a.cr;
+                i32 slot[PCH];
+#pragma unroll
+                for (int j = 0; j < PCH; j++) slot[j] = __ldg(a.perm + lo + j);
+                for (i32 v = lane * VW; v < cols; v += 32 * VW) {
+                    V r[PCH];
+#pragma unroll
+                    for (int j = 0; j < PCH; j++) r[j] = __ldcg(reinterpret_cast<const V *>(gb + (i64)slot[j] * cols + v));
+                    V acc;
+                    float *pa = reinterpret_cast<float *>(&acc);
+#pragma unroll
+                    for (int q = 0; q < VW; q++) pa[q] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < PCH; j++)
+#pragma unroll
+                        for (int q = 0; q < VW; q++) pa[q] += reinterpret_cast<const float *>(&r[j])[q];
+                    *reinterpret_cast<V *>(const_cast<float *>(a.partial) + (i64)w * a.pcols + v) = acc;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(d.hub_ctr, 1ull); trace_max(d.trace, 8); }
+        return;
+    }
+    const i32 bid = hid < 0 ? -1 : hid - d.hub_blocks;
+    int t = 0;
+    if (bid >= 0) while (bid >= a.tab[t].blk_end) t++;     // block-uniform
+    const DenseTab &T = a.tab[t];
+    bool live = false;
+    unsigned lv = 0, col = 0;
+    int4 seg = make_int4(-1, 0, 0, 0);
+    V xv, mv, vv;
+    if (bid >= 0) {
+        const unsigned nvec = (unsigned)(T.vec_end - (t ? a.tab[t - 1].vec_end : 0));
+        lv = ((unsigned)bid - (unsigned)(t ? a.tab[t - 1].blk_end : 0)) * 256u + threadIdx.x;
+        live = lv < nvec;
+        if (live) {
+            const unsigned vpr = (unsigned)T.D / VW;
+            const unsigned row = T.magic ? (__umulhi(lv, T.magic) >> T.shift) : (lv >> T.shift);
+            col = (lv - row * vpr) * VW;
+            seg = __ldg(a.rowhead + T.key_off + row);
+            const size_t e = (size_t)lv * VW;
+            if (d.adam || seg.x >= 0) xv = *reinterpret_cast<const V *>(T.x + e);
+            if (d.adam) { mv = *reinterpret_cast<const V *>(T.m + e); vv = *reinterpret_cast<const V *>(T.v + e); }
+        }
+    }
+    pdl_wait();                                            // this rank's grad kernel is complete: announce it
+    if (threadIdx.x == 0) trace_min(d.trace, 6);
+    dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, blockIdx.x == 0, d.hs_mode);
+    if (threadIdx.x == 0) trace_min(d.trace, 7);
+    // the loss is summed by as many threads as the single-GPU kernel of this optimizer has (sgd_kernel: 128): same fp32 order
+    if (bid < 0) { loss_block(a, (i32)blockIdx.x, d.adam ? (i32)blockDim.x : WARPS_PER_BLOCK * 32); return; }
+    if (!live || (!d.adam && seg.x < 0)) return;           // SGD leaves rows without gradient untouched
+    float g[VW];
+#pragma unroll
+    for (int q = 0; q < VW; q++) g[q] = 0.f;
+    if (a.hub && seg.x >= 0 && seg.y - seg.x > PCH && (seg.x + PCH - 1) / PCH < seg.y / PCH) {     // long segment: block sums ready?
+        unsigned long long seen;
+        do { asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(d.hub_ctr) : "memory"); } while (seen < d.hub_target);
+    }
+    adam_gsum<VW, true>(a, T, seg, col, g);                // peers wrote these rows: coherent loads
+    const size_t e = (size_t)lv * VW;
+    float *xs = reinterpret_cast<float *>(&xv);
+    if (d.adam) {
+        const float b1 = a.hp.beta1, b2 = a.hp.beta2;
+        float *ms = reinterpret_cast<float *>(&mv), *vs = reinterpret_cast<float *>(&vv);
+#pragma unroll
+        for (int q = 0; q < VW; q++) adam_elem(xs[q], ms[q], vs[q], g[q], b1, b2, 1.f - b1, 1.f - b2, a.hp.lr, a.hp.eps);
+        *reinterpret_cast<V *>(T.m + e) = mv; *reinterpret_cast<V *>(T.v + e) = vv;
+    } else {
+#pragma unroll
+        for (int q = 0; q < VW; q++) xs[q] -= a.hp.lr * g[q];
+    }
+    char *xp = reinterpret_cast<char *>(T.x + e);
+    for (int p = 0; p < d.world; p++) *reinterpret_cast<V *>(xp + d.delta[p]) = xv;
+    if (threadIdx.x == 0) trace_max(d.trace, 9);
+}
+
 static void fill_upd_args(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, const float *gent, const float *grel,
                           const float *loss_terms, UpdArgs &a) {
     const i64 n = c->plan_ne + c->plan_nr, total = (c->plan_hi - c->plan_lo) * n, rel = (step - c->plan_lo) * n;
@@ -1222,6 +1365,94 @@ static void fill_upd_args(okb_ctx *c, const okb_model *m, const okb_hyper *hp, I
     a.hub = (double)c->plan_ne * c->max_ent_share > PCH || (double)c->plan_nr * c->max_rel_share > PCH;
     a.partial = nullptr; a.by_row = 1; a.loss_blocks = 1;
     a.loss_part = nullptr; a.loss_ctr = nullptr; a.bad = nullptr;
+}
+
+// n steps of the scatter form (see DpSc): per step  grad (peer stores of the gradient rows)  ->  [hub pre-reduction]  ->
+// owner update (peer stores of the new rows); two flag exchanges per step, riding on the kernel boundaries
+static int dp_scatter_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step_lo, INT n, float *loss_out, int vw, int nv,
+                            cudaStream_t s) {
+    const okb_dp &P = c->dp;
+    int rc;
+    if (P.off_gent < 0 || P.off_grel < 0 || P.off_loss < 0) OKB_FAIL(c, OKB_ERR_ARG, "arena has no receive buffers (okb_dp_layout with scatter = 1)");
+    if (P.global_batch != c->B || P.neg_ent != c->K || P.neg_rel != c->KR) OKB_FAIL(c, OKB_ERR_ARG, "sampled batch does not match the arena's receive buffers");
+    if (!planned(c, step_lo, step_lo + n, 0, c->B)) {      // the GLOBAL batch, like one GPU would plan it
+        if ((rc = plan_steps(c, step_lo, c->steps, 0, c->B, s))) return rc;
+    }
+    char *own = (char *)P.arena[P.rank];
+    float *gent = (float *)(own + P.off_gent), *grel = (float *)(own + P.off_grel), *lterms = (float *)(own + P.off_loss);
+    cudaLaunchAttribute pat[1];
+    pat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pat[0].val.programmaticStreamSerializationAllowed = 1;
+    const i64 own_e = (c->E + P.world - 1) / P.world, own_r = (c->R + P.world - 1) / P.world;
+    DpSc d;
+    for (int q = 0; q < OKB_DP_MAX; q++) {
+        d.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
+        d.delta[q] = q < P.world ? (i64)((char *)P.arena[q] - own) : 0;
+    }
+    d.off_flags = P.off_flags; d.world = P.world; d.rank = P.rank; d.adam = m->optimizer == OKB_ADAM;
+    d.ent_lo = (i32)std::min<i64>(c->E, P.rank * own_e); d.ent_hi = (i32)std::min<i64>(c->E, (P.rank + 1) * own_e);
+    d.rel_lo = (i32)std::min<i64>(c->R, P.rank * own_r); d.rel_hi = (i32)std::min<i64>(c->R, (P.rank + 1) * own_r);
+    const unsigned long long *xflags = (const unsigned long long *)(own + P.off_flags) + DP_FLAG_X;
+    for (INT i = 0; i < n; i++) {
+        const INT step = step_lo + i;
+        d.epoch = c->dp_epoch + 1;
+        if ((rc = launch_grad(c, m, hp + i, step, P.b_lo, P.b_hi, 0, gent, grel, lterms, xflags, c->dp_epoch, P.world, s))) return rc;
+        UpdArgs a;
+        i32 blk = 0;
+        bool lean = true;
+        if ((rc = okb_fill_update(c, m, hp + i, step, gent, grel, lterms, loss_out ? loss_out + i : nullptr, vw, s, a, blk, lean))) return rc;
+        a.ntab = 0;                                        // the table list: this rank's rows only
+        i64 acc = 0;
+        i32 oblk = 0;
+        auto add = [&](float *x, float *mm, float *vv, bool is_ent, int part) {
+            if (!x) return;
+            const int D = is_ent ? m->ent_dim : m->rel_dim;
+            const i64 lo = is_ent ? d.ent_lo : d.rel_lo, hi = is_ent ? d.ent_hi : d.rel_hi;
+            acc += (hi - lo) * D / vw;
+            oblk += (i32)(((hi - lo) * D / vw + 255) / 256);
+            DenseTab T = {};
+            T.x = x + lo * D; T.m = mm ? mm + lo * D : nullptr; T.v = vv ? vv + lo * D : nullptr;
+            T.grad = is_ent ? gent : grel; T.vec_end = acc; T.D = D;
+            T.key_off = (i32)((is_ent ? 0 : c->E) + lo); T.cols = is_ent ? a.ce : a.cr; T.part = part;
+            T.slot_off = is_ent ? 0 : (i32)c->plan_ne; T.blk_end = oblk; T.sblk_end = oblk;
+            const unsigned vpr = (unsigned)(D / vw);
+            unsigned sh = 0;
+            while ((2u << sh) <= vpr) sh++;
+            if ((1u << sh) == vpr) { T.magic = 0; T.shift = sh; }
+            else { T.magic = (unsigned)((((unsigned long long)1 << (32 + sh)) + vpr - 1) / vpr); T.shift = sh; }
+            a.tab[a.ntab++] = T;
+        };
+        add(m->ent, m->m_ent, m->v_ent, true, 0);
+        if (m->model == OKB_TRANSD) add(m->ent_aux, m->m_ent_aux, m->v_ent_aux, true, 1);
+        add(m->rel, m->m_rel, m->v_rel, false, 0);
+        if (m->model != OKB_TRANSE) add(m->rel_aux, m->m_rel_aux, m->v_rel_aux, false, 1);
+        if (oblk == 0) a.tab[0].blk_end = 1;               // owns no rows: the loss blocks still take part in the flag exchange
+        d.hub_blocks = a.hub ? (i32)((a.n / PCH + 7) / 8) : 0;
+        d.hub_ctr = (unsigned long long *)(c->flags.as<unsigned>() + OKB_FLAGS_HUBCTR);
+        c->hub_done += (unsigned long long)d.hub_blocks;
+        d.hub_target = c->hub_done;
+        d.hs_mode = c->dp_hs_mode;
+        d.trace = c->dp_trace_on ? c->dp_trace.as<unsigned long long>() + (d.epoch % 64) * 16 : nullptr;
+        {
+            ProfScope po(c, PROF_DP_OWNER, s);
+            cudaLaunchConfig_t oc = {};
+            oc.gridDim = dim3((unsigned)(oblk + a.loss_blocks + d.hub_blocks)); oc.blockDim = dim3(256); oc.stream = s; oc.attrs = pat; oc.numAttrs = c->pdl ? 1 : 0;
+            if (vw == 4) cudaLaunchKernelEx(&oc, dp_scatter_update_kernel<4>, a, d);
+            else if (vw == 2) cudaLaunchKernelEx(&oc, dp_scatter_update_kernel<2>, a, d);
+            else cudaLaunchKernelEx(&oc, dp_scatter_update_kernel<1>, a, d);
+        }
+        OKB_LAUNCHED(1);
+        c->dp_epoch = d.epoch;
+    }
+    {
+        DpPush e;
+        for (int q = 0; q < OKB_DP_MAX; q++) e.arena[q] = q < P.world ? (char *)P.arena[q] : nullptr;
+        e.off_flags = P.off_flags; e.world = P.world; e.rank = P.rank; e.epoch = c->dp_epoch;
+        dp_announce_kernel<<<1, 32, 0, s>>>(e);
+        OKB_LAUNCHED(1);
+    }
+    OKB_CUDA(c, cudaGetLastError());
+    return 0;
 }
 
 extern "C" {
@@ -1269,10 +1500,20 @@ int okb_dp_layout(okb_ctx *c, const okb_model *m, INT world, okb_dp *out) {
     out->off_rel = take(tb_r);
     out->off_rel_aux = m->model != OKB_TRANSE ? take(tb_r) : -1;
     const i64 own_e = (c->E + world - 1) / world, own_r = (c->R + world - 1) / world;
-    out->off_stage_ent = take(world * own_e * ce * 4);
-    out->off_stage_rel = take(world * own_r * cr * 4);
+    out->off_stage_ent = out->off_stage_rel = -1;
+    if (!out->scatter) {
+        out->off_stage_ent = take(world * own_e * ce * 4);
+        out->off_stage_rel = take(world * own_r * cr * 4);
+    }
     out->off_flags = take(DP_FLAG_BYTES);
     out->off_rowhead = out->off_perm = out->off_gent = out->off_grel = out->off_loss = out->off_partial = -1;
+    if (out->scatter) {                                    // scatter form: receive buffers for the gradient rows of the GLOBAL batch
+        if (out->global_batch < 1 || out->neg_ent < 0 || out->neg_rel < 0) OKB_FAIL(c, OKB_ERR_ARG, "scatter form needs global_batch, neg_ent, neg_rel");
+        out->off_gent = take(out->global_batch * (2 + out->neg_ent) * ce * 4);
+        out->off_grel = take(out->global_batch * (1 + out->neg_rel) * cr * 4);
+        out->off_loss = take(out->global_batch * 4);
+        out->plan_steps = 0;
+    }
     if (out->plan_steps > 0 && out->max_local > 0) {       // pull form: plan, gradient rows and loss terms in the arena too
         const i64 NE = 2 + out->neg_ent, NR = 1 + out->neg_rel, Bl = out->max_local;
         out->off_rowhead = take(out->plan_steps * (c->E + c->R) * (i64)sizeof(int4));
@@ -1300,6 +1541,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         (m->ent_aux && (char *)m->ent_aux != own + P.off_ent_aux) || (m->rel_aux && (char *)m->rel_aux != own + P.off_rel_aux))
         OKB_FAIL(c, OKB_ERR_ARG, "model tables must live in this rank's peer arena at the okb_dp_layout offsets");
     cudaStream_t s = (cudaStream_t)stream;
+    if (P.scatter) return dp_scatter_steps(c, m, hp, step_lo, n, loss_out, vw, nv, s);
     const i64 Bl = P.b_hi - P.b_lo;
     INT er, ec, rr, rcn;
     if ((rc = okb_grad_sizes(c, m, Bl, c->K, c->KR, &er, &ec, &rr, &rcn))) return rc;
@@ -1393,6 +1635,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
         d.off_stage_ent = P.off_stage_ent; d.off_stage_rel = P.off_stage_rel; d.off_flags = P.off_flags;
         for (int q = 0; q <= P.world; q++) { d.ent_lo[q] = (i32)std::min<i64>(c->E, q * own_e); d.rel_lo[q] = (i32)std::min<i64>(c->R, q * own_r); }
         d.own_max_ent = (i32)own_e; d.own_max_rel = (i32)own_r; d.world = P.world; d.rank = P.rank; d.Bl = (i32)Bl; d.epoch = epoch;
+        d.trace = c->dp_trace_on ? c->dp_trace.as<unsigned long long>() + (epoch % 64) * 16 : nullptr; d.hs_mode = c->dp_hs_mode;
         a.work_blocks = (i32)((a.key_limit + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
         {
             ProfScope ps(c, PROF_UPDATE, s);
@@ -1408,6 +1651,7 @@ int okb_dp_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
             o.off_flags = P.off_flags; o.world = P.world; o.rank = P.rank; o.adam = m->optimizer == OKB_ADAM; o.epoch = epoch;
             o.loss_out = loss_out ? loss_out + i : nullptr;
             o.w = 1.0f / (float)(c->B * (c->K + c->KR));
+            o.trace = d.trace; o.hs_mode = c->dp_hs_mode;
             o.ntab = 0;
             i64 acc = 0;
             i32 oblk = 0;

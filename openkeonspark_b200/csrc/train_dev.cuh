@@ -17,12 +17,14 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // Spin until a peer's flag word reaches `epoch` (acquire, system scope).  A peer that died would otherwise hang this GPU
 // for good: after ~20 s without progress the kernel traps, which surfaces as a CUDA error in the host process.
-__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long epoch) {
+// mode 1: relaxed polls and ONE acquire fence once the value has arrived (instead of an acquire per poll)
+__device__ __forceinline__ void spin_until(const unsigned long long *flag, unsigned long long epoch, int mode = 0) {
     unsigned long long v, t0 = 0;
     unsigned polls = 0;
     for (;;) {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-        if (v >= epoch) return;
+        if (mode) asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        else asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= epoch) { if (mode) asm volatile("fence.acq_rel.sys;" ::: "memory"); return; }
         if ((++polls & 0x3ffu) == 0u) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -31,6 +33,10 @@ __device__ __forceinline__ void spin_until(const unsigned long long *flag, unsig
         }
     }
 }
+// OKB_FLAG_DP_TRACE: phase stamps of the data-parallel kernels (tr = nullptr: off).  "max" slots keep the complement.
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_min(unsigned long long *tr, int slot) { if (tr) atomicMin(tr + slot, gtimer()); }
+__device__ __forceinline__ void trace_max(unsigned long long *tr, int slot) { if (tr) atomicMin(tr + slot, ~gtimer()); }
 #define WARPS_PER_BLOCK 4
 #define PCH 8                  // long segments (> PCH rows) are pre-reduced in fixed chunks of PCH sorted positions
 // grad kernel: one warp per block so that residency is quantised in single warps: <= 120 registers
@@ -343,7 +349,41 @@ struct GradArgs {
     const long long *vh;
     unsigned *vflag;
     i32 vS, vblocks;
+    // scatter form of the owner-sharded data-parallel step (sc_world > 0): every gradient row is stored straight into the
+    // arena of the rank that OWNS its table row, at the row's slot of the GLOBAL batch, and the hinge term into every
+    // rank's loss buffer — the reduce-scatter of the step is these peer stores (train.cu, "data parallel")
+    char *sc_arena[OKB_DP_MAX];
+    i64 sc_gent, sc_grel, sc_loss;                         // byte offsets of the receive buffers inside an arena
+    i32 sc_ent_lo[OKB_DP_MAX + 1], sc_rel_lo[OKB_DP_MAX + 1];
+    i32 sc_world;
+    unsigned long long *trace;
+    i32 hs_mode;               // flag handshake: 0 = release store / acquire polls, bit 0 = relaxed polls + one fence, bit 1 = relaxed store
 };
+__device__ __forceinline__ void st_flag_sys(unsigned long long *p, unsigned long long v, int relaxed) {
+    if (relaxed) asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    else asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// destination of the gradient row in global slot `slot` whose table row is entity / relation `id` (id < 0: the slot is not
+// part of any segment — a negative equal to its positive — and nothing is stored)
+__device__ __forceinline__ float *grad_dst_ent(const GradArgs &a, i32 id, i64 slot, int ce) {
+    if (!a.sc_world) return a.gent + slot * ce;
+    if (id < 0) return nullptr;
+    int o = 0;
+    while (id >= a.sc_ent_lo[o + 1]) o++;
+    return reinterpret_cast<float *>(a.sc_arena[o] + a.sc_gent) + slot * ce;
+}
+__device__ __forceinline__ float *grad_dst_rel(const GradArgs &a, i32 id, i64 slot, int cr) {
+    if (!a.sc_world) return a.grel + slot * cr;
+    if (id < 0) return nullptr;
+    int o = 0;
+    while (id >= a.sc_rel_lo[o + 1]) o++;
+    return reinterpret_cast<float *>(a.sc_arena[o] + a.sc_grel) + slot * cr;
+}
+__device__ __forceinline__ void grad_put_loss(const GradArgs &a, i32 b, float term, int lane) {
+    if (!a.sc_world) { if (lane == 0) a.loss_terms[b - a.slot_base] = term; return; }
+    term = __shfl_sync(FULL, term, 0);
+    if (lane < a.sc_world) reinterpret_cast<float *>(a.sc_arena[lane] + a.sc_loss)[b - a.slot_base] = term;
+}
 __device__ __forceinline__ void grad_verify_block(const GradArgs &a, i32 vb) {
     // one element per thread: every PCIe read of the launch is in flight at once (a loop per thread would serialise
     // round trips of ~2 us each)
@@ -377,7 +417,7 @@ __device__ __forceinline__ void grad_body(const GradArgs &a, i32 b, int lane, in
     EntG<MODEL, N> accH, accT;
     RelG<MODEL, N> accR;
     accH.zero(); accT.zero(); accR.zero();
-    float *ge = a.gent + (i64)(b - a.slot_base) * a.NE * ce, *gr = a.grel + (i64)(b - a.slot_base) * a.NR * cr;
+    const i64 es = (i64)(b - a.slot_base) * a.NE, rs = (i64)(b - a.slot_base) * a.NR;      // first entity / relation slot
     float hinge_sum = 0.f;
     i32 active = 0;
 
@@ -406,7 +446,7 @@ __device__ __forceinline__ void grad_body(const GradArgs &a, i32 b, int lane, in
             const float x = a.margin;
             if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rp, gp, -a.w, accH, accT, accR); }
         }
-        put_ent<MODEL, VW, NV>(ge + (i64)(2 + m) * ce, gnew, D, lane);
+        if (float *dst = grad_dst_ent(a, cnh != ph ? cnh : (cnt_ != pt ? cnt_ : -1), es + 2 + m, ce)) put_ent<MODEL, VW, NV>(dst, gnew, D, lane);
     }
     for (i32 m = 0; m < (wid == 0 ? a.kr : 0); m++) {      // relation negatives (Base.cpp:133-139): warp 0
         const i32 nr = a.br[b + (1 + a.k + m) * a.B];
@@ -432,7 +472,7 @@ __device__ __forceinline__ void grad_body(const GradArgs &a, i32 b, int lane, in
             const float x = a.margin;
             if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rp, gp, -a.w, accH, accT, accR); }
         }
-        put_rel<MODEL, VW, NV>(gr + (i64)(1 + m) * cr, gnew, D, lane);
+        if (float *dst = grad_dst_rel(a, nr != pr ? nr : -1, rs + 1 + m, cr)) put_rel<MODEL, VW, NV>(dst, gnew, D, lane);
     }
     if (WPPMAX > 1 && wpp > 1) {                           // warps 1.. hand their accumulators to warp 0, which adds them in warp order
         constexpr int F = 2 * (MODEL == OKB_TRANSD ? 2 : 1) + (MODEL == OKB_TRANSE ? 1 : 2);      // fragments per warp
@@ -467,10 +507,10 @@ __device__ __forceinline__ void grad_body(const GradArgs &a, i32 b, int lane, in
         }
     }
     if (active) score_bw<MODEL, N>(Hp, Tp, Rp, gp, a.w * (float)active, accH, accT, accR);
-    put_ent<MODEL, VW, NV>(ge, accH, D, lane);
-    put_ent<MODEL, VW, NV>(ge + ce, accT, D, lane);
-    put_rel<MODEL, VW, NV>(gr, accR, D, lane);
-    if (lane == 0) a.loss_terms[b - a.slot_base] = hinge_sum;
+    put_ent<MODEL, VW, NV>(grad_dst_ent(a, ph, es, ce), accH, D, lane);
+    put_ent<MODEL, VW, NV>(grad_dst_ent(a, pt, es + 1, ce), accT, D, lane);
+    put_rel<MODEL, VW, NV>(grad_dst_rel(a, pr, rs, cr), accR, D, lane);
+    grad_put_loss(a, b, hinge_sum, lane);
 }
 
 // WPPMAX = 1: one warp per positive (GRAD_WARPS positives per block).  WPPMAX = 4: ONE positive per block and blockDim / 32
@@ -492,18 +532,21 @@ __global__ void __launch_bounds__(WPPMAX == 1 ? GRAD_WARPS * 32 : WPPMAX * 32, W
     if (wid < a.k) { nh = a.bh[b + (wid + 1) * a.B]; nt = a.bt[b + (wid + 1) * a.B]; }
     // The batch ids do not depend on the previous update kernel; the table rows do.  Dependents (this step's update
     // kernel) are released only after the wait, so they can never start before the previous update has finished.
+    if (threadIdx.x == 0) trace_min(a.trace, 0);
     pdl_wait();
+    if (threadIdx.x == 0) trace_min(a.trace, 1);
     pdl_launch_dependents();
     if (a.wait_flags) {                                    // owner-sharded data parallelism: peers still publishing rows?
         if (lane < a.wait_n) {
             // this rank's previous owner-update kernel has completed (griddepcontrol.wait above): tell every peer, then
             // wait until every peer has said the same
             if (blockIdx.x == 0 && threadIdx.x < 32)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
-            spin_until(a.wait_flags + lane, a.wait_epoch);
+                st_flag_sys(a.announce[lane], a.wait_epoch, a.hs_mode & 2);
+            spin_until(a.wait_flags + lane, a.wait_epoch, a.hs_mode & 1);
         }
         __syncwarp();
     }
+    if (threadIdx.x == 0) { trace_min(a.trace, 2); trace_max(a.trace, 3); }
     if (lane < a.npf) {
         const unsigned off = (unsigned)(b - a.b_lo) * a.pf_slice[lane];
         if (off < a.pf_bytes[lane]) {
@@ -513,6 +556,7 @@ __global__ void __launch_bounds__(WPPMAX == 1 ? GRAD_WARPS * 32 : WPPMAX * 32, W
     }
 
     grad_body<MODEL, VW, NV, WPPMAX, false>(a, b, lane, wid, wpp, grad_sm, ph, pt, pr, nh, nt);
+    if (threadIdx.x == 0) trace_max(a.trace, 4);
 }
 
 // ------------------------------------------------------------------------------------------ grad, k = 1 specialisation
@@ -707,12 +751,12 @@ __device__ __forceinline__ void grad_k1_body(const GradArgs &a, i32 b, int lane,
             }
         }
     }
-    float *ge = a.gent + (i64)(b - a.slot_base) * a.NE * ce, *gr = a.grel + (i64)(b - a.slot_base) * a.NR * cr;
-    put_ent<MODEL, VW, NV>(ge, accH, D, lane);
-    put_ent<MODEL, VW, NV>(ge + ce, accT, D, lane);
-    put_ent<MODEL, VW, NV>(ge + 2 * (i64)ce, gnew, D, lane);
-    put_rel<MODEL, VW, NV>(gr, accR, D, lane);
-    if (lane == 0) a.loss_terms[b - a.slot_base] = active ? x : 0.f;
+    const i64 es = (i64)(b - a.slot_base) * a.NE, rs = (i64)(b - a.slot_base) * a.NR;
+    put_ent<MODEL, VW, NV>(grad_dst_ent(a, ph, es, ce), accH, D, lane);
+    put_ent<MODEL, VW, NV>(grad_dst_ent(a, pt, es + 1, ce), accT, D, lane);
+    if (float *dst = grad_dst_ent(a, nh != ph ? nh : (nt != pt ? nt : -1), es + 2, ce)) put_ent<MODEL, VW, NV>(dst, gnew, D, lane);
+    put_rel<MODEL, VW, NV>(grad_dst_rel(a, pr, rs, cr), accR, D, lane);
+    grad_put_loss(a, b, active ? x : 0.f, lane);
 }
 
 template <int MODEL, int VW, int NV>
@@ -723,17 +767,21 @@ __global__ void __launch_bounds__(32, GRAD1_MIN_BLOCKS) grad_k1_kernel(GradArgs 
     if (b >= a.b_hi) return;
     const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
     const i32 nh = a.bh[b + a.B], nt = a.bt[b + a.B];
+    if (lane == 0) trace_min(a.trace, 0);
     pdl_wait();
+    if (lane == 0) trace_min(a.trace, 1);
     pdl_launch_dependents();
     if (a.wait_flags) {                                    // owner-sharded data parallelism: see grad_kernel
         if (lane < a.wait_n) {
             if (blockIdx.x == 0)
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.announce[lane]), "l"(a.wait_epoch) : "memory");
-            spin_until(a.wait_flags + lane, a.wait_epoch);
+                st_flag_sys(a.announce[lane], a.wait_epoch, a.hs_mode & 2);
+            spin_until(a.wait_flags + lane, a.wait_epoch, a.hs_mode & 1);
         }
         __syncwarp();
     }
+    if (lane == 0) { trace_min(a.trace, 2); trace_max(a.trace, 3); }
     grad_k1_body<MODEL, VW, NV, false>(a, b, lane, ph, pt, pr, nh, nt);
+    if (lane == 0) trace_max(a.trace, 4);
 }
 
 // ------------------------------------------------------------------------------------------ update

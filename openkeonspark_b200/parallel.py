@@ -218,10 +218,20 @@ class OwnerSharded(DataParallel):
     """Owner-sharded synchronous data parallelism over peer memory (see the module docstring)."""
     mode = "owner"
 
-    def __init__(self, con, group=None, pull=None):
+    def __init__(self, con, group=None, pull=None, form=None):
         super().__init__(con, group)
         import os
         pull = os.environ.get("OKB200_DP_PULL") == "1" if pull is None else pull      # measured slower: A/B runs only
+        # form: "scatter" = the grad kernel stores gradient rows straight into their row owner's arena (two kernels per
+        # step, bit-identical to one GPU); "push" = per-rank partial sums through staging slabs (three kernels per step)
+        # default by world size: measured crossover (profiles/r02_dp_phase_traces.txt) — the scatter form's grad kernel slows
+        # down as the share of remote rows grows and its owner update pre-reduces the GLOBAL batch's long segments
+        form = os.environ.get("OKB200_DP_FORM", "scatter" if self.world <= 4 else "push") if form is None else form
+        if pull:
+            form = "pull"
+        if form not in ("scatter", "push", "pull"):
+            raise ValueError("form must be 'scatter', 'push' or 'pull'")
+        self.form = form
         from ._native import okb_dp
         from .Config import _AUX_ENT, _AUX_REL
         con._ensure_model()
@@ -236,6 +246,9 @@ class OwnerSharded(DataParallel):
             lay.plan_steps, lay.max_local = int(con.plan_ahead), int(self.chunk)
             lay.neg_ent, lay.neg_rel = int(con.negative_ent), int(con.negative_rel)
             con.ctx.call("okb_set_flag", 7, 1)
+        if form == "scatter":
+            lay.scatter, lay.global_batch = 1, int(con.batch_size)
+            lay.neg_ent, lay.neg_rel = int(con.negative_ent), int(con.negative_rel)
         con.ctx.call("okb_dp_layout", ctypes.byref(m), self.world, ctypes.byref(lay))
         own, handle = _vp(), (ctypes.c_ubyte * 64)()
         con.ctx.call("okb_peer_alloc", lay.arena_bytes, ctypes.byref(own), handle)
@@ -271,7 +284,8 @@ class OwnerSharded(DataParallel):
         lay.b_lo, lay.b_hi = self.ranges[self.rank]
         self._lay, self._own = lay, own.value
         per = con.workThreads // self.world
-        self.streams = (self.rank * per, (self.rank + 1) * per)
+        # scatter form: every rank samples (and plans) the global batch; the other forms only this rank's streams
+        self.streams = (0, con.workThreads) if form == "scatter" else (self.rank * per, (self.rank + 1) * per)
         con.ctx.call("okb_dp_attach", ctypes.byref(lay))
         torch.cuda.synchronize()
         dist.barrier(group=self.group)                # every arena initialised before anyone pushes into it
@@ -285,7 +299,7 @@ class OwnerSharded(DataParallel):
         """One train step; batches are sampled (this rank's streams only) and planned plan_ahead steps at a time."""
         from .Config import _stream
         if con._chunk_pos >= con._chunk_len:
-            n = con.batch_size * (3 + con.negative_ent + con.negative_rel) // self.world
+            n = con.batch_size * (3 + con.negative_ent + con.negative_rel) // (1 if self.form == "scatter" else self.world)
             self._sample(con, max(1, min(int(con.plan_ahead), (1 << 24) // max(n, 1))))
         m = con._cmodel()
         (hp,), powers = con._hypers(1)
@@ -348,7 +362,7 @@ class OwnerSharded(DataParallel):
         self._opened = []
 
 
-def attach(con, group=None, mode="auto", pull=None):
+def attach(con, group=None, mode="auto", pull=None, form=None):
     """Enable data-parallel mode on a Config whose init() has run (torch.distributed initialised).
     mode: "owner" (peer-memory owner-sharded update), "exact" (all-gather of gradient rows, bit-identical to one GPU),
     "auto" = owner on NCCL/GPU for TransE/H/D when the batch touches a sizeable share of the rows, else exact."""
@@ -368,5 +382,5 @@ def attach(con, group=None, mode="auto", pull=None):
             _, ranges = partition(con.batch_size, con.workThreads, dist.get_world_size(group))
             if dense and con.trainModel.name != "TransR" and all(hi > lo for lo, hi in ranges):    # every rank must own positives
                 mode = "owner"
-    con._world = OwnerSharded(con, group, pull) if mode == "owner" else DataParallel(con, group)
+    con._world = OwnerSharded(con, group, pull, form) if mode == "owner" else DataParallel(con, group)
     return con._world

@@ -19,7 +19,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def make(path, model, opt, W, dp, mode="exact"):
+def make(path, model, opt, W, dp, mode="exact", form=None):
     import openkeonspark_b200 as okb
     from openkeonspark_b200 import parallel
     from conftest import make_params
@@ -41,7 +41,7 @@ def make(path, model, opt, W, dp, mode="exact"):
     seeds = np.arange(1, W + 1, dtype=np.uint64) * np.uint64(7919)
     con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), W)
     if dp:
-        parallel.attach(con, mode=mode)
+        parallel.attach(con, mode=mode, form=form)
     return con
 
 
@@ -74,10 +74,37 @@ def main():
         assert np.array_equal(ra, rb), (model, rank)
         if rank == 0:
             print("dp%d %s/%s: tables and link-prediction records bit-identical to single GPU" % (world, model, opt))
-    # owner-sharded mode (peer-memory reduce/push + owner update): replicas bit-identical to EACH OTHER, and equal to the
-    # single-GPU run up to fp32 re-association of the per-row gradient sums
+    # owner-sharded mode, scatter form (the default: the grad kernel stores gradient rows into their row owner's arena, the
+    # owner runs the single-GPU update over its rows): losses and tables bit-identical to ONE GPU training the global batch,
+    # step by step and through the chunked entry point; zipf graph, so hub rows (pre-reduced long segments) are covered
+    for model, opt in (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam"), ("TransD", "SGD"), ("TransE", "Adam")):
+        a = make(d, model, opt, 8, True, mode="owner", form="scatter")
+        b = make(d, model, opt, 8, False)
+        assert a._world.mode == "owner" and a._world.form == "scatter"
+        a.plan_ahead = 6
+        for it in range(6):
+            la = float(a.next_step_device().item())
+            b.sampling_device()
+            lb = float(b.train_step_device(0).item())
+            assert la == lb, (model, opt, it, la, lb)
+        lc = a.train_chunk_device(5)
+        for it in range(5):
+            b.sampling_device()
+            lb = float(b.train_step_device(0).item())
+            assert float(lc[it]) == lb, (model, opt, "chunk", it, float(lc[it]), lb)
+        pa, pb = a.get_parameters(), b.get_parameters()
+        for k in pa:
+            assert np.array_equal(pa[k], pb[k]), (model, opt, k, rank, float(np.abs(pa[k] - pb[k]).max()))
+        ra = a._world.link_prediction(a).cpu().numpy()
+        rb = b.link_prediction_records().cpu().numpy()
+        assert np.array_equal(ra, rb), (model, opt, rank)
+        a._world.close(a)
+        if rank == 0:
+            print("dp%d owner-sharded scatter form %s/%s: losses, tables and link-prediction records bit-identical to single GPU" % (world, model, opt))
+    # owner-sharded mode, push form (peer-memory reduce/push + owner update): replicas bit-identical to EACH OTHER, and equal
+    # to the single-GPU run up to fp32 re-association of the per-row gradient sums
     for model, opt in (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam"), ("TransD", "SGD")):
-        a = make(d, model, opt, 8, True, mode="owner")
+        a = make(d, model, opt, 8, True, mode="owner", form="push")
         b = make(d, model, opt, 8, False)
         assert a._world.mode == "owner"
         a.plan_ahead = 6                              # sample exactly the 6 steps consumed below (streams stay aligned with b)
@@ -141,7 +168,7 @@ def main():
             seeds = np.arange(1, 9, dtype=np.uint64) * np.uint64(7919)
             a.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), 8)
             from openkeonspark_b200 import parallel
-            parallel.attach(a, mode="owner", pull=not push)
+            parallel.attach(a, mode="owner", pull=not push, form="push")
             a.plan_ahead = 4
             losses = [float(a.next_step_device().item()) for _ in range(4)] + [float(x) for x in a.train_chunk_device(4)]
             res.append((losses, a.get_parameters()))
