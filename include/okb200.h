@@ -270,6 +270,12 @@ int okb_transr_set_shard(okb_ctx *c, INT r_lo, INT r_hi);
  *      the streams first, so results never depend on prefetching. */
 int okb_chunk_begin(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, void *cuda_stream);
 int okb_chunk_prefetch(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, void *cuda_stream);
+/* the same pipeline under owner-sharded data parallelism (after okb_dp_attach): the chunk is sampled from the sampler streams
+ * [stream_lo, stream_hi) and planned over the positives this rank plans (its own; the global batch in the scatter form) */
+int okb_dp_chunk_begin(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, INT stream_lo, INT stream_hi,
+                       void *cuda_stream);
+int okb_dp_chunk_prefetch(okb_ctx *c, INT batch_size, INT neg_ent, INT neg_rel, INT steps, INT stream_lo, INT stream_hi,
+                          void *cuda_stream);
 
 /* ---- scoring = TransX.predict_def (TransE.py:53-58 ...).  h,t,r: device int64[n]; out: device
  *      float[n] (TransE: mean over d; others: sum).  Canonical evaluation order, see DESIGN.md. */

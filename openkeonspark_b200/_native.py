@@ -92,6 +92,8 @@ _SIGS = {
     "okb_transr_set_shard": (_int, [_vp, _i64, _i64]),
     "okb_chunk_begin": (_int, [_vp, _i64, _i64, _i64, _i64, _vp]),
     "okb_chunk_prefetch": (_int, [_vp, _i64, _i64, _i64, _i64, _vp]),
+    "okb_dp_chunk_begin": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp]),
+    "okb_dp_chunk_prefetch": (_int, [_vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp]),
     "okb_predict": (_int, [_vp, C.POINTER(okb_model), _vp, _vp, _vp, _i64, _vp, _vp]),
     "okb_rank": (_int, [_vp, C.POINTER(okb_model), _i64, _i64, _int, _i64, _i64, _vp, _vp, _vp]),
     "okb_rank_finalize": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),

@@ -1785,6 +1785,63 @@ int okb_chunk_prefetch(okb_ctx *c, INT B, INT k, INT kr, INT steps, void *stream
     return 0;
 }
 
+/* The same pipeline under owner-sharded data parallelism: the chunk is sampled from the sampler streams [stream_lo, stream_hi)
+ * (this rank's — or all of them in the scatter form) and planned over the positives the rank plans (its own; the global batch
+ * in the scatter form).  Not for the pull form, whose plan lives in the peer arena. */
+static void dp_plan_range(const okb_ctx *c, INT B, INT &lo, INT &hi) {
+    if (c->dp.scatter) { lo = 0; hi = B; } else { lo = c->dp.b_lo; hi = c->dp.b_hi; }
+}
+int okb_dp_chunk_begin(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT stream_hi, void *stream) {
+    if (!c->dp_on) OKB_FAIL(c, OKB_ERR_STATE, "okb_dp_attach first");
+    cudaStream_t s = (cudaStream_t)stream;
+    INT lo, hi;
+    dp_plan_range(c, B, lo, hi);
+    if (c->alt_ready && c->alt.B == B && c->alt.K == k && c->alt.KR == kr && c->alt.steps == steps && c->alt.plan_b_lo == lo &&
+        c->alt.plan_b_hi == hi && !c->rowseg_e.external) {
+        OKB_CUDA(c, cudaStreamWaitEvent(s, c->ev_side, 0));
+        swap_slot(c);
+        c->alt_ready = false;
+        return 0;
+    }
+    int rc = okb_discard_prefetch(c);
+    if (rc) return rc;
+    if ((rc = okb_sample(c, B, k, kr, steps, stream_lo, stream_hi, stream))) return rc;
+    if (c->rowseg_e.external) return 0;                    // pull form: okb_dp_train_steps plans into the arena
+    if ((rc = plan_steps(c, 0, steps, lo, hi, stream))) return rc;
+    return ensure_rowhead(c, s);
+}
+int okb_dp_chunk_prefetch(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_lo, INT stream_hi, void *stream) {
+    if (!c->dp_on || steps < 1 || c->rowseg_e.external) return 0;
+    int rc = okb_discard_prefetch(c);
+    if (rc) return rc;
+    if (!c->side) {
+        OKB_CUDA(c, cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+        OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
+        OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    }
+    if (!c->d_state_saved || c->saved_n != c->state.size()) {
+        if (c->d_state_saved) cudaFree(c->d_state_saved);
+        c->saved_n = c->state.size();
+        OKB_CUDA(c, cudaMalloc((void **)&c->d_state_saved, sizeof(u64) * std::max<size_t>(c->saved_n, 1)));
+    }
+    INT lo, hi;
+    dp_plan_range(c, B, lo, hi);
+    OKB_CUDA(c, cudaEventRecord(c->ev_main, (cudaStream_t)stream));
+    OKB_CUDA(c, cudaStreamWaitEvent(c->side, c->ev_main, 0));
+    OKB_CUDA(c, cudaMemcpyAsync(c->d_state_saved, c->d_state, sizeof(u64) * c->state.size(), cudaMemcpyDeviceToDevice, c->side));
+    swap_slot(c);
+    c->in_prefetch = true;
+    rc = okb_sample(c, B, k, kr, steps, stream_lo, stream_hi, c->side);
+    if (!rc) rc = plan_steps(c, 0, steps, lo, hi, c->side);
+    if (!rc) rc = ensure_rowhead(c, c->side);
+    c->in_prefetch = false;
+    swap_slot(c);
+    if (rc) return rc;
+    OKB_CUDA(c, cudaEventRecord(c->ev_side, c->side));
+    c->alt_ready = true;
+    return 0;
+}
+
 /* ---- peer memory: allocations other processes of the box map over NVLink (CUDA IPC) */
 int okb_peer_alloc(okb_ctx *c, INT bytes, void **ptr, unsigned char *handle64) {
     if (bytes <= 0 || !ptr || !handle64) OKB_FAIL(c, OKB_ERR_ARG, "bad peer allocation request");

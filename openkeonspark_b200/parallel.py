@@ -232,6 +232,7 @@ class OwnerSharded(DataParallel):
         if form not in ("scatter", "push", "pull"):
             raise ValueError("form must be 'scatter', 'push' or 'pull'")
         self.form = form
+        self.prefetch = os.environ.get("OKB200_DP_PREFETCH", "1") == "1" and form != "pull"
         from ._native import okb_dp
         from .Config import _AUX_ENT, _AUX_REL
         con._ensure_model()
@@ -312,7 +313,13 @@ class OwnerSharded(DataParallel):
         """n steps in ONE library call (sample + plan + n x [grad, reduce/push, owner update])."""
         from ._native import okb_hyper
         from .Config import _stream
-        self._sample(con, n)
+        # chunk pipeline: this chunk is the one the side stream produced during the previous call (else it is produced now),
+        # and the next one is started before this chunk's steps are issued, so it is sampled + planned under them
+        geo = (con.batch_size, con.negative_ent, con.negative_rel, n, self.streams[0], self.streams[1], _stream())
+        con.ctx.call("okb_dp_chunk_begin", *geo)
+        if self.prefetch:
+            con.ctx.call("okb_dp_chunk_prefetch", *geo)
+        con._chunk_pos, con._chunk_len = 0, n
         m = con._cmodel()
         hl, powers = con._hypers(n)
         hps = (okb_hyper * n)(*hl)
