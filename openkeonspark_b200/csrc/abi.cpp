@@ -60,6 +60,7 @@ int okb_destroy(okb_ctx *c) {
     if (c->ev_main) cudaEventDestroy(c->ev_main);
     if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->ev_sampled) cudaEventDestroy(c->ev_sampled);
+    if (c->host_flag) cudaFreeHost(c->host_flag);
     if (c == g_ctx) g_ctx = nullptr;
     delete c;
     return 0;

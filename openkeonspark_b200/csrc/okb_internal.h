@@ -84,6 +84,11 @@ struct okb_ctx {
     bool loss_ctr_ready = false;
     const void *verify_h = nullptr;   // pending comparison of the caller's block (device alias) with the resident batch: rides in the next grad launch
     i64 verify_S = 0;
+    // okb_sample_to_host, one-kernel plan: the int64 copy of the batch for the caller's page-locked block is written by extra
+    // CTAs of the plan launch (plan_steps consumes mirror_dst), which then raise *host_flag (page-locked) for the waiting host
+    long long *mirror_dst = nullptr;
+    unsigned *host_flag = nullptr, *host_flag_dev = nullptr;          // page-locked word and its device alias
+    bool defer_advance = false;       // sample_impl leaves the stream advance to its caller (okb_sample_to_host issues it after the plan)
     const void *spec_mirror = nullptr;// host block the last okb_sample_to_host filled while its batch is still resident and planned
     bool batch_from_host = false;     // the current batch came through okb_batch_from_host: update kernels honour the "bad id" flag
     bool chunk_kernel = false;        // OKB_FLAG_CHUNK_KERNEL: okb_train_steps runs a chunk as one persistent kernel where covered (measured slower: off)
@@ -194,10 +199,12 @@ i64 okb_host_new_tail(okb_ctx *c, i64 h, i64 r);      // Corrupt.h corrupt_head(
 #define OKB_FLAGS_BYTES (sizeof(float) * 64 + 128)
 #define OKB_FLAGS_BAD 68
 #define OKB_FLAGS_GRIDBAR 72
+#define OKB_FLAGS_MIRRORCTR 78  // mirror CTAs of the one-step plan launch that have finished
 #define OKB_FLAGS_HUBCTR 76    // u64 (byte 304): hub blocks finished since the context was created (scatter-form owner update)
 int okb_ensure_flags(okb_ctx *c, cudaStream_t s);     // train.cu: allocate + zero once
 
 extern "C" int okb_verify_flush(okb_ctx *c, void *stream);       // sampler.cu: launch a pending comparison stand-alone
+bool okb_plan_small_ok(const okb_ctx *c, INT B, INT k, INT kr);                     // train.cu: a one-step plan of this batch is ONE kernel
 extern "C" int okb_batch_verify_host(okb_ctx *c, INT B, INT k, INT kr, const INT *h, const INT *t, const INT *r, void *stream);   // sampler.cu
 
 // train.cu: forget a prefetched chunk (restores the RNG streams); every entry point that touches the streams calls it

@@ -227,9 +227,10 @@ static int sample_impl(okb_ctx *c, INT B, INT k, INT kr, INT steps, INT stream_l
     { ProfScope ps(c, PROF_SAMPLE, s);
     sample_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(a); }
     if (sampled) OKB_CUDA(c, cudaEventRecord(sampled, s));   // the batch is complete here; the stream advance below is not waited for
-    advance_kernel<<<(unsigned)((c->W + 63) / 64), 64, 0, s>>>(c->d_state, a.W, a.B, a.per, 1 + 2 * (u64)k + (u64)kr,
-                                                              a.steps, 0, a.W);   // every rank advances ALL streams
-    OKB_LAUNCHED(2);
+    if (!c->defer_advance)
+        advance_kernel<<<(unsigned)((c->W + 63) / 64), 64, 0, s>>>(c->d_state, a.W, a.B, a.per, 1 + 2 * (u64)k + (u64)kr,
+                                                                  a.steps, 0, a.W);   // every rank advances ALL streams
+    OKB_LAUNCHED(c->defer_advance ? 1 : 2);
     c->state_dirty = true;
     OKB_CUDA(c, cudaGetLastError());
     return 0;
@@ -296,6 +297,35 @@ int okb_sample_to_host(okb_ctx *c, INT B, INT k, INT kr, INT stream_lo, INT stre
     if (!dh) {
         int rc = sample_impl(c, B, k, kr, 1, stream_lo, stream_hi, nullptr, nullptr, stream);
         return rc ? rc : okb_batch_to_host(c, 0, h, t, r, nullptr, stream);
+    }
+    if (stream_lo == 0 && stream_hi >= c->W && !c->dp_on && okb_plan_small_ok(c, B, k, kr) && (i64)c->state.size() == c->W && c->d_raw) {
+        // One-kernel plan: the sample kernel only fills the resident batch; the int64 copy for the caller's block is
+        // written by a second cluster of the PLAN launch (posted PCIe stores next to the 8-SM sort instead of in front of
+        // it), whose last CTA raises a page-locked word this call polls.  The stream advance is issued after the plan, so the
+        // order on the stream is sample -> plan (+ copy) -> advance and nothing but the sort stands between the batch and
+        // the step that okb_train_step_host starts on it.
+        if (!c->host_flag) {
+            OKB_CUDA(c, cudaHostAlloc((void **)&c->host_flag, 64, cudaHostAllocMapped));
+            OKB_CUDA(c, cudaHostGetDevicePointer((void **)&c->host_flag_dev, c->host_flag, 0));
+        }
+        c->defer_advance = true;
+        int rc = sample_impl(c, B, k, kr, 1, stream_lo, stream_hi, nullptr, nullptr, stream);
+        c->defer_advance = false;
+        if (rc) return rc;
+        *(volatile unsigned *)c->host_flag = 0u;
+        c->mirror_dst = (long long *)dh;
+        c->spec_mirror = nullptr;
+        rc = okb_plan_steps(c, 0, 1, stream);
+        const bool copied = rc == 0 && c->mirror_dst == nullptr;          // consumed by the one-kernel plan
+        c->mirror_dst = nullptr;
+        const i32 per = (i32)(B / c->W + (B % c->W ? 1 : 0));
+        advance_kernel<<<(unsigned)((c->W + 63) / 64), 64, 0, (cudaStream_t)stream>>>(c->d_state, (i32)c->W, (i32)B, per, 1 + 2 * (u64)k + (u64)kr, 1, 0, (i32)c->W);
+        OKB_LAUNCHED(1);
+        OKB_CUDA(c, cudaGetLastError());
+        if (rc) return rc;
+        if (!copied) return okb_batch_to_host(c, 0, h, t, r, nullptr, stream);
+        c->spec_mirror = h;
+        return okb_wait_word(c, c->host_flag, 0u, stream);
     }
     if (!c->ev_sampled) OKB_CUDA(c, cudaEventCreateWithFlags(&c->ev_sampled, cudaEventDisableTiming));
     int rc = sample_impl(c, B, k, kr, 1, stream_lo, stream_hi, dh, c->ev_sampled, stream);

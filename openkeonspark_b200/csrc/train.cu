@@ -84,6 +84,11 @@ struct PlanSmallArgs {
     i32 n, rows, ib, db;
     unsigned magic_e, magic_r; // ceil(2^32 / NE), ceil(2^32 / NR): exact division of an index < 2^16 by one multiply
     i32 chunk;                 // entries per warp: 32, 64 or 128 (a power of two, so that position -> owning CTA is a shift)
+    // optional second cluster of the launch: int64 copy of the step's batch [3][S] into the caller's page-locked block
+    // (okb_sample_to_host), then *mirror_flag = mirror_token for the host that waits on it
+    long long *mirror;
+    unsigned *mirror_flag, *mirror_ctr;
+    unsigned mirror_token;
 };
 #define PS_CTAS 8
 #define PS_THREADS 1024
@@ -177,6 +182,25 @@ __global__ void __cluster_dims__(PS_CTAS, 1, 1) __launch_bounds__(PS_THREADS, 1)
 #define PS_STAMP() do { } while (0)
 #endif
     PS_STAMP();
+    if (blockIdx.x >= PS_CTAS) {                            // the mirror cluster: posted PCIe stores while the first cluster sorts
+        pdl_wait();
+        pdl_launch_dependents();
+        const i32 *src = a.p.batch + (i64)a.p.step_lo * 3 * a.p.S;
+        const i32 tot = 3 * a.p.S, nth = (i32)(gridDim.x - PS_CTAS) * PS_THREADS;
+        for (i32 i = (i32)(blockIdx.x - PS_CTAS) * PS_THREADS + (i32)threadIdx.x; i < tot; i += nth) a.mirror[i] = (long long)src[i];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned done = atomicAdd(a.mirror_ctr, 1u);
+            if (done == gridDim.x - PS_CTAS - 1) {          // last mirror CTA: every CTA's stores are ordered before the flag
+                *a.mirror_ctr = 0u;
+                __threadfence_system();
+                *(volatile unsigned *)a.mirror_flag = a.mirror_token;
+                __threadfence_system();
+            }
+        }
+        return;
+    }
     cg::cluster_group cl = cg::this_cluster();
     extern __shared__ __align__(16) unsigned psm[];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, cta = (int)cl.block_rank();
@@ -506,6 +530,10 @@ int okb_plan_steps(okb_ctx *c, INT step_lo, INT step_hi, void *stream) { return 
 static bool planned(const okb_ctx *c, INT lo, INT hi, INT b_lo, INT b_hi) {
     return lo >= c->plan_lo && hi <= c->plan_hi && c->plan_b_lo == b_lo && c->plan_b_hi == b_hi;
 }
+bool okb_plan_small_ok(const okb_ctx *c, INT B, INT k, INT kr) {
+    const i64 n = B * ((2 + k) + (1 + kr));
+    return n <= PS_MAX_N && bits_for(c->E + c->R + 1) <= 16 && !c->plan_multi;
+}
 static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, void *stream) {
     if (step_lo < 0 || step_hi > c->steps || step_lo >= step_hi) OKB_FAIL(c, OKB_ERR_ARG, "step range out of range (sample first)");
     if (b_lo < 0 || b_hi > c->B || b_lo >= b_hi) OKB_FAIL(c, OKB_ERR_ARG, "bad positive range");
@@ -538,8 +566,16 @@ static int plan_steps(okb_ctx *c, INT step_lo, INT step_hi, INT b_lo, INT b_hi, 
         q.magic_e = (unsigned)(((1ull << 32) + NE - 1) / NE); q.magic_r = (unsigned)(((1ull << 32) + NR - 1) / NR);
         const size_t smem = (size_t)(2 * chunk * PS_WARPS + PS_WARPS * (ndig + 1) + 2 * ndig + PS_WARPS) * 4;
         OKB_CUDA(c, okb_smem_optin(c, plan_small_kernel, 80 * 1024));     // up to 2 x 16 KB of items + 33 KB of counters
+        q.mirror = nullptr; q.mirror_flag = nullptr; q.mirror_ctr = nullptr; q.mirror_token = 0;
+        if (c->mirror_dst && b_lo == 0 && b_hi == c->B) {                 // okb_sample_to_host: second cluster copies the batch out
+            int rc2 = okb_ensure_flags(c, s);
+            if (rc2) return rc2;
+            q.mirror = c->mirror_dst; q.mirror_flag = (unsigned *)c->host_flag_dev; q.mirror_ctr = c->flags.as<unsigned>() + OKB_FLAGS_MIRRORCTR;
+            q.mirror_token = 1u;
+        }
+        c->mirror_dst = nullptr;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(PS_CTAS); cfg.blockDim = dim3(PS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cfg.gridDim = dim3(q.mirror ? 2 * PS_CTAS : PS_CTAS); cfg.blockDim = dim3(PS_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = 1;
