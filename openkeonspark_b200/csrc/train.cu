@@ -724,18 +724,19 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
-#define CALL_GRAD(VW, NV)                                                                              \
-    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV, 1>, a);       \
-    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV, 1>, a);  \
-    else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV, 1>, a)
-#define CALL_GRADW(VW, NV)                                                                             \
-    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV, 4>, a);       \
-    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV, 4>, a);  \
-    else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV, 4>, a)
-#define CALL_GRAD1(VW, NV)                                                                             \
-    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSE, VW, NV>, a);       \
-    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSH, VW, NV>, a);  \
-    else cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSD, VW, NV>, a)
+    // sc: the variant with the scatter form's owner search and the phase stamps compiled in (data parallel only)
+    const bool sc = a.sc_world > 0 || a.trace != nullptr;
+#define CALL_GRAD_(VW, NV, W, SC)                                                                          \
+    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV, W, SC>, a);       \
+    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV, W, SC>, a);  \
+    else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV, W, SC>, a)
+#define CALL_GRAD(VW, NV) if (sc) { CALL_GRAD_(VW, NV, 1, true); } else { CALL_GRAD_(VW, NV, 1, false); }
+#define CALL_GRADW(VW, NV) if (sc) { CALL_GRAD_(VW, NV, 4, true); } else { CALL_GRAD_(VW, NV, 4, false); }
+#define CALL_GRAD1_(VW, NV, SC)                                                                            \
+    if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSE, VW, NV, SC>, a);       \
+    else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSH, VW, NV, SC>, a);  \
+    else cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSD, VW, NV, SC>, a)
+#define CALL_GRAD1(VW, NV) if (sc) { CALL_GRAD1_(VW, NV, true); } else { CALL_GRAD1_(VW, NV, false); }
     const bool k1 = c->K == 1 && c->KR == 0 && !c->grad_generic && a.npf == 0;
     if (k1) { cfg.gridDim = dim3((unsigned)(b_hi - b_lo)); cfg.blockDim = dim3(32); }
     // small batches with several negatives: 2..4 warps per positive, as many as fill ~20 warp slots per SM
