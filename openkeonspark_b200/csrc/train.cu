@@ -724,14 +724,17 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
-    // sc: the variant with the scatter form's owner search and the phase stamps compiled in (data parallel only)
+    // sc: the variant with the scatter form's owner search and the phase stamps compiled in.  The k = 1 kernel (the default
+    // batch, the bench path) exists in both variants — without that code it is 200 instructions (1.3 us) shorter, and the two
+    // compile to the same floating-point instructions (tests/dist_gpu_check.py compares them bit for bit); the generic
+    // kernels have ONE variant, because there the compiler's FMA contraction was seen to differ between the two.
     const bool sc = a.sc_world > 0 || a.trace != nullptr;
 #define CALL_GRAD_(VW, NV, W, SC)                                                                          \
     if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSE, VW, NV, W, SC>, a);       \
     else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSH, VW, NV, W, SC>, a);  \
     else cudaLaunchKernelEx(&cfg, grad_kernel<OKB_TRANSD, VW, NV, W, SC>, a)
-#define CALL_GRAD(VW, NV) if (sc) { CALL_GRAD_(VW, NV, 1, true); } else { CALL_GRAD_(VW, NV, 1, false); }
-#define CALL_GRADW(VW, NV) if (sc) { CALL_GRAD_(VW, NV, 4, true); } else { CALL_GRAD_(VW, NV, 4, false); }
+#define CALL_GRAD(VW, NV) CALL_GRAD_(VW, NV, 1, true)
+#define CALL_GRADW(VW, NV) CALL_GRAD_(VW, NV, 4, true)
 #define CALL_GRAD1_(VW, NV, SC)                                                                            \
     if (m->model == OKB_TRANSE) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSE, VW, NV, SC>, a);       \
     else if (m->model == OKB_TRANSH) cudaLaunchKernelEx(&cfg, grad_k1_kernel<OKB_TRANSH, VW, NV, SC>, a);  \

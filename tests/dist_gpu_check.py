@@ -101,6 +101,36 @@ def main():
         a._world.close(a)
         if rank == 0:
             print("dp%d owner-sharded scatter form %s/%s: losses, tables and link-prediction records bit-identical to single GPU" % (world, model, opt))
+    # the default batch (one entity negative, no relation negative) runs the k = 1 grad kernel, which is compiled in two variants
+    # (with / without the scatter form's owner search): the two must agree bit for bit
+    for model, opt in (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam")):
+        pair = []
+        for dp in (True, False):
+            con = make(d, model, opt, 8, False)
+            con.set_ent_neg_rate(1); con.set_rel_neg_rate(0)
+            con.init()
+            con.set_model_and_session(__import__("openkeonspark_b200").__dict__[model])
+            from conftest import make_params
+            con.set_parameters(make_params(model, con.entTotal, con.relTotal, 100, seed=4))
+            seeds = np.arange(1, 9, dtype=np.uint64) * np.uint64(7919)
+            con.ctx.call("okb_set_streams", ctypes.c_void_p(seeds.ctypes.data), 8)
+            if dp:
+                from openkeonspark_b200 import parallel
+                parallel.attach(con, mode="owner", form="scatter")
+                con.plan_ahead = 5
+                losses = [float(con.next_step_device().item()) for _ in range(5)]
+            else:
+                losses = []
+                for _ in range(5):
+                    con.sampling_device()
+                    losses.append(float(con.train_step_device(0).item()))
+            pair.append((losses, con.get_parameters(), con))
+        assert pair[0][0] == pair[1][0], (model, opt, pair[0][0], pair[1][0])
+        for k in pair[0][1]:
+            assert np.array_equal(pair[0][1][k], pair[1][1][k]), (model, opt, k, rank)
+        pair[0][2]._world.close(pair[0][2])
+        if rank == 0:
+            print("dp%d owner-sharded scatter form, k = 1 batch %s/%s: losses and tables bit-identical to single GPU" % (world, model, opt))
     # owner-sharded mode, push form (peer-memory reduce/push + owner update): replicas bit-identical to EACH OTHER, and equal
     # to the single-GPU run up to fp32 re-association of the per-row gradient sums
     for model, opt in (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam"), ("TransD", "SGD")):
