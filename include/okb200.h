@@ -238,7 +238,10 @@ typedef struct {
      * that owns its table row (off_gent / off_grel: receive buffers with one slot per gradient row of the global batch;
      * off_loss: hinge terms, stored to every rank); the owner runs the single-GPU update over its rows and stores the new
      * rows into every rank's tables.  Two kernels and two flag exchanges per step, no staging slabs, and tables + loss
-     * bit-identical to ONE GPU training the global batch. */
+     * bit-identical to ONE GPU training the global batch.
+     * scatter = 2 is the "gather" form: the grad kernel stores every gradient row into EVERY rank's arena (two receive
+     * buffers used in turn) and every rank runs the full single-GPU update on its own copy — ONE exchange per step instead
+     * of two; (world - 1) x the gradient rows leave every rank, so it pays for two ranks only.  Same bit-identity. */
     INT scatter, global_batch;
 } okb_dp;
 int okb_peer_alloc(okb_ctx *c, INT bytes, void **dev_ptr, unsigned char *handle64);

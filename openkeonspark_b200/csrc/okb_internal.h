@@ -109,6 +109,8 @@ struct okb_ctx {
     DevBuf dp_trace;                  // OKB_FLAG_DP_TRACE: [64 steps][16] globaltimer stamps of the data-parallel kernels (debugging aid)
     bool dp_trace_on = false;
     int dp_hs_mode = 2;               // OKB_FLAG_DP_HANDSHAKE: see GradArgs::hs_mode (2 measured fastest: 42.4 -> 39.2 us per step at 2 GPUs)
+    int sc_launch = 0;                // set around launch_grad by the scatter (1) / gather (2) form of the data-parallel step
+    long long sc_buf_off[3] = {0, 0, 0};   // byte offsets of the receive buffers in use (gather form: alternating halves)
     unsigned long long hub_done = 0;  // value OKB_FLAGS_HUBCTR will have reached when every launch issued so far has finished
     bool dp_pull = false;             // OKB_FLAG_DP_PULL: row owners pull partial rows from their peers instead of the reduce+push kernel
     PlanSlot alt;                     // prefetched chunk (okb_chunk_prefetch)

@@ -656,7 +656,7 @@ void okb_fill_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step
     a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi; a.slot_base = (i32)slot_base;
     a.wait_flags = nullptr; a.wait_epoch = 0; a.wait_n = 0; a.npf = 0;
     a.vh = nullptr; a.vflag = nullptr; a.vS = 0; a.vblocks = 0;
-    a.sc_world = 0; a.trace = nullptr; a.hs_mode = c->dp_hs_mode;
+    a.sc_world = 0; a.sc_gather = 0; a.trace = nullptr; a.hs_mode = c->dp_hs_mode;
 }
 // warps per positive the generic grad kernel uses for this batch (1 = one warp per positive); a function of the GLOBAL
 // batch, so that a data-parallel rank's slice is computed exactly like the same positives on one GPU
@@ -692,15 +692,15 @@ static int launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT 
     if (wait_flags)
         for (int q = 0; q < wait_n; q++)
             a.announce[q] = (unsigned long long *)((char *)c->dp.arena[q] + c->dp.off_flags) + DP_FLAG_X + c->dp.rank;
-    if (wait_flags && c->dp.scatter) {                     // gradient rows go to their table rows' owners (global slots)
-        const okb_dp &P = c->dp;
+    if (c->sc_launch) {                                    // scatter form: gradient rows go to their table rows' owners (global
+        const okb_dp &P = c->dp;                           // slots); gather form: to every rank
         const i64 own_e = (c->E + P.world - 1) / P.world, own_r = (c->R + P.world - 1) / P.world;
-        a.sc_world = P.world;
-        for (int q = 0; q < P.world; q++) a.sc_arena[q] = (char *)P.arena[q];
+        a.sc_world = P.world; a.sc_gather = c->sc_launch == 2;
+        for (int q = 0; q < P.world; q++) { a.sc_arena[q] = (char *)P.arena[q]; a.sc_delta[q] = (i64)((char *)P.arena[q] - (char *)P.arena[0]); }
         for (int q = 0; q <= P.world; q++) { a.sc_ent_lo[q] = (i32)std::min<i64>(c->E, q * own_e); a.sc_rel_lo[q] = (i32)std::min<i64>(c->R, q * own_r); }
-        a.sc_gent = P.off_gent; a.sc_grel = P.off_grel; a.sc_loss = P.off_loss;
+        a.sc_gent = P.off_gent + c->sc_buf_off[0]; a.sc_grel = P.off_grel + c->sc_buf_off[1]; a.sc_loss = P.off_loss + c->sc_buf_off[2];
     }
-    if (wait_flags && c->dp_trace_on) a.trace = c->dp_trace.as<unsigned long long>() + ((wait_epoch + 1) % 64) * 16;
+    if (c->dp_on && c->dp_trace_on) a.trace = c->dp_trace.as<unsigned long long>() + ((c->dp_epoch + 1) % 64) * 16;
     const unsigned grid = (unsigned)((b_hi - b_lo + GRAD_WARPS - 1) / GRAD_WARPS);
     a.npf = 0;
     if (m->optimizer == OKB_ADAM && c->l2_prefetch && m->m_ent) {
@@ -1281,6 +1281,7 @@ struct DpSc {
     i64 off_flags;
     i32 world, rank, adam;
     i32 ent_lo, ent_hi, rel_lo, rel_hi;                    // owned rows
+    i32 nbcast;                                            // copies of a new row: world (scatter form) or 1 (gather form: this rank's own)
     unsigned long long epoch;
     // hub rows: `hub_blocks` CTAs in front of the tiles pre-reduce the PCH-blocks of this rank's long segments (what
     // prereduce_kernel does on one GPU) and count themselves off in *hub_ctr; a tile thread whose row has a long segment
@@ -1385,7 +1386,7 @@ __global__ void __launch_bounds__(256, 4) dp_scatter_update_kernel(UpdArgs a, Dp
         for (int q = 0; q < VW; q++) xs[q] -= a.hp.lr * g[q];
     }
     char *xp = reinterpret_cast<char *>(T.x + e);
-    for (int p = 0; p < d.world; p++) *reinterpret_cast<V *>(xp + d.delta[p]) = xv;
+    for (int p = 0; p < d.nbcast; p++) *reinterpret_cast<V *>(xp + d.delta[p]) = xv;
     if (threadIdx.x == 0) trace_max(d.trace, 9);
 }
 
@@ -1419,7 +1420,11 @@ static int dp_scatter_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp,
         if ((rc = plan_steps(c, step_lo, c->steps, 0, c->B, s))) return rc;
     }
     char *own = (char *)P.arena[P.rank];
-    float *gent = (float *)(own + P.off_gent), *grel = (float *)(own + P.off_grel), *lterms = (float *)(own + P.off_loss);
+    const bool gather = P.scatter == 2;
+    i32 ce0, cr0;
+    group_cols(m, ce0, cr0);
+    const i64 buf_bytes[3] = {((c->B * (2 + c->K) * ce0 * 4) + 255) & ~(i64)255, ((c->B * (1 + c->KR) * cr0 * 4) + 255) & ~(i64)255,
+                              ((c->B * 4) + 255) & ~(i64)255};
     cudaLaunchAttribute pat[1];
     pat[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     pat[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1432,11 +1437,25 @@ static int dp_scatter_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp,
     d.off_flags = P.off_flags; d.world = P.world; d.rank = P.rank; d.adam = m->optimizer == OKB_ADAM;
     d.ent_lo = (i32)std::min<i64>(c->E, P.rank * own_e); d.ent_hi = (i32)std::min<i64>(c->E, (P.rank + 1) * own_e);
     d.rel_lo = (i32)std::min<i64>(c->R, P.rank * own_r); d.rel_hi = (i32)std::min<i64>(c->R, (P.rank + 1) * own_r);
+    d.nbcast = P.world;
+    if (gather) {                                          // every rank updates every row of its own copy
+        d.ent_lo = 0; d.ent_hi = (i32)c->E; d.rel_lo = 0; d.rel_hi = (i32)c->R;
+        d.nbcast = 1; d.delta[0] = 0;
+    }
     const unsigned long long *xflags = (const unsigned long long *)(own + P.off_flags) + DP_FLAG_X;
     for (INT i = 0; i < n; i++) {
         const INT step = step_lo + i;
         d.epoch = c->dp_epoch + 1;
-        if ((rc = launch_grad(c, m, hp + i, step, P.b_lo, P.b_hi, 0, gent, grel, lterms, xflags, c->dp_epoch, P.world, s))) return rc;
+        // gather form: the receive buffers are used in turn — a peer's grad kernel of step n + 1 can only run after it has
+        // seen this rank's "gradient rows landed" announcement of step n, i.e. after this rank's update of step n - 1
+        const i64 par = gather ? (i64)(d.epoch & 1) : 0;
+        for (int z = 0; z < 3; z++) c->sc_buf_off[z] = par * buf_bytes[z];
+        float *gent = (float *)(own + P.off_gent + c->sc_buf_off[0]), *grel = (float *)(own + P.off_grel + c->sc_buf_off[1]),
+              *lterms = (float *)(own + P.off_loss + c->sc_buf_off[2]);
+        c->sc_launch = gather ? 2 : 1;
+        rc = launch_grad(c, m, hp + i, step, P.b_lo, P.b_hi, 0, gent, grel, lterms, gather ? nullptr : xflags, c->dp_epoch, gather ? 0 : P.world, s);
+        c->sc_launch = 0;
+        if (rc) return rc;
         UpdArgs a;
         i32 blk = 0;
         bool lean = true;
@@ -1549,9 +1568,10 @@ int okb_dp_layout(okb_ctx *c, const okb_model *m, INT world, okb_dp *out) {
     out->off_rowhead = out->off_perm = out->off_gent = out->off_grel = out->off_loss = out->off_partial = -1;
     if (out->scatter) {                                    // scatter form: receive buffers for the gradient rows of the GLOBAL batch
         if (out->global_batch < 1 || out->neg_ent < 0 || out->neg_rel < 0) OKB_FAIL(c, OKB_ERR_ARG, "scatter form needs global_batch, neg_ent, neg_rel");
-        out->off_gent = take(out->global_batch * (2 + out->neg_ent) * ce * 4);
-        out->off_grel = take(out->global_batch * (1 + out->neg_rel) * cr * 4);
-        out->off_loss = take(out->global_batch * 4);
+        const i64 nb = out->scatter == 2 ? 2 : 1;          // gather form: two buffers, used in turn (no "buffer free" exchange)
+        out->off_gent = take(nb * (((out->global_batch * (2 + out->neg_ent) * ce * 4) + 255) & ~(i64)255));
+        out->off_grel = take(nb * (((out->global_batch * (1 + out->neg_rel) * cr * 4) + 255) & ~(i64)255));
+        out->off_loss = take(nb * (((out->global_batch * 4) + 255) & ~(i64)255));
         out->plan_steps = 0;
     }
     if (out->plan_steps > 0 && out->max_local > 0) {       // pull form: plan, gradient rows and loss terms in the arena too

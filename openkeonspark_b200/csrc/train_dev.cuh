@@ -356,6 +356,9 @@ struct GradArgs {
     i64 sc_gent, sc_grel, sc_loss;                         // byte offsets of the receive buffers inside an arena
     i32 sc_ent_lo[OKB_DP_MAX + 1], sc_rel_lo[OKB_DP_MAX + 1];
     i32 sc_world;
+    // gather form (sc_gather): every row goes to EVERY rank (arena[0] + sc_delta[p]) and every rank runs the full update
+    i32 sc_gather;
+    i64 sc_delta[OKB_DP_MAX];
     unsigned long long *trace;
     i32 hs_mode;               // flag handshake: 0 = release store / acquire polls, bit 0 = relaxed polls + one fence, bit 1 = relaxed store
 };
@@ -370,20 +373,33 @@ template <bool SC> __device__ __forceinline__ float *grad_dst_ent(const GradArgs
     if (!SC || !a.sc_world) return a.gent + slot * ce;
     if (id < 0) return nullptr;
     int o = 0;
-    while (id >= a.sc_ent_lo[o + 1]) o++;
+    if (!a.sc_gather) while (id >= a.sc_ent_lo[o + 1]) o++;
     return reinterpret_cast<float *>(a.sc_arena[o] + a.sc_gent) + slot * ce;
 }
 template <bool SC> __device__ __forceinline__ float *grad_dst_rel(const GradArgs &a, i32 id, i64 slot, int cr) {
     if (!SC || !a.sc_world) return a.grel + slot * cr;
     if (id < 0) return nullptr;
     int o = 0;
-    while (id >= a.sc_rel_lo[o + 1]) o++;
+    if (!a.sc_gather) while (id >= a.sc_rel_lo[o + 1]) o++;
     return reinterpret_cast<float *>(a.sc_arena[o] + a.sc_grel) + slot * cr;
 }
 template <bool SC> __device__ __forceinline__ void grad_put_loss(const GradArgs &a, i32 b, float term, int lane) {
     if (!SC || !a.sc_world) { if (lane == 0) a.loss_terms[b - a.slot_base] = term; return; }
     term = __shfl_sync(FULL, term, 0);
     if (lane < a.sc_world) reinterpret_cast<float *>(a.sc_arena[lane] + a.sc_loss)[b - a.slot_base] = term;
+}
+// store a gradient row at its destination (and, in the gather form, at the same place in every other rank's arena)
+template <int MODEL, int VW, int NV, bool SC>
+__device__ __forceinline__ void put_ent_sc(const GradArgs &a, float *dst, const EntG<MODEL, VW * NV> &g, int D, int lane) {
+    put_ent<MODEL, VW, NV>(dst, g, D, lane);
+    if (SC && a.sc_gather)
+        for (int p = 1; p < a.sc_world; p++) put_ent<MODEL, VW, NV>(reinterpret_cast<float *>(reinterpret_cast<char *>(dst) + a.sc_delta[p]), g, D, lane);
+}
+template <int MODEL, int VW, int NV, bool SC>
+__device__ __forceinline__ void put_rel_sc(const GradArgs &a, float *dst, const RelG<MODEL, VW * NV> &g, int D, int lane) {
+    put_rel<MODEL, VW, NV>(dst, g, D, lane);
+    if (SC && a.sc_gather)
+        for (int p = 1; p < a.sc_world; p++) put_rel<MODEL, VW, NV>(reinterpret_cast<float *>(reinterpret_cast<char *>(dst) + a.sc_delta[p]), g, D, lane);
 }
 __device__ __forceinline__ void grad_verify_block(const GradArgs &a, i32 vb) {
     // one element per thread: every PCIe read of the launch is in flight at once (a loop per thread would serialise
@@ -447,7 +463,7 @@ __device__ __forceinline__ void grad_body(const GradArgs &a, i32 b, int lane, in
             const float x = a.margin;
             if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rp, gp, -a.w, accH, accT, accR); }
         }
-        if (float *dst = grad_dst_ent<SC>(a, cnh != ph ? cnh : (cnt_ != pt ? cnt_ : -1), es + 2 + m, ce)) put_ent<MODEL, VW, NV>(dst, gnew, D, lane);
+        if (float *dst = grad_dst_ent<SC>(a, cnh != ph ? cnh : (cnt_ != pt ? cnt_ : -1), es + 2 + m, ce)) put_ent_sc<MODEL, VW, NV, SC>(a, dst, gnew, D, lane);
     }
     for (i32 m = 0; m < (wid == 0 ? a.kr : 0); m++) {      // relation negatives (Base.cpp:133-139): warp 0
         const i32 nr = a.br[b + (1 + a.k + m) * a.B];
@@ -473,7 +489,7 @@ __device__ __forceinline__ void grad_body(const GradArgs &a, i32 b, int lane, in
             const float x = a.margin;
             if (x >= 0.f) { hinge_sum += x; active++; score_bw<MODEL, N>(Hp, Tp, Rp, gp, -a.w, accH, accT, accR); }
         }
-        if (float *dst = grad_dst_rel<SC>(a, nr != pr ? nr : -1, rs + 1 + m, cr)) put_rel<MODEL, VW, NV>(dst, gnew, D, lane);
+        if (float *dst = grad_dst_rel<SC>(a, nr != pr ? nr : -1, rs + 1 + m, cr)) put_rel_sc<MODEL, VW, NV, SC>(a, dst, gnew, D, lane);
     }
     if (WPPMAX > 1 && wpp > 1) {                           // warps 1.. hand their accumulators to warp 0, which adds them in warp order
         constexpr int F = 2 * (MODEL == OKB_TRANSD ? 2 : 1) + (MODEL == OKB_TRANSE ? 1 : 2);      // fragments per warp
@@ -508,9 +524,9 @@ __device__ __forceinline__ void grad_body(const GradArgs &a, i32 b, int lane, in
         }
     }
     if (active) score_bw<MODEL, N>(Hp, Tp, Rp, gp, a.w * (float)active, accH, accT, accR);
-    put_ent<MODEL, VW, NV>(grad_dst_ent<SC>(a, ph, es, ce), accH, D, lane);
-    put_ent<MODEL, VW, NV>(grad_dst_ent<SC>(a, pt, es + 1, ce), accT, D, lane);
-    put_rel<MODEL, VW, NV>(grad_dst_rel<SC>(a, pr, rs, cr), accR, D, lane);
+    put_ent_sc<MODEL, VW, NV, SC>(a, grad_dst_ent<SC>(a, ph, es, ce), accH, D, lane);
+    put_ent_sc<MODEL, VW, NV, SC>(a, grad_dst_ent<SC>(a, pt, es + 1, ce), accT, D, lane);
+    put_rel_sc<MODEL, VW, NV, SC>(a, grad_dst_rel<SC>(a, pr, rs, cr), accR, D, lane);
     grad_put_loss<SC>(a, b, hinge_sum, lane);
 }
 
@@ -755,10 +771,10 @@ __device__ __forceinline__ void grad_k1_body(const GradArgs &a, i32 b, int lane,
         }
     }
     const i64 es = (i64)(b - a.slot_base) * a.NE, rs = (i64)(b - a.slot_base) * a.NR;
-    put_ent<MODEL, VW, NV>(grad_dst_ent<SC>(a, ph, es, ce), accH, D, lane);
-    put_ent<MODEL, VW, NV>(grad_dst_ent<SC>(a, pt, es + 1, ce), accT, D, lane);
-    if (float *dst = grad_dst_ent<SC>(a, nh != ph ? nh : (nt != pt ? nt : -1), es + 2, ce)) put_ent<MODEL, VW, NV>(dst, gnew, D, lane);
-    put_rel<MODEL, VW, NV>(grad_dst_rel<SC>(a, pr, rs, cr), accR, D, lane);
+    put_ent_sc<MODEL, VW, NV, SC>(a, grad_dst_ent<SC>(a, ph, es, ce), accH, D, lane);
+    put_ent_sc<MODEL, VW, NV, SC>(a, grad_dst_ent<SC>(a, pt, es + 1, ce), accT, D, lane);
+    if (float *dst = grad_dst_ent<SC>(a, nh != ph ? nh : (nt != pt ? nt : -1), es + 2, ce)) put_ent_sc<MODEL, VW, NV, SC>(a, dst, gnew, D, lane);
+    put_rel_sc<MODEL, VW, NV, SC>(a, grad_dst_rel<SC>(a, pr, rs, cr), accR, D, lane);
     grad_put_loss<SC>(a, b, active ? x : 0.f, lane);
 }
 

@@ -226,11 +226,15 @@ class OwnerSharded(DataParallel):
         # step, bit-identical to one GPU); "push" = per-rank partial sums through staging slabs (three kernels per step)
         # default by world size: measured crossover (profiles/r02_dp_phase_traces.txt) — the scatter form's grad kernel slows
         # down as the share of remote rows grows and its owner update pre-reduces the GLOBAL batch's long segments
-        form = os.environ.get("OKB200_DP_FORM", "scatter" if self.world <= 4 else "push") if form is None else form
+        # "gather": gradient rows go to EVERY rank and every rank runs the full update — one exchange per step, bit-identical
+        # to one GPU too, but measured slower even at 2 ranks (61.6 vs 53.8 us per step: the grad kernel's peer stores run at
+        # ~350 GB/s, so doubling them costs more than the second exchange); kept as an option
+        default = "scatter" if self.world <= 4 else "push"
+        form = os.environ.get("OKB200_DP_FORM", default) if form is None else form
         if pull:
             form = "pull"
-        if form not in ("scatter", "push", "pull"):
-            raise ValueError("form must be 'scatter', 'push' or 'pull'")
+        if form not in ("gather", "scatter", "push", "pull"):
+            raise ValueError("form must be 'gather', 'scatter', 'push' or 'pull'")
         self.form = form
         self.prefetch = os.environ.get("OKB200_DP_PREFETCH", "1") == "1" and form != "pull"
         from ._native import okb_dp
@@ -247,8 +251,8 @@ class OwnerSharded(DataParallel):
             lay.plan_steps, lay.max_local = int(con.plan_ahead), int(self.chunk)
             lay.neg_ent, lay.neg_rel = int(con.negative_ent), int(con.negative_rel)
             con.ctx.call("okb_set_flag", 7, 1)
-        if form == "scatter":
-            lay.scatter, lay.global_batch = 1, int(con.batch_size)
+        if form in ("scatter", "gather"):
+            lay.scatter, lay.global_batch = (1 if form == "scatter" else 2), int(con.batch_size)
             lay.neg_ent, lay.neg_rel = int(con.negative_ent), int(con.negative_rel)
         con.ctx.call("okb_dp_layout", ctypes.byref(m), self.world, ctypes.byref(lay))
         own, handle = _vp(), (ctypes.c_ubyte * 64)()
@@ -286,7 +290,7 @@ class OwnerSharded(DataParallel):
         self._lay, self._own = lay, own.value
         per = con.workThreads // self.world
         # scatter form: every rank samples (and plans) the global batch; the other forms only this rank's streams
-        self.streams = (0, con.workThreads) if form == "scatter" else (self.rank * per, (self.rank + 1) * per)
+        self.streams = (0, con.workThreads) if form in ("scatter", "gather") else (self.rank * per, (self.rank + 1) * per)
         con.ctx.call("okb_dp_attach", ctypes.byref(lay))
         torch.cuda.synchronize()
         dist.barrier(group=self.group)                # every arena initialised before anyone pushes into it
@@ -300,7 +304,7 @@ class OwnerSharded(DataParallel):
         """One train step; batches are sampled (this rank's streams only) and planned plan_ahead steps at a time."""
         from .Config import _stream
         if con._chunk_pos >= con._chunk_len:
-            n = con.batch_size * (3 + con.negative_ent + con.negative_rel) // (1 if self.form == "scatter" else self.world)
+            n = con.batch_size * (3 + con.negative_ent + con.negative_rel) // (1 if self.form in ("scatter", "gather") else self.world)
             self._sample(con, max(1, min(int(con.plan_ahead), (1 << 24) // max(n, 1))))
         m = con._cmodel()
         (hp,), powers = con._hypers(1)

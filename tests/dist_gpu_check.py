@@ -77,10 +77,12 @@ def main():
     # owner-sharded mode, scatter form (the default: the grad kernel stores gradient rows into their row owner's arena, the
     # owner runs the single-GPU update over its rows): losses and tables bit-identical to ONE GPU training the global batch,
     # step by step and through the chunked entry point; zipf graph, so hub rows (pre-reduced long segments) are covered
-    for model, opt in (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam"), ("TransD", "SGD"), ("TransE", "Adam")):
-        a = make(d, model, opt, 8, True, mode="owner", form="scatter")
+    # ... and the gather form (every gradient row to every rank, full update everywhere, one exchange per step): same bar
+    for form, model, opt in [(f, mo, o) for f in ("scatter", "gather") for mo, o in
+                             (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam"), ("TransD", "SGD"), ("TransE", "Adam"))]:
+        a = make(d, model, opt, 8, True, mode="owner", form=form)
         b = make(d, model, opt, 8, False)
-        assert a._world.mode == "owner" and a._world.form == "scatter"
+        assert a._world.mode == "owner" and a._world.form == form
         a.plan_ahead = 6
         for it in range(6):
             la = float(a.next_step_device().item())
@@ -100,7 +102,7 @@ def main():
         assert np.array_equal(ra, rb), (model, opt, rank)
         a._world.close(a)
         if rank == 0:
-            print("dp%d owner-sharded scatter form %s/%s: losses, tables and link-prediction records bit-identical to single GPU" % (world, model, opt))
+            print("dp%d owner-sharded %s form %s/%s: losses, tables and link-prediction records bit-identical to single GPU" % (world, form, model, opt))
     # the default batch (one entity negative, no relation negative) runs the k = 1 grad kernel, which is compiled in two variants
     # (with / without the scatter form's owner search): the two must agree bit for bit
     for model, opt in (("TransH", "Adam"), ("TransE", "SGD"), ("TransD", "Adam")):

@@ -18,6 +18,6 @@ def test_two_rank_data_parallel(built):
            "--master-port", "29533", os.path.join(ROOT, "tests", "dist_gpu_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("bit-identical to single GPU") == 13 and r.stdout.count("owner-sharded") == 16 and r.stdout.count("scatter form") == 8, r.stdout[-2000:]
+    assert r.stdout.count("bit-identical to single GPU") == 18 and r.stdout.count("owner-sharded") == 21 and r.stdout.count("scatter form") == 8 and r.stdout.count("gather form") == 5, r.stdout[-2000:]
     assert r.stdout.count("pull == push") == 3, r.stdout[-2000:]
     assert r.stdout.count("relation-sharded TransR") == 2 and r.stdout.count("save -> restore -> continue") == 1, r.stdout[-2000:]
