@@ -1311,13 +1311,23 @@ __global__ void __launch_bounds__(256, 4) dp_scatter_update_kernel(UpdArgs a, Dp
     if (threadIdx.x == 0) trace_min(d.trace, 5);
     const i32 hid = (i32)blockIdx.x - a.loss_blocks;       // loss blocks, then hub blocks, then the tiles
     if (hid >= 0 && hid < d.hub_blocks) {
+        // one warp per PCH-block of sorted positions; same additions in the same order as prereduce_body.  Which blocks lie
+        // inside ONE segment of a row this rank owns is plan data: a CTA without such a block leaves before the waits
+        const i32 w = hid * 8 + (i32)(threadIdx.x >> 5), lo = w * PCH, lane = threadIdx.x & 31;
+        bool mine = false;
+        i32 key = 0;
+        if (lo + PCH <= a.n) {
+            key = a.skeys[lo];
+            mine = key < a.key_limit && dp_owns_key(a, d, key) && a.skeys[lo + PCH - 1] == key;
+        }
+        if (!__syncthreads_or(mine)) {
+            if (threadIdx.x == 0) { atomicAdd(d.hub_ctr, 1ull); trace_max(d.trace, 8); }
+            return;
+        }
         pdl_wait();
         dp_announce_and_wait(d.arena, d.off_flags, d.world, d.rank, DP_FLAG_STAGE, d.epoch, false, d.hs_mode);
-        // one warp per PCH-block of sorted positions; same additions in the same order as prereduce_body
-        const i32 w = hid * 8 + (i32)(threadIdx.x >> 5), lo = w * PCH, lane = threadIdx.x & 31;
-        if (lo + PCH <= a.n) {
-            const i32 key = a.skeys[lo];
-            if (key < a.key_limit && dp_owns_key(a, d, key) && a.skeys[lo + PCH - 1] == key) {
+        {
+            if (mine) {
                 const bool is_ent = key < a.E;
                 const i32 cols = is_ent ? a.ce : a.cr;
                 const float *gb = is_ent ? a.gent : a.grel - (i64)a.n_ent_slots * a.cr;
