@@ -109,3 +109,29 @@ def test_wait_word_host_side(built):
     with pytest.raises(_native.OkbError):
         c.call("okb_wait_word", ctypes.c_void_p(w.ctypes.data), 0xFFC0DEAD, None)
     c.close()
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """okb_model / okb_hyper / okb_dp cross the C ABI by pointer: every field of the ctypes mirrors must sit at the offset
+    the C compiler gives it in include/okb200.h (a field added on one side only would silently shift everything after it)."""
+    import subprocess
+    from openkeonspark_b200 import _native
+    structs = {"okb_model": _native.okb_model, "okb_hyper": _native.okb_hyper, "okb_dp": _native.okb_dp}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "okb200.h"', 'int main(void) {']
+    for name, cls in structs.items():
+        lines.append('  printf("%s.sizeof %%zu\\n", sizeof(%s));' % (name, name))
+        for field, _ in cls._fields_:
+            lines.append('  printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (name, field, name, field))
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]            # a field the header does not have fails here
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for name, cls in structs.items():
+        assert int(out[name + ".sizeof"]) == ctypes.sizeof(cls), name
+        for field, _ in cls._fields_:
+            assert int(out["%s.%s" % (name, field)]) == getattr(cls, field).offset, (name, field)
+    # ... and the header has no field the mirror lacks (sizes equal + every mirrored field at its place covers it)
