@@ -178,6 +178,9 @@ typedef struct {
  * okb_train_step runs the three phases on context-owned buffers and writes the mean loss to
  * loss_out (device float).  The phases are public so that data-parallel ranks can all-gather
  * grad_ent / grad_rel / loss_terms between okb_grad and okb_update. */
+/* TransR: grad_rel holds one [d rel_embeddings | d transfer_matrix] row per RELATION (rel_rows = R; the train kernel emits the
+ * gradients already reduced per relation) when neg_rel == 0, and one such row per (positive, relation slot) — like the other
+ * models — when neg_rel > 0 (TransR.py:61-65: every negative is projected by its own relation's matrix). */
 int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT batch_size, INT neg_ent, INT neg_rel,
                    INT *ent_rows, INT *ent_cols, INT *rel_rows, INT *rel_cols);
 int okb_plan(okb_ctx *c, INT step, void *cuda_stream);

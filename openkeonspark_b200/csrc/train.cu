@@ -477,7 +477,8 @@ bool okb_pick_layout(int D, int &vw, int &nv) {
 int okb_transr_check(okb_ctx *c, const okb_model *m);
 int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const i32 *batch, const i32 *skeys, const i32 *perm,
                            const int4 *rowhead, i64 n, INT b_lo, INT b_hi, float *gent, float *grel, float *loss_terms, cudaStream_t s);
-int okb_transr_launch_rel_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const int4 *rowhead, const float *grel, cudaStream_t s);
+int okb_transr_launch_rel_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const int4 *rowhead, const float *grel, cudaStream_t s,
+                                 const i32 *perm);
 
 static int check_model(okb_ctx *c, const okb_model *m, int &vw, int &nv) {
     if (!m || !m->ent || !m->rel) OKB_FAIL(c, OKB_ERR_ARG, "model tables missing");
@@ -523,7 +524,9 @@ extern "C" {
 int okb_grad_sizes(okb_ctx *c, const okb_model *m, INT B, INT k, INT kr, INT *er, INT *ec, INT *rr, INT *rc) {
     i32 ce, cr;
     group_cols(m, ce, cr);
-    *er = B * (2 + k); *ec = ce; *rr = m->model == OKB_TRANSR ? c->R : B * (1 + kr); *rc = cr;
+    // TransR: one [d rel | d M_r] row per RELATION (gradients come out reduced) — or, with relation negatives, per
+    // (positive, relation slot) like the other models (transr_general_kernel)
+    *er = B * (2 + k); *ec = ce; *rr = (m->model == OKB_TRANSR && kr == 0) ? c->R : B * (1 + kr); *rc = cr;
     return 0;
 }
 
@@ -912,7 +915,8 @@ int okb_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT step, co
     }
     if (is_tr) {                                          // rel_embeddings + transfer_matrix rows (gradients already per relation)
         if ((rc = ensure_rowhead(c, s))) return rc;
-        if ((rc = okb_transr_launch_rel_update(c, m, hp, c->rowseg_e.as<int4>() + (step - c->plan_lo) * (c->E + c->R), grel, s))) return rc;
+        if ((rc = okb_transr_launch_rel_update(c, m, hp, c->rowseg_e.as<int4>() + (step - c->plan_lo) * (c->E + c->R), grel, s,
+                                               c->perm_ent.as<i32>() + (step - c->plan_lo) * n))) return rc;
     }
     OKB_CUDA(c, cudaGetLastError());
     return 0;

@@ -1,6 +1,7 @@
 // TransR train step (TransR.py:36-75): entities are mapped into relation space by the positive's
 // matrix, e' = e . M_r with M_r = transfer_matrix[r] viewed as [ent_size, rel_size]; with
-// negative_rel == 0 the negatives use the POSITIVE's matrix (TransR.py:57-60).
+// negative_rel == 0 the negatives use the POSITIVE's matrix (TransR.py:57-60).  (negative_rel > 0, TransR.py:61-65:
+// transr_general_kernel further down.)
 //
 // The reference gathers one 40 KB matrix per batch row (B x De x Dr floats materialised per step) and
 // runs a batched [1,De]x[De,Dr] matmul.  Here the batch is bucketed by relation — the plan's sorted
@@ -626,6 +627,167 @@ __global__ void __launch_bounds__(TRF_THREADS, 1) transr_fused_kernel(TrArgs a, 
     }
 }
 
+// ------------------------------------------------------------------------------------------ general form (rel_neg_rate > 0)
+// TransR.py:61-65: with relation negatives EVERY negative is projected by ITS OWN relation's matrix (for an entity negative
+// that is the positive's), so a relation negative (h, t, r') needs h.M_r' and t.M_r' — a second 40 KB matrix per negative,
+// and its gradients go to M_r' and rel_embeddings[r'].  One CTA per POSITIVE does everything for its group (matrices read
+// through L1 / L2, no bucketing): entity rows -> the positive's (2 + k) entity gradient rows (the relation negatives' share
+// of d h, d t is added into the positive's rows: same entities), relation side -> one [d rel | d M] gradient row PER
+// (positive, relation slot), summed per relation in slot order by transr_rel_update_kernel (general mode).  A slow path
+// (770 MB of matrix reads and 390 MB of gradient rows per step at the FB15K shape) for a non-default option; deterministic.
+#define TG_THREADS 128
+__global__ void __launch_bounds__(TG_THREADS) transr_general_kernel(TrArgs a, i32 kr) {
+    extern __shared__ __align__(16) float sm[];
+    const int De = a.m.ent_dim, Dr = a.m.rel_dim, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int k = a.k, per = 2 + k, NR = 1 + kr;
+    const i32 b = (i32)blockIdx.x;
+    float *A = sm;                                      // [per][De]     gathered entity rows: h, t, entity negatives
+    float *P = A + per * De;                            // [per][Dr]     projected by M_r, normalised
+    float *G = P + per * Dr;                            // [per][Dr]     gradient w.r.t. the normalised projected rows
+    float *P2 = G + per * Dr;                           // [kr][2][Dr]   h, t projected by the negative relation's matrix
+    float *G2 = P2 + kr * 2 * Dr;                       // [kr][2][Dr]
+    float *rh = G2 + kr * 2 * Dr;                       // [NR][Dr]      r_hat of the positive's and the negatives' relations
+    float *gr = rh + NR * Dr;                           // [NR][Dr]      gradient w.r.t. each r_hat
+    float *dHT = gr + NR * Dr;                          // [2][De]       d h, d t
+    float *inv = dHT + 2 * De;                          // [per + 2 kr]
+    i32 *proj = (i32 *)(inv + per + 2 * kr);            // [per + 2 kr]
+    i32 *rowid = proj + per + 2 * kr;                   // [per]
+    i32 *side = rowid + per;                            // [k]
+    i32 *relid = side + k;                              // [NR]          pr, then the negative relations (-1: same triple)
+    float *rinv = (float *)(relid + NR);                // [NR]
+    i32 *rproj = (i32 *)(rinv + NR);                    // [NR]
+    const i32 ph = a.bh[b], pt = a.bt[b], pr = a.br[b];
+    if (tid == 0) {
+        rowid[0] = ph; rowid[1] = pt; relid[0] = pr;
+        for (int m = 0; m < k; m++) {
+            const i32 at = b + (m + 1) * a.B, nh = a.bh[at], nt = a.bt[at];
+            const int sd = nh != ph ? 0 : (nt != pt ? 1 : 2);
+            side[m] = sd; rowid[2 + m] = sd == 0 ? nh : (sd == 1 ? nt : ph);
+        }
+        for (int m = 0; m < kr; m++) { const i32 nr = a.br[b + (1 + k + m) * a.B]; relid[1 + m] = nr != pr ? nr : -1; }
+    }
+    __syncthreads();
+    for (int i = tid; i < per * De; i += TG_THREADS) A[i] = a.m.ent[(i64)rowid[i / De] * De + i % De];
+    for (int i = tid; i < per * Dr; i += TG_THREADS) G[i] = 0.f;
+    for (int i = tid; i < kr * 2 * Dr; i += TG_THREADS) { P2[i] = 0.f; G2[i] = 0.f; }
+    for (int i = tid; i < NR * Dr; i += TG_THREADS) gr[i] = 0.f;
+    for (int i = tid; i < 2 * De; i += TG_THREADS) dHT[i] = 0.f;
+    __syncthreads();
+    // ---- projections: P[row] = A[row] . M_pr ; P2[m][0/1] = h / t . M_r'   (sequential over the input dimension)
+    for (int o = tid; o < (per + 2 * kr) * Dr; o += TG_THREADS) {
+        const int row = o / Dr, kk = o - row * Dr;
+        const float *src; const float *M;
+        if (row < per) { src = A + row * De; M = a.m.rel_aux + (i64)pr * De * Dr; }
+        else { const int m = (row - per) >> 1; if (relid[1 + m] < 0) continue; src = A + ((row - per) & 1) * De; M = a.m.rel_aux + (i64)relid[1 + m] * De * Dr; }
+        float acc = 0.f;
+        for (int i = 0; i < De; i++) acc += src[i] * __ldg(M + (i64)i * Dr + kk);
+        if (row < per) P[row * Dr + kk] = acc; else P2[(row - per) * Dr + kk] = acc;
+    }
+    __syncthreads();
+    // ---- l2-normalise every projected row and every r_hat (one warp per vector)
+    for (int v = warp; v < per + 2 * kr + NR; v += TG_THREADS / 32) {
+        const bool is_rel = v >= per + 2 * kr;
+        const int ri = v - (per + 2 * kr);
+        if (is_rel ? relid[ri] < 0 : (v >= per && relid[1 + ((v - per) >> 1)] < 0)) continue;
+        float *vec = is_rel ? rh + ri * Dr : (v < per ? P + v * Dr : P2 + (v - per) * Dr);
+        float ss = 0.f;
+        for (int kk = lane; kk < Dr; kk += 32) { const float x = is_rel ? a.m.rel[(i64)relid[ri] * Dr + kk] : vec[kk]; ss += x * x; }
+        ss = wsum_t(ss);
+        const float iv = rsqrtf(fmaxf(ss, EPS_NORM));
+        for (int kk = lane; kk < Dr; kk += 32) vec[kk] = (is_rel ? a.m.rel[(i64)relid[ri] * Dr + kk] : vec[kk]) * iv;
+        if (lane == 0) { if (is_rel) { rinv[ri] = iv; rproj[ri] = ss > EPS_NORM; } else { inv[v] = iv; proj[v] = ss > EPS_NORM; } }
+    }
+    __syncthreads();
+    // ---- scores, hinge, gradients w.r.t. the normalised rows and the r_hats: warp 0
+    if (warp == 0) {
+        const float *Ph = P, *Pt = P + Dr;
+        float sp = 0.f;
+        for (int kk = lane; kk < Dr; kk += 32) sp += fabsf((Ph[kk] + rh[kk]) - Pt[kk]);
+        sp = wsum_t(sp);
+        // adds coef * d score(H, T, r_hat) to the gradient rows gH, gT, gR (score = sum |H + r_hat - T|, rows normalised)
+        auto backward = [&](const float *H, const float *T, const float *R, int hi, int ti, float coef, float *gH, float *gT, float *gR) {
+            float d1 = 0.f, d2 = 0.f;
+            for (int kk = lane; kk < Dr; kk += 32) {
+                const float u = (H[kk] + R[kk]) - T[kk], g = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+                d1 += g * H[kk]; d2 += g * T[kk];
+            }
+            d1 = wsum_t(d1); d2 = wsum_t(d2);
+            if (!proj[hi]) d1 = 0.f;
+            if (!proj[ti]) d2 = 0.f;
+            const float ih = inv[hi] * coef, it = inv[ti] * coef;
+            for (int kk = lane; kk < Dr; kk += 32) {
+                const float u = (H[kk] + R[kk]) - T[kk], g = u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f);
+                gH[kk] += ih * (g - H[kk] * d1);
+                gT[kk] -= it * (g - T[kk] * d2);
+                gR[kk] += coef * g;
+            }
+        };
+        float hinge = 0.f;
+        int active = 0;
+        for (int m = 0; m < k; m++) {                      // entity negatives: the positive's matrix and r_hat
+            const int sd = side[m], nrow = 2 + m;
+            if (sd == 2) { hinge += a.margin; continue; }  // same triple: the term is the margin, its gradient is zero
+            const float *H = sd == 0 ? P + nrow * Dr : Ph, *T = sd == 1 ? P + nrow * Dr : Pt;
+            float sn = 0.f;
+            for (int kk = lane; kk < Dr; kk += 32) sn += fabsf((H[kk] + rh[kk]) - T[kk]);
+            sn = wsum_t(sn);
+            const float x = sp - sn + a.margin;
+            if (x >= 0.f) {
+                hinge += x; active++;
+                backward(H, T, rh, sd == 0 ? nrow : 0, sd == 1 ? nrow : 1, -a.w, sd == 0 ? G + nrow * Dr : G, sd == 1 ? G + nrow * Dr : G + Dr, gr);
+            }
+        }
+        for (int m = 0; m < kr; m++) {                     // relation negatives: their own matrix and r_hat
+            if (relid[1 + m] < 0) { hinge += a.margin; continue; }
+            const float *H = P2 + (2 * m) * Dr, *T = P2 + (2 * m + 1) * Dr, *R = rh + (1 + m) * Dr;
+            float sn = 0.f;
+            for (int kk = lane; kk < Dr; kk += 32) sn += fabsf((H[kk] + R[kk]) - T[kk]);
+            sn = wsum_t(sn);
+            const float x = sp - sn + a.margin;
+            if (x >= 0.f) {
+                hinge += x; active++;
+                backward(H, T, R, per + 2 * m, per + 2 * m + 1, -a.w, G2 + (2 * m) * Dr, G2 + (2 * m + 1) * Dr, gr + (1 + m) * Dr);
+            }
+        }
+        if (active) backward(Ph, Pt, rh, 0, 1, a.w * (float)active, G, G + Dr, gr);
+        if (lane == 0) a.loss_terms[b] = hinge;
+    }
+    __syncthreads();
+    // ---- entity gradient rows: dA = G . M^T; the relation negatives' share of d h, d t goes into the positive's rows
+    for (int o = tid; o < per * De; o += TG_THREADS) {
+        const int row = o / De, i = o - row * De;
+        const float *M = a.m.rel_aux + ((i64)pr * De + i) * Dr;
+        float acc = 0.f;
+        for (int kk = 0; kk < Dr; kk++) acc += G[row * Dr + kk] * __ldg(M + kk);
+        if (row < 2)
+            for (int m = 0; m < kr; m++) {
+                if (relid[1 + m] < 0) continue;
+                const float *M2 = a.m.rel_aux + ((i64)relid[1 + m] * De + i) * Dr;
+                float a2 = 0.f;
+                for (int kk = 0; kk < Dr; kk++) a2 += G2[(2 * m + row) * Dr + kk] * __ldg(M2 + kk);
+                acc += a2;
+            }
+        a.gent[((i64)b * a.NE + row) * De + i] = acc;
+    }
+    // ---- relation gradient rows [d rel (Dr) | d M (De x Dr)], one per (positive, relation slot); unused slots are not read
+    const i64 cols = (i64)Dr + (i64)De * Dr;
+    for (int j = 0; j < NR; j++) {
+        if (relid[j] < 0) continue;
+        float *out = a.grel + ((i64)b * NR + j) * cols;
+        const float *R = rh + j * Dr, *gR = gr + j * Dr;
+        float d = 0.f;                                     // every thread: dot(gR, R) in index order (same bits everywhere)
+        for (int kk = 0; kk < Dr; kk++) d += gR[kk] * R[kk];
+        for (int kk = tid; kk < Dr; kk += TG_THREADS) out[kk] = rinv[j] * (gR[kk] - (rproj[j] ? R[kk] * d : 0.f));
+        for (int o = tid; o < De * Dr; o += TG_THREADS) {
+            const int i = o / Dr, kk = o - i * Dr;
+            float acc = 0.f;
+            if (j == 0) for (int row = 0; row < per; row++) acc += A[row * De + i] * G[row * Dr + kk];
+            else acc = A[i] * G2[(2 * (j - 1)) * Dr + kk] + A[De + i] * G2[(2 * (j - 1) + 1) * Dr + kk];
+            out[Dr + o] = acc;
+        }
+    }
+}
+
 // rel_embeddings and transfer_matrix rows: gradients arrive already reduced per relation.
 //   SGD : touched relations only, x -= lr g.      Adam: every relation (TF1 dense decay), g = 0 if untouched.
 struct TrUpdArgs {
@@ -635,6 +797,10 @@ struct TrUpdArgs {
     const float *grel;
     const unsigned *bad;       // "bad id" flag of the host-batch path: set -> leave the tables alone
     i32 E, R, adam, r_lo;
+    // general form (rel_neg_rate > 0): grel holds one row per (positive, relation slot); a relation's gradient is the sum of
+    // its segment's rows in slot order (perm: slot of each sorted position, nes: first relation slot)
+    const i32 *perm;
+    i32 general, nes;
 };
 __global__ void __launch_bounds__(256) transr_rel_update_kernel(TrUpdArgs a) {
     const i32 r = a.r_lo + (i32)blockIdx.x;
@@ -649,7 +815,15 @@ __global__ void __launch_bounds__(256) transr_rel_update_kernel(TrUpdArgs a) {
         const bool is_rel = e < Dr;
         const i64 off = is_rel ? (i64)r * Dr + e : (i64)r * De * Dr + (e - Dr);
         float *x = (is_rel ? a.m.rel : a.m.rel_aux) + off;
-        const float4 g = touched ? __ldg(g4 + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (touched && !a.general) g = __ldg(g4 + v);
+        else if (touched) {
+            const int4 seg = a.rowhead[a.E + r];
+            for (i32 j = seg.x; j < seg.y; j++) {
+                const float4 y = __ldg(reinterpret_cast<const float4 *>(a.grel + (i64)(__ldg(a.perm + j) - a.nes) * cols) + v);
+                g.x += y.x; g.y += y.y; g.z += y.z; g.w += y.w;
+            }
+        }
         float4 xv = *reinterpret_cast<float4 *>(x);
         const float gs[4] = {g.x, g.y, g.z, g.w};
         float *xs = reinterpret_cast<float *>(&xv);
@@ -674,8 +848,8 @@ int okb_transr_check(okb_ctx *c, const okb_model *m) {
     if (m->ent_dim % 4 || m->rel_dim % 4 || m->ent_dim > 128 || m->rel_dim > 128)
         OKB_FAIL(c, OKB_ERR_ARG, "TransR training needs ent_size, rel_size multiples of 4 and <= 128");
     if ((m->ent_dim / 4) * (m->rel_dim / 4) > TR_MAXT * TR_THREADS) OKB_FAIL(c, OKB_ERR_ARG, "TransR matrix too large");
-    if (c->KR != 0) OKB_FAIL(c, OKB_ERR_ARG, "TransR training with rel_neg_rate > 0 is not supported yet");
-    if (2 + c->K > TR_ROWS) OKB_FAIL(c, OKB_ERR_ARG, "TransR training: ent_neg_rate too large for the chunk size");
+    if (c->KR == 0 && 2 + c->K > TR_ROWS) OKB_FAIL(c, OKB_ERR_ARG, "TransR training: ent_neg_rate too large for the chunk size");
+    if (c->KR != 0 && (c->tr_hi > c->tr_lo)) OKB_FAIL(c, OKB_ERR_ARG, "TransR with rel_neg_rate > 0 cannot be relation-sharded (a relation negative belongs to two shards)");
     return 0;
 }
 
@@ -685,18 +859,33 @@ int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, 
     int rc = okb_transr_check(c, m);
     if (rc) return rc;
     if (b_lo != 0 || b_hi != c->B) OKB_FAIL(c, OKB_ERR_ARG, "TransR gradients are reduced per relation: shard the RELATIONS (okb_transr_set_shard), not the positives");
-    const i64 S = c->B * (1 + c->K);
+    const i64 S = c->B * (1 + c->K + c->KR);
     TrArgs a;
     a.m = *m; a.bh = batch; a.bt = batch + S; a.br = batch + 2 * S;
     a.skeys = skeys; a.perm = perm; a.rowhead = rowhead;
     a.gent = gent; a.grel = grel; a.loss_terms = loss_terms;
-    a.margin = hp->margin; a.w = 1.0f / (float)(c->B * c->K);
+    a.margin = hp->margin; a.w = 1.0f / (float)(c->B * (c->K + c->KR));
     a.B = (i32)c->B; a.k = (i32)c->K; a.NE = (i32)(2 + c->K); a.E = (i32)c->E; a.R = (i32)c->R; a.n = (i32)n;
     a.nes = (i32)c->plan_ne; a.b_lo = (i32)b_lo; a.b_hi = (i32)b_hi;
     a.CH = (i32)(TR_ROWS / (2 + c->K));
     const i64 r_lo = c->tr_hi > c->tr_lo ? c->tr_lo : 0, r_hi = c->tr_hi > c->tr_lo ? c->tr_hi : c->R;
     a.r_lo = (i32)r_lo;
     const int De = m->ent_dim, Dr = m->rel_dim;
+    if (c->KR > 0) {                                       // relation negatives: the general form, one CTA per positive
+        const i64 per = 2 + c->K, kr = c->KR, NR = 1 + kr;
+        const size_t gsmem = sizeof(float) * (size_t)(per * De + 2 * per * Dr + 4 * kr * Dr + 2 * NR * Dr + 2 * De + (per + 2 * kr) + NR) +
+                             sizeof(i32) * (size_t)((per + 2 * kr) + per + c->K + 2 * NR) + 64;
+        if (gsmem > 200 * 1024) OKB_FAIL(c, OKB_ERR_ARG, "TransR with relation negatives: too many negatives for shared memory");
+        OKB_CUDA(c, okb_smem_optin(c, transr_general_kernel, gsmem));
+        c->transr_rel_done = false;
+        {
+            ProfScope ps(c, PROF_GRAD, s);
+            transr_general_kernel<<<(unsigned)c->B, TG_THREADS, gsmem, s>>>(a, (i32)kr);
+        }
+        OKB_LAUNCHED(1);
+        OKB_CUDA(c, cudaGetLastError());
+        return 0;
+    }
     if (c->transr_fused && loss_terms) {
         // persistent form with the relation-side update applied in place (transr_fused_kernel); grel is not used
         const size_t fsmem = sizeof(float) * (2 * (size_t)De * Dr + (size_t)TR_ROWS * De + 2 * (size_t)TR_ROWS * Dr + (size_t)a.CH * Dr + 2 * Dr + TR_ROWS) +
@@ -733,10 +922,12 @@ int okb_transr_launch_grad(okb_ctx *c, const okb_model *m, const okb_hyper *hp, 
 }
 
 int okb_transr_launch_rel_update(okb_ctx *c, const okb_model *m, const okb_hyper *hp, const int4 *rowhead, const float *grel,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, const i32 *perm) {
     if (c->transr_rel_done) { c->transr_rel_done = false; return 0; }      // applied in place by transr_fused_kernel
     TrUpdArgs a;
     a.m = *m; a.hp = *hp; a.rowhead = rowhead; a.grel = grel; a.E = (i32)c->E; a.R = (i32)c->R;
+    a.general = c->KR > 0 ? 1 : 0; a.perm = perm; a.nes = (i32)c->plan_ne;
+    if (a.general && !perm) OKB_FAIL(c, OKB_ERR_STATE, "TransR with relation negatives: the step's plan is missing");
     a.adam = m->optimizer == OKB_ADAM;
     a.bad = c->batch_from_host && c->flags.p ? c->flags.as<unsigned>() + OKB_FLAGS_BAD : nullptr;
     if (a.adam && (!m->m_rel_aux || !m->v_rel_aux)) OKB_FAIL(c, OKB_ERR_ARG, "Adam slots missing");

@@ -195,9 +195,51 @@ def test_transr_train_step_parity(built, small_ds, opt, D, Dr, k):
             assert err.max() <= 2 * 0.01 * 3 + 1e-6, (name, err.max())
 
 
-def test_transr_unsupported_configs_fail_loudly(built, small_ds):
+@pytest.mark.parametrize("opt", ["SGD", "Adam"])
+@pytest.mark.parametrize("D,Dr,k,kr", [(20, 20, 1, 1), (40, 24, 2, 2), (100, 100, 1, 1), (16, 32, 3, 1)])
+def test_transr_relation_negatives_parity(built, small_ds, opt, D, Dr, k, kr):
+    """TransR with rel_neg_rate > 0 (TransR.py:61-65: every negative is projected by ITS relation's matrix): the general
+    kernel (one CTA per positive, a [d rel | d M] gradient row per (positive, relation slot), summed per relation in slot
+    order by the relation update) against the TF-graph restatement, same bars as the default TransR path.  small_ds has 23
+    relations, so negative relations coincide with other positives' relations and long relation segments occur."""
+    import torch
+    from oracle import models_ref
+    con = _config(small_ds, "TransR", D, k, kr, opt, Dr=Dr)
+    P = make_params("TransR", con.entTotal, con.relTotal, D, seed=7, Dr=Dr)
+    con.set_parameters(P)
+    ref32 = models_ref.Trainer("TransR", P, margin=1.0, lr=0.01, opt=opt)
+    ref64 = models_ref.Trainer("TransR", P, margin=1.0, lr=0.01, opt=opt, dtype=torch.float64)
+    B = con.batch_size
+    for it in range(3):
+        con.sampling()
+        h, t, r = con.batch_h.copy(), con.batch_t.copy(), con.batch_r.copy()
+        loss = float(con.train_step_device(0).item())
+        ref32.step(h, t, r, B, k, kr)
+        l64 = ref64.step(h, t, r, B, k, kr)
+        tol = 2e-5 if (opt == "SGD" or it == 0) else 1e-3
+        assert abs(loss - l64) <= tol * abs(l64) + 1e-6, (it, loss, l64)
+        if it == 0 and opt == "Adam":
+            _check_adam_slots(con, ref64)
+    got, exp = con.get_parameters(), ref64.params()
+    for name in exp:
+        delta = np.abs(exp[name] - P[name]).max()
+        err = np.abs(got[name] - exp[name])
+        err32 = np.abs(ref32.params()[name] - exp[name]).max()
+        if opt == "SGD":
+            assert err.max() <= max(4 * err32, 1e-4 * delta + 2e-6), (name, err.max(), err32, delta)
+        else:
+            assert np.median(err) <= 1e-5, (name, np.median(err))
+            assert err.max() <= 2 * 0.01 * 3 + 1e-6, (name, err.max())
+    # the chunked entry point takes the same path
+    l2 = con.train_chunk_device(2, 0)
+    assert np.all(np.isfinite(l2.cpu().numpy()))
+
+
+def test_transr_relation_negatives_cannot_be_relation_sharded(built, small_ds):
+    """A relation negative belongs to two relation shards: refused loudly, not computed wrongly."""
     from openkeonspark_b200 import OkbError
-    con = _config(small_ds, "TransR", 20, 1, 1, "SGD")          # rel_neg_rate > 0
+    con = _config(small_ds, "TransR", 20, 1, 1, "SGD")
+    con.ctx.call("okb_transr_set_shard", 0, 5)
     con.sampling_device()
     with pytest.raises(OkbError):
         con.train_step_device(0)
