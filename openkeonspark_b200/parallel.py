@@ -9,13 +9,19 @@ process per GPU over torch.distributed (NCCL over NVLink):
          computes gradients only for the positives of ITS streams [g*W/G, (g+1)*W/G) (Base.cpp:85-92
          slice geometry).  One all-gather of the gradient rows, then every rank applies the same
          sorted, fixed-order update -> replicas stay bit-identical without a parameter broadcast.
-  train  (owner-sharded, the default on GPUs for TransE/H/D) every rank samples and plans only ITS positives, keeps
-         the full tables in a peer arena the other ranks map over NVLink (CUDA IPC), pushes per-row partial gradient
-         sums into the row owner's staging slab and receives the owner's updated rows — the reduce-scatter and
-         all-gather are plain peer stores inside the update kernels (csrc/train.cu, "data parallel, owner-sharded"),
-         no NCCL call per step.  Replicas stay bit-identical to each other; against the single-GPU order the sums
-         differ by fp32 re-association ((a+b)+(c+d)), so that mode is checked to a tolerance and `mode="exact"`
-         keeps the all-gather path below.
+  train  (owner-sharded, the default on GPUs for TransE/H/D) every rank keeps the full tables in a peer arena the other
+         ranks map over NVLink (CUDA IPC) and OWNS the update of a contiguous range of rows; the reduce-scatter and the
+         all-gather of a synchronous step are plain peer stores inside the step's own kernels (csrc/train.cu, "data
+         parallel, owner-sharded"), no NCCL call per step.  Forms (`form=`):
+           scatter (default up to 4 ranks)  every rank samples + plans the GLOBAL batch; the grad kernel stores each
+                   gradient row straight into its row owner's arena; the owner runs the single-GPU update over its rows
+                   and stores the new rows into every rank's table: two kernels per step, losses / tables / records
+                   bit-identical to ONE GPU training the global batch;
+           push    (default above 4 ranks)  every rank samples + plans only ITS positives and pushes per-row partial
+                   sums into the owner's staging slab; three kernels per step; replicas bit-identical to each other,
+                   against the single-GPU order the sums differ by fp32 re-association ((a+b)+(c+d)): a tolerance;
+           gather / pull  measured-slower alternatives kept for A/B runs.
+         `mode="exact"` keeps the NCCL all-gather path below (CPU / gloo tests).
   eval   candidate entities are split into G contiguous ranges; tables are replicated, so every rank
          computes each query's reference score bit-identically, counts better candidates in its range,
          and the integer counts are all-reduced (sum) / the packed argmins all-reduced (min).
