@@ -23,8 +23,9 @@
 //
 // The grad and update kernels are chained with programmatic dependent launch (griddepcontrol): each one's
 // parameter-independent prologue overlaps the tail of its predecessor.
-// The last section is the owner-sharded data-parallel form of the update over NVLink peer memory
-// (dp_reduce_push_kernel / dp_owner_kernel; dp_pull_kernel as the measured-slower alternative).
+// The last section is the owner-sharded data-parallel form of the step over NVLink peer memory: the scatter form (the grad
+// kernels' SC variant + dp_scatter_update_kernel: two kernels per step, bit-identical to one GPU), the push form
+// (dp_reduce_push_kernel / dp_owner_kernel) and the measured-slower gather / pull alternatives.
 //
 // Roofline: latency-bound gathers and an HBM/L2 stream of fp32 rows; no dense contraction, so no tensor cores
 // here (TransR's projection lives in transr.cu / transr_tc.cu).
@@ -965,7 +966,8 @@ int okb_train_steps(okb_ctx *c, const okb_model *m, const okb_hyper *hp, INT ste
 
 // ------------------------------------------------------------------------------------------ data parallel, owner-sharded
 // One process per GPU inside a box.  Every rank holds the full tables (the gathers of the grad kernel stay local) but
-// OWNS the update of a contiguous range of rows: its Adam slots are only maintained for that range.  A step is
+// OWNS the update of a contiguous range of rows: its Adam slots are only maintained for that range.  In the PUSH form
+// (described first; the scatter form follows further down, see DpSc) a step is
 //
 //   grad         local positives only (this rank's sampler streams)            -> local gradient rows
 //   reduce+push  one warp per table row: fixed-order segment sum of the local gradient rows of that row, stored
