@@ -212,6 +212,19 @@ def owner_rows(n_rows, world):
     return [(min(n_rows, g * per), min(n_rows, (g + 1) * per)) for g in range(world)]
 
 
+def default_form(world, pull=False, form=None):
+    """Form of the owner-sharded step: an explicit `form` wins, then the A/B switches (`pull`, OKB200_DP_FORM), then the
+    measured default by world size — scatter up to 4 ranks, push above (profiles/r02_dp_phase_traces.txt)."""
+    import os
+    if form is None:
+        form = os.environ.get("OKB200_DP_FORM", "scatter" if world <= 4 else "push")
+    if pull:
+        form = "pull"
+    if form not in ("gather", "scatter", "push", "pull"):
+        raise ValueError("form must be 'gather', 'scatter', 'push' or 'pull'")
+    return form
+
+
 class _ArenaView:
     """__cuda_array_interface__ over raw device memory, so torch can wrap a slice of the peer arena."""
 
@@ -235,12 +248,7 @@ class OwnerSharded(DataParallel):
         # "gather": gradient rows go to EVERY rank and every rank runs the full update — one exchange per step, bit-identical
         # to one GPU too, but measured slower even at 2 ranks (61.6 vs 53.8 us per step: the grad kernel's peer stores run at
         # ~350 GB/s, so doubling them costs more than the second exchange); kept as an option
-        default = "scatter" if self.world <= 4 else "push"
-        form = os.environ.get("OKB200_DP_FORM", default) if form is None else form
-        if pull:
-            form = "pull"
-        if form not in ("gather", "scatter", "push", "pull"):
-            raise ValueError("form must be 'gather', 'scatter', 'push' or 'pull'")
+        form = default_form(self.world, pull=pull, form=form)
         self.form = form
         self.prefetch = os.environ.get("OKB200_DP_PREFETCH", "1") == "1" and form != "pull"
         from ._native import okb_dp

@@ -178,3 +178,16 @@ def test_relation_sharded_host_logic_gloo_world2(B, R):
 def test_data_parallel_host_logic_gloo_world2(B, W):
     port = 29500 + (os.getpid() + B) % 2000
     mp.spawn(_worker, args=(2, port, B, W), nprocs=2, join=True)
+
+
+def test_default_form_of_the_owner_sharded_step(monkeypatch):
+    """scatter up to 4 ranks, push above; an explicit form or the A/B switches override; unknown names are refused."""
+    from openkeonspark_b200 import parallel
+    monkeypatch.delenv("OKB200_DP_FORM", raising=False)
+    assert [parallel.default_form(w) for w in (1, 2, 4, 5, 8, 16)] == ["scatter", "scatter", "scatter", "push", "push", "push"]
+    assert parallel.default_form(8, form="scatter") == "scatter" and parallel.default_form(2, form="gather") == "gather"
+    assert parallel.default_form(2, pull=True) == "pull"
+    monkeypatch.setenv("OKB200_DP_FORM", "push")
+    assert parallel.default_form(2) == "push" and parallel.default_form(2, form="scatter") == "scatter"
+    with pytest.raises(ValueError):
+        parallel.default_form(2, form="ring")
