@@ -52,6 +52,16 @@ def test_host_only_calls_work_without_gpu(built, tmp_path):
     c.call("okb_set_in_path", str(tmp_path).encode())
     with pytest.raises(_native.OkbError):          # missing files -> OKB_ERR_IO, not a crash
         c.call("okb_import_train_files")
+    # gradient-buffer geometry (pure host arithmetic): TransR's relation rows are per RELATION without relation negatives
+    # and per (positive, relation slot) with them (TransR.py:57-65); the other models always use the latter
+    m = _native.okb_model()
+    m.ent_dim, m.rel_dim = 20, 12
+    er, ec, rr, rc = (ctypes.c_int64() for _ in range(4))
+    for model, kr, want_rows, want_cols in ((2, 0, 0, 12 + 20 * 12), (2, 2, 100 * 3, 12 + 20 * 12), (1, 2, 100 * 3, 2 * 12), (0, 0, 100, 12)):
+        m.model = model
+        c.call("okb_grad_sizes", ctypes.byref(m), 100, 3, kr, ctypes.byref(er), ctypes.byref(ec), ctypes.byref(rr), ctypes.byref(rc))
+        assert (er.value, ec.value) == (100 * 5, 20), model
+        assert (rr.value, rc.value) == (want_rows, want_cols), (model, kr)      # TransR, kr = 0: R rows = 0 before any import
     c.close()
 
 
